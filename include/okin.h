@@ -1,0 +1,115 @@
+/* C ABI of the B200-native batched suspension-kinematics solver.
+ *
+ * The reference (nickmccleery/open-kinematics, pure Python) has no FFI; its solve-path
+ * seams are the Python functions listed below (paths relative to src/kinematics/core/).
+ * This header is what a ctypes/cffi binding of those seams binds instead:
+ *
+ *   okin_topology_create   <- ResidualComputer.__init__ / build_jac_plan (solver.py:187-214,
+ *                             :281-500) + DerivedPointsManager.__init__ (points/derived/
+ *                             manager.py:95-105): everything computed once per topology.
+ *   okin_solve_batch       <- solve_suspension_sweep (solver.py:654-776), once per instance,
+ *                             plus compute_state_tangents (sensitivity.py:57-143) when
+ *                             tangents_out is given.
+ *   okin_solve_batch_device   same, on buffers already resident in device memory.
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer, every function returns 0 on
+ * success and a negative code on error (message via okin_last_error), no exceptions cross the
+ * boundary.  A topology handle may be used from several threads as long as each thread uses a
+ * different device.  All floating point is IEEE fp64.
+ *
+ * Buffer layouts ("instance-major": one instance's data is contiguous, so a warp that owns an
+ * instance reads and writes coalesced rows and an instance range is one contiguous slab):
+ *   hardpoints      [n_instances][n_in_points*3]     authored positions, slot order = the
+ *                                                    compiled topology's input points
+ *   target_values   [n_targets][n_steps]             sweep values shared by all instances
+ *                                                    (relative displacement or absolute coordinate,
+ *                                                    as declared per target)
+ *   positions_out   [n_instances][n_steps][n_out_points*3]   NaN after a failed step
+ *   iters_out       [n_instances][n_steps]           residual evaluations (SolverInfo.nfev)
+ *   max_residual_out[n_instances][n_steps]           max |r| at the solution (SolverInfo.max_residual)
+ *   tangents_out    [n_instances][n_steps][n_targets][n_unknowns]  dq/dt_j, reference column order
+ *   status_out      [n_instances]                    OKIN_STATUS_*
+ *   failed_step_out [n_instances]                    -1 or the first failed step
+ * Any *_out pointer except status_out / failed_step_out may be NULL.
+ */
+#ifndef OKIN_H
+#define OKIN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OKIN_OK 0
+#define OKIN_ERR_USAGE (-1)
+#define OKIN_ERR_CUDA (-2)
+#define OKIN_ERR_NO_DEVICE (-3)
+
+#define OKIN_STATUS_OK 0
+#define OKIN_STATUS_NOT_CONVERGED 1     /* RuntimeError("Solver failed to converge") solver.py:726-730 */
+#define OKIN_STATUS_RESIDUAL_REJECTED 2 /* RuntimeError("...did not reach an acceptable residual") solver.py:738-747 */
+#define OKIN_STATUS_INVALID_GEOMETRY 3  /* NaN / degenerate design pose */
+
+typedef struct okin_topology okin_topology;
+
+/* Flat program produced by the host topology compiler (open-kinematics_b200/core/topology.py);
+ * layout in open-kinematics_b200/csrc/okin_defs.h. */
+typedef struct okin_topology_desc {
+  const int32_t* hdr;   /* [OKIN_HDR_SIZE] */
+  const int32_t* iblob;
+  int64_t n_iblob;
+  const double* fblob;
+  int64_t n_fblob;
+} okin_topology_desc;
+
+/* Solver controls.  residual_tol mirrors SolverConfig.residual_tolerance (solver.py:80); the
+ * MINPACK ftol/xtol/gtol of the reference have no counterpart: the device solve always runs its
+ * Gauss-Newton iteration to max|dx| <= step_tol. */
+typedef struct okin_solver_cfg {
+  double step_tol;       /* mm; default 1e-9 */
+  double residual_tol;   /* default 1e-3 */
+  double mu_init;        /* first Marquardt damping after a rejected step; default 1e-3 */
+  int32_t max_iter;      /* linear solves per step; default 50 */
+  int32_t use_predictor; /* 1: warm-start each step along the previous tangents */
+} okin_solver_cfg;
+
+typedef struct okin_topology_info {
+  int32_t n_points, n_in_points, n_out_points, n_unknowns, n_targets, n_rows;
+  int32_t smem_bytes_per_instance, n_levels;
+} okin_topology_info;
+
+int okin_device_count(int* out);
+int okin_default_cfg(okin_solver_cfg* out);
+int okin_topology_create(const okin_topology_desc* desc, okin_topology** out);
+int okin_topology_destroy(okin_topology* topo);
+int okin_topology_get_info(const okin_topology* topo, okin_topology_info* out);
+
+/* Host buffers; instance range sharded evenly over device_ids (NULL / 0 => device 0). */
+int okin_solve_batch(okin_topology* topo, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
+                     const double* hardpoints, const double* target_values, const int32_t* device_ids,
+                     int32_t n_devices, double* positions_out, int32_t* status_out, int32_t* failed_step_out,
+                     int32_t* iters_out, double* max_residual_out, double* tangents_out);
+
+/* Device buffers on `device`; enqueues on `stream` (a cudaStream_t, may be NULL) and returns
+ * without synchronising. */
+int okin_solve_batch_device(okin_topology* topo, const okin_solver_cfg* cfg, int32_t device, void* stream,
+                            int64_t n_instances, int32_t n_steps, const double* d_hardpoints,
+                            const double* d_target_values, double* d_positions_out, int32_t* d_status_out,
+                            int32_t* d_failed_step_out, int32_t* d_iters_out, double* d_max_residual_out,
+                            double* d_tangents_out);
+
+/* Launch geometry the library would use for n_instances on `device` (for reporting). */
+int okin_launch_geometry(okin_topology* topo, int32_t device, int64_t n_instances, int32_t* grid, int32_t* block,
+                         int32_t* smem_bytes, int32_t* ctas_per_sm);
+
+/* Dependent-DFMA-chain microbenchmark: measured fp64 FMA peak of `device` in TFLOP/s
+ * (the roofline denominator; MEASURED_PEAKS.json carries no fp64 figure). */
+int okin_fp64_peak(int32_t device, double* tflops_out);
+
+int okin_last_error(char* buf, int32_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OKIN_H */

@@ -1,0 +1,206 @@
+"""ctypes binding of the C ABI in ``include/okin.h`` (library built from ``csrc/``).
+
+There is no fallback: if ``csrc/libokin.so`` is missing or no CUDA device is
+visible, every solve entry point raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libokin.so")
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+class TopologyDesc(ctypes.Structure):
+    _fields_ = [("hdr", c_i32p), ("iblob", c_i32p), ("n_iblob", ctypes.c_int64),
+                ("fblob", c_f64p), ("n_fblob", ctypes.c_int64)]
+
+
+class SolverCfg(ctypes.Structure):
+    _fields_ = [("step_tol", ctypes.c_double), ("residual_tol", ctypes.c_double), ("mu_init", ctypes.c_double),
+                ("max_iter", ctypes.c_int32), ("use_predictor", ctypes.c_int32)]
+
+
+class TopologyInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "n_points", "n_in_points", "n_out_points", "n_unknowns", "n_targets", "n_rows",
+        "smem_bytes_per_instance", "n_levels")]
+
+
+# name -> (restype, argtypes); also the list the "exports every declared symbol" test checks.
+SIGNATURES = {
+    "okin_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "okin_default_cfg": (ctypes.c_int, [ctypes.POINTER(SolverCfg)]),
+    "okin_topology_create": (ctypes.c_int, [ctypes.POINTER(TopologyDesc), ctypes.POINTER(ctypes.c_void_p)]),
+    "okin_topology_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "okin_topology_get_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(TopologyInfo)]),
+    "okin_solve_batch": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int64, ctypes.c_int32,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "okin_solve_batch_device": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p]),
+    "okin_launch_geometry": (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_i32p]),
+    "okin_fp64_peak": (ctypes.c_int, [ctypes.c_int32, c_f64p]),
+    "okin_last_error": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile ``csrc/okin_abi.cu`` for sm_100a into ``csrc/libokin.so`` (in-tree)."""
+    sources = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    sources.append(os.path.join(_HERE, "..", "include", "okin.h"))
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in sources):
+            return LIB_PATH
+    cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB_PATH, os.path.join(CSRC, "okin_abi.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{proc.stdout}\n{proc.stderr}")
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} not found: build the CUDA extension first "
+                    "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback."
+                )
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (restype, argtypes) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = restype
+                fn.argtypes = argtypes
+            _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    buf = ctypes.create_string_buffer(1024)
+    load().okin_last_error(buf, len(buf))
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    rc = load().okin_device_count(ctypes.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def require_device() -> None:
+    if device_count() < 1:
+        raise RuntimeError("No CUDA device visible: the solver has no CPU fallback (" + last_error() + ")")
+
+
+def default_cfg(**overrides) -> SolverCfg:
+    cfg = SolverCfg()
+    check(load().okin_default_cfg(ctypes.byref(cfg)), "okin_default_cfg")
+    for key, value in overrides.items():
+        if value is not None:
+            setattr(cfg, key, value)
+    return cfg
+
+
+class DeviceTopology:
+    """Owns an ``okin_topology*`` created from a compiled ``TopologyProgram``."""
+
+    def __init__(self, program):
+        self.program = program
+        self._hdr = np.ascontiguousarray(program.hdr, dtype=np.int32)
+        self._ib = np.ascontiguousarray(program.iblob, dtype=np.int32)
+        self._fb = np.ascontiguousarray(program.fblob, dtype=np.float64)
+        desc = TopologyDesc(
+            self._hdr.ctypes.data_as(c_i32p), self._ib.ctypes.data_as(c_i32p), self._ib.size,
+            self._fb.ctypes.data_as(c_f64p), self._fb.size,
+        )
+        self.handle = ctypes.c_void_p()
+        check(load().okin_topology_create(ctypes.byref(desc), ctypes.byref(self.handle)), "okin_topology_create")
+
+    def info(self) -> TopologyInfo:
+        out = TopologyInfo()
+        check(load().okin_topology_get_info(self.handle, ctypes.byref(out)), "okin_topology_get_info")
+        return out
+
+    def launch_geometry(self, n_instances: int, device: int = 0) -> dict:
+        vals = [ctypes.c_int32() for _ in range(4)]
+        check(load().okin_launch_geometry(self.handle, device, n_instances, *[ctypes.byref(v) for v in vals]),
+              "okin_launch_geometry")
+        return dict(zip(("grid", "block", "smem_bytes", "ctas_per_sm"), (v.value for v in vals)))
+
+    def close(self) -> None:
+        if self.handle:
+            load().okin_topology_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    # -- host buffers ------------------------------------------------------------------
+    def solve_batch(self, hardpoints: np.ndarray, target_values: np.ndarray, cfg: SolverCfg | None = None,
+                    devices=None, want_positions=True, want_tangents=False) -> dict:
+        """hardpoints [n_inst, n_in*3]; target_values [n_targets, n_steps]."""
+        require_device()
+        prog = self.program
+        hp = np.ascontiguousarray(hardpoints, dtype=np.float64)
+        if hp.ndim != 2 or hp.shape[1] != 3 * prog.n_in:
+            raise ValueError(f"hardpoints must have shape (n_instances, {3 * prog.n_in}), got {hp.shape}")
+        tv = np.ascontiguousarray(target_values, dtype=np.float64)
+        nt = len(prog.target_points)
+        if tv.ndim != 2 or tv.shape[0] != nt:
+            raise ValueError(f"target_values must have shape ({nt}, n_steps), got {tv.shape}")
+        n_inst, n_steps = hp.shape[0], tv.shape[1]
+        cfg = cfg or default_cfg()
+        out = {
+            "positions": np.empty((n_inst, n_steps, prog.n_out, 3)) if want_positions else None,
+            "status": np.empty(n_inst, np.int32),
+            "failed_step": np.empty(n_inst, np.int32),
+            "iters": np.empty((n_inst, n_steps), np.int32),
+            "max_residual": np.empty((n_inst, n_steps)),
+            "tangents": np.empty((n_inst, n_steps, nt, prog.n_unknowns)) if want_tangents else None,
+        }
+        dev = np.ascontiguousarray(devices if devices is not None else [0], dtype=np.int32)
+
+        def p(a):
+            return None if a is None else a.ctypes.data
+
+        check(load().okin_solve_batch(
+            self.handle, ctypes.byref(cfg), n_inst, n_steps, p(hp), p(tv), p(dev), dev.size,
+            p(out["positions"]), p(out["status"]), p(out["failed_step"]), p(out["iters"]),
+            p(out["max_residual"]), p(out["tangents"])), "okin_solve_batch")
+        return out

@@ -1,0 +1,601 @@
+"""Topology compiler: suspension model -> flat device program.
+
+Runs once per topology on the host (never per instance).  It lowers
+
+* the point table (fixed / free / derived, reference ``core/state.py:50`` column order),
+* the derived-point DAG (reference ``core/points/derived/manager.py:146-197``),
+* the constraint list plus sweep targets into least-squares rows with the
+  point-on-line rows replaced by two linear pins (reference
+  ``core/sensitivity.py:146-174``),
+* the gather lists that assemble the normal equations ``A = J^T J``, ``g = J^T r``
+  from per-row gradients, and
+* a symbolic 3x3-block sparse Cholesky of ``A`` (fill-reducing order, elimination
+  tree levels, left-looking update lists, triangular-solve lists)
+
+into the int32/double blobs described in ``csrc/okin_defs.h``.  The CUDA kernel
+(``csrc/okin_core.cuh``) is an interpreter of that program, so one kernel serves
+every topology the host can describe.
+"""
+
+from __future__ import annotations
+
+import os
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .constraints import (
+    AngleConstraint, Constraint, CoplanarPointsConstraint, DistanceConstraint, EqualDistanceConstraint,
+    FixedAxisConstraint, MidpointOnPlaneConstraint, PointOnLineConstraint, PointOnPlaneConstraint,
+    ScalarTripleProductConstraint, SphericalJointConstraint, ThreePointAngleConstraint,
+    VectorsParallelConstraint, VectorsPerpendicularConstraint,
+)
+from .enums import TargetPositionMode
+from .points.derived.manager import DerivedPointsManager, DerivedPointsSpec
+from .targeting import PointTarget, resolve_target
+
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
+
+
+def _parse_defs() -> dict:
+    """Read the integer constants of csrc/okin_defs.h (single source of truth)."""
+    text = open(os.path.join(_CSRC, "okin_defs.h"), encoding="utf-8").read()
+    text = re.sub(r"//[^\n]*", "", text)
+    out: dict = {}
+    for name, value in re.findall(r"#define\s+(OKIN_\w+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\s*$", text, re.M):
+        out[name] = int(value, 0)
+    for body in re.findall(r"enum\s+\w+\s*\{([^}]*)\}", text):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                name, expr = (s.strip() for s in item.split("=", 1))
+                nxt = int(eval(expr, {}, dict(out)))  # noqa: S307 - arithmetic on parsed constants
+            else:
+                name = item
+            out[name] = nxt
+            nxt += 1
+    return out
+
+
+D = _parse_defs()
+
+FAMILY_CODE = {
+    "distance": D["OKIN_FAM_DISTANCE"], "spherical": D["OKIN_FAM_SPHERICAL"], "angle": D["OKIN_FAM_ANGLE"],
+    "three_point_angle": D["OKIN_FAM_THREE_POINT_ANGLE"], "vectors_parallel": D["OKIN_FAM_VECTORS_PARALLEL"],
+    "vectors_perpendicular": D["OKIN_FAM_VECTORS_PERPENDICULAR"], "equal_distance": D["OKIN_FAM_EQUAL_DISTANCE"],
+    "point_on_line": D["OKIN_FAM_POINT_ON_LINE"], "linear_point": D["OKIN_FAM_LINEAR_POINT"],
+    "midpoint_on_plane": D["OKIN_FAM_MIDPOINT_ON_PLANE"], "coplanar": D["OKIN_FAM_COPLANAR"],
+    "scalar_triple": D["OKIN_FAM_SCALAR_TRIPLE"], "target": D["OKIN_FAM_TARGET"],
+}
+_DOP_CODE = {"midpoint": D["OKIN_DOP_MIDPOINT"], "along_line": D["OKIN_DOP_ALONG_LINE"],
+             "contact_patch": D["OKIN_DOP_CONTACT_PATCH"]}
+
+
+def pin_normals(direction: np.ndarray) -> tuple:
+    """Two unit normals spanning the plane perpendicular to a line direction
+    (reference core/sensitivity.py:159-173)."""
+    d = np.asarray(direction, dtype=np.float64)
+    d = d / np.linalg.norm(d)
+    least = np.zeros(3)
+    least[int(np.argmin(np.abs(d)))] = 1.0
+    n1 = np.cross(d, least)
+    n1 /= np.linalg.norm(n1)
+    return n1, np.cross(d, n1)
+
+
+@dataclass
+class _Row:
+    fam: int
+    points: list            # point indices (len <= 4)
+    consts: list            # default constants (floats)
+    rule: int
+    source: tuple           # ("constraint", index) | ("pin", index, k) | ("target", index) | ("report", index)
+    aux: int = 0
+    eff: list = field(default_factory=list)        # effective free blocks (reference column block ids)
+    slotmap: list = field(default_factory=list)
+    cst_off: int = 0
+    rg_off: int = 0
+
+
+@dataclass
+class TopologyProgram:
+    hdr: np.ndarray
+    iblob: np.ndarray
+    fblob: np.ndarray
+    point_keys: list          # index -> key
+    free_order: list          # reference column order (sorted free keys)
+    in_keys: list             # input slot -> key
+    out_keys: list            # output slot -> key
+    n_constraints: int
+    row_source: list          # LS rows then report rows
+    target_points: list
+    stats: dict
+
+    @property
+    def n_unknowns(self) -> int:
+        return 3 * len(self.free_order)
+
+    @property
+    def n_in(self) -> int:
+        return len(self.in_keys)
+
+    @property
+    def n_out(self) -> int:
+        return len(self.out_keys)
+
+    def section(self, name: str) -> np.ndarray:
+        s = D[name]
+        off, n = self.hdr[D["OKIN_H_SEC0"] + 2 * s], self.hdr[D["OKIN_H_SEC0"] + 2 * s + 1]
+        return self.iblob[off: off + n]
+
+    def fsection(self, name: str) -> np.ndarray:
+        s = D[name]
+        off, n = self.hdr[D["OKIN_H_FSEC0"] + 2 * s], self.hdr[D["OKIN_H_FSEC0"] + 2 * s + 1]
+        return self.fblob[off: off + n]
+
+
+# ---------------------------------------------------------------------------
+def _constraint_rows(index: int, c: Constraint, pidx: dict, design_rules: bool) -> list:
+    """Lower one constraint declaration to least-squares / report rows."""
+    RULE_X, RULE_V, RULE_P = D["OKIN_RULE_EXPLICIT"], D["OKIN_RULE_DESIGN_VALUE"], D["OKIN_RULE_DESIGN_POINT"]
+    pts = [pidx[k] for k in c.point_keys]
+    src = ("constraint", index)
+    rule_v = RULE_V if design_rules else RULE_X
+    if isinstance(c, DistanceConstraint):
+        return [_Row(FAMILY_CODE["distance"], pts, [c.target_distance], rule_v, src)]
+    if isinstance(c, SphericalJointConstraint):
+        return [_Row(FAMILY_CODE["spherical"], pts, [], RULE_X, src)]
+    if isinstance(c, AngleConstraint):
+        return [_Row(FAMILY_CODE["angle"], pts, [c.target_angle], rule_v, src)]
+    if isinstance(c, ThreePointAngleConstraint):
+        return [_Row(FAMILY_CODE["three_point_angle"], pts, [c.target_angle], RULE_X, src)]
+    if isinstance(c, VectorsParallelConstraint):
+        return [_Row(FAMILY_CODE["vectors_parallel"], pts, [], RULE_X, src)]
+    if isinstance(c, VectorsPerpendicularConstraint):
+        return [_Row(FAMILY_CODE["vectors_perpendicular"], pts, [], RULE_X, src)]
+    if isinstance(c, EqualDistanceConstraint):
+        return [_Row(FAMILY_CODE["equal_distance"], pts, [], RULE_X, src)]
+    if isinstance(c, ScalarTripleProductConstraint):
+        return [_Row(FAMILY_CODE["scalar_triple"], pts, [c.target_volume, 1.0 / c.scale], rule_v, src)]
+    if isinstance(c, CoplanarPointsConstraint):
+        return [_Row(FAMILY_CODE["coplanar"], pts, [], RULE_X, src)]
+    if isinstance(c, FixedAxisConstraint):
+        n = np.zeros(3)
+        n[int(c.axis)] = 1.0
+        return [_Row(FAMILY_CODE["linear_point"], pts, [*(n * c.value), *n], RULE_X, src)]
+    if isinstance(c, PointOnPlaneConstraint):
+        return [_Row(FAMILY_CODE["linear_point"], pts, [*c.plane_point.data, *c.plane_normal.data], RULE_X, src)]
+    if isinstance(c, MidpointOnPlaneConstraint):
+        return [_Row(FAMILY_CODE["midpoint_on_plane"], pts, [*c.plane_point.data, *c.plane_normal.data], RULE_X, src)]
+    if isinstance(c, PointOnLineConstraint):
+        # One scalar row cannot express a 2-DOF restriction and its gradient vanishes on
+        # the line; the solve uses two linear pins, the original residual is kept as a
+        # report row for max|r| (reference solver.py:735-747).
+        d = c.line_direction.data
+        n1, n2 = pin_normals(d)
+        rule_p = RULE_P if design_rules else RULE_X
+        p0 = list(c.line_point.data)
+        return [
+            _Row(FAMILY_CODE["linear_point"], pts, [*p0, *n1], rule_p, ("pin", index, 0)),
+            _Row(FAMILY_CODE["linear_point"], pts, [*p0, *n2], rule_p, ("pin", index, 1)),
+            _Row(FAMILY_CODE["point_on_line"], pts, [*p0, *d], rule_p, ("report", index)),
+        ]
+    raise TypeError(f"No device lowering for {type(c).__name__}")
+
+
+def _min_degree(nf: int, adjacency: list) -> tuple:
+    """Greedy minimum-degree ordering with symbolic elimination.  Returns
+    (order, struct) where struct[v] is the set of later-eliminated neighbours of v."""
+    adj = [set(a) for a in adjacency]
+    alive = set(range(nf))
+    order, struct = [], {}
+    while alive:
+        v = min(alive, key=lambda u: (len(adj[u]), u))
+        nbrs = set(adj[v])
+        struct[v] = nbrs
+        order.append(v)
+        alive.discard(v)
+        for u in nbrs:
+            adj[u] |= nbrs - {u}
+            adj[u].discard(v)
+    return order, struct
+
+
+def compile_topology(
+    initial_state,
+    constraints: list,
+    derived_spec: DerivedPointsSpec,
+    targets: list,
+    output_points=None,
+    design_rules: bool = True,
+) -> TopologyProgram:
+    """Compile one topology.
+
+    ``targets``: one ``PointTarget`` per sweep dimension (value ignored; point,
+    direction and mode define the row).  ``design_rules=True`` makes the device
+    recompute every design constant from each instance's own hardpoints (batch
+    use); ``False`` bakes the explicit constants of the given constraint objects
+    (the single-instance ``solve_suspension_sweep`` boundary).
+    """
+    positions = initial_state.positions
+    manager = DerivedPointsManager(derived_spec)
+    derived_keys = list(manager.update_order)
+    free_order = list(initial_state.free_points_order)
+    if set(free_order) & set(derived_keys):
+        raise ValueError("A point cannot be both free and derived")
+
+    point_keys = sorted(positions.keys())
+    pidx = {k: i for i, k in enumerate(point_keys)}
+    P, NF = len(point_keys), len(free_order)
+    col_of = {k: i for i, k in enumerate(free_order)}      # reference column block
+    kind = np.zeros(P, np.int32)
+    for k in free_order:
+        kind[pidx[k]] = D["OKIN_PT_FREE"]
+    for k in derived_keys:
+        kind[pidx[k]] = D["OKIN_PT_DERIVED"]
+
+    n_res = len(constraints) + len(targets)
+    if 3 * NF > n_res:
+        raise ValueError(
+            f"System is underdetermined (n_vars={3 * NF} > m_res={n_res}). The solve method "
+            "(Levenberg-Marquardt) requires at least as many residuals as variables."
+        )
+
+    # ---- derived ops -----------------------------------------------------
+    in_keys = [k for k in point_keys if k not in derived_spec.functions]
+    dops, par_mode, par_val = [], [], []
+    dop_of = {}
+    for key in derived_keys:
+        fn = derived_spec.functions[key]
+        if fn.OP not in _DOP_CODE:
+            raise TypeError(f"Derived point {key!r}: op {fn.OP!r} cannot be compiled for the device")
+        ins = [pidx[k] for k in fn.inputs] + [-1] * (3 - len(fn.inputs))
+        authored = -1
+        if fn.design_projection is not None and design_rules:
+            if fn.design_projection not in in_keys:
+                in_keys.append(fn.design_projection)
+            par_mode.append(D["OKIN_PAR_DESIGN_PROJECTION"])
+        else:
+            par_mode.append(D["OKIN_PAR_SHARED"])
+        par_val.append(float(fn.param))
+        dop_of[key] = len(dops)
+        dops.append([_DOP_CODE[fn.OP], pidx[key], ins[0], ins[1], ins[2], len(par_val) - 1, authored, 0])
+    in_keys = sorted(in_keys)
+    in_slot = {k: i for i, k in enumerate(in_keys)}
+    for key in derived_keys:
+        fn = derived_spec.functions[key]
+        if fn.design_projection is not None and design_rules:
+            dops[dop_of[key]][6] = in_slot[fn.design_projection]
+
+    def base_deps(key) -> list:
+        """Free points a derived point depends on (transitively), in column order."""
+        seen, stack, out = set(), [key], set()
+        while stack:
+            k = stack.pop()
+            if k in seen:
+                continue
+            seen.add(k)
+            if k in derived_spec.functions:
+                stack.extend(derived_spec.dependencies[k])
+            elif k in col_of:
+                out.add(k)
+        return sorted(out, key=lambda k: col_of[k])
+
+    def chain_of(key) -> list:
+        """Derived ops needed to evaluate ``key``, in evaluation order."""
+        need, stack = set(), [key]
+        while stack:
+            k = stack.pop()
+            if k in derived_spec.functions and k not in need:
+                need.add(k)
+                stack.extend(derived_spec.dependencies[k])
+        return [dop_of[k] for k in derived_keys if k in need]
+
+    # ---- rows --------------------------------------------------------------
+    ls_rows, report_rows = [], []
+    for ci, c in enumerate(constraints):
+        for row in _constraint_rows(ci, c, pidx, design_rules):
+            (report_rows if row.source[0] == "report" else ls_rows).append(row)
+    trow0 = len(ls_rows)
+    if len(targets) > D["OKIN_MAX_TARGETS"]:
+        raise ValueError(f"At most {D['OKIN_MAX_TARGETS']} simultaneous sweep targets are supported")
+    for ti, t in enumerate(targets):
+        if t.point_id not in pidx:
+            raise ValueError(f"Sweep target point {t.point_id!r} is not part of the model")
+        direction = resolve_target(t.direction).data
+        relative = TargetPositionMode(t.mode) == TargetPositionMode.RELATIVE
+        base = float(np.dot(positions[t.point_id].data, direction)) if relative else 0.0
+        rule = D["OKIN_RULE_TARGET_BASE"] if (relative and design_rules) else D["OKIN_RULE_EXPLICIT"]
+        ls_rows.append(_Row(FAMILY_CODE["target"], [pidx[t.point_id]], [*direction, base], rule, ("target", ti), aux=ti))
+    rows = ls_rows + report_rows
+    NROW, NREP = len(ls_rows), len(report_rows)
+
+    # effective free blocks + slot maps + derived Jacobian storage
+    der_desc, der_index = [], {}
+    dblk_off, adj_tasks, adj_chain = {}, [], []
+    ndb = 0
+    ncst = nrg = 0
+    for row in rows:
+        eff: list = []
+        per_slot = []
+        for p in row.points:
+            key = point_keys[p]
+            if key in col_of:
+                per_slot.append(("free", [key]))
+            elif key in derived_spec.functions:
+                per_slot.append(("derived", base_deps(key)))
+            else:
+                per_slot.append(("fixed", []))
+            for dep in per_slot[-1][1]:
+                if col_of[dep] not in eff:
+                    eff.append(col_of[dep])
+        row.eff = eff
+        is_ls = row.source[0] != "report"
+        for (what, deps), p in zip(per_slot, row.points):
+            if what == "fixed" or (what == "derived" and not deps) or not is_ls:
+                row.slotmap.append(-1)
+            elif what == "free":
+                row.slotmap.append(eff.index(col_of[deps[0]]))
+            else:
+                key = point_keys[p]
+                if len(deps) > 3:
+                    raise ValueError(f"Derived point {key!r} depends on more than 3 free points")
+                desc = [len(deps)]
+                for dep in deps:
+                    if (key, dep) not in dblk_off:
+                        dblk_off[(key, dep)] = ndb
+                        chain = chain_of(key)
+                        if len(chain) > D["OKIN_MAX_CHAIN"]:
+                            raise ValueError(f"Derived chain of {key!r} is longer than {D['OKIN_MAX_CHAIN']}")
+                        begin = len(adj_chain)
+                        adj_chain.extend(chain)
+                        for op_index in chain:
+                            dops[op_index][7] = 1      # evaluated inside the solve iterations
+                        for comp in range(3):
+                            adj_tasks.append([pidx[key], pidx[dep], comp, ndb, begin, len(adj_chain), 0, 0])
+                        ndb += 9
+                    desc += [dblk_off[(key, dep)], eff.index(col_of[dep])]
+                desc += [0] * (D["OKIN_DER_STRIDE"] - len(desc))
+                tdesc = tuple(desc)
+                if tdesc not in der_index:
+                    der_index[tdesc] = len(der_desc)
+                    der_desc.append(desc)
+                row.slotmap.append(D["OKIN_SLOT_DER"] + der_index[tdesc])
+        row.slotmap += [-1] * (4 - len(row.slotmap))
+        row.cst_off = ncst
+        ncst += len(row.consts)
+        row.rg_off = nrg
+        if is_ls:
+            nrg += 3 * len(eff)
+    if nrg >= 65536:
+        raise ValueError("Row-gradient storage exceeds the 16-bit index range")
+
+    # ---- elimination order and symbolic block Cholesky ----------------------
+    adjacency = [set() for _ in range(NF)]
+    for row in ls_rows:
+        for a in row.eff:
+            for b in row.eff:
+                if a != b:
+                    adjacency[a].add(b)
+    order, struct_by_col = _min_degree(NF, adjacency)
+    pos_of = {v: i for i, v in enumerate(order)}             # column block -> elimination position
+    struct = [sorted(pos_of[u] for u in struct_by_col[order[j]]) for j in range(NF)]
+    parent = [s[0] if s else -1 for s in struct]
+    level = [0] * NF
+    for j in range(NF):
+        if parent[j] >= 0:
+            level[parent[j]] = max(level[parent[j]], level[j] + 1)
+    NLEV = max(level) + 1 if NF else 0
+
+    block_id = {}
+    for j in range(NF):
+        block_id[(j, j)] = len(block_id)
+        for i in struct[j]:
+            block_id[(i, j)] = len(block_id)
+    NB = len(block_id)
+    if 9 * NB >= 32768:
+        raise ValueError("Factor storage exceeds the 15-bit offset range")
+
+    def boff(i, j) -> int:
+        return 9 * block_id[(i, j)]
+
+    # ---- assembly gather lists (A = J^T J) -----------------------------------
+    contrib: dict = {}
+    for row in ls_rows:
+        for ea, ca in enumerate(row.eff):
+            for eb, cb in enumerate(row.eff):
+                pa, pb = pos_of[ca], pos_of[cb]
+                if pa < pb:
+                    continue
+                for r in range(3):
+                    for c in range(3):
+                        if pa == pb and (ea != eb or c > r):
+                            continue
+                        contrib.setdefault((pa, pb, r, c), []).append(
+                            ((row.rg_off + 3 * ea + r) << 16) | (row.rg_off + 3 * eb + c))
+    asm_ptr, asm_dst, asm_con = [0], [], []
+    for (i, j), b in block_id.items():
+        for r in range(3):
+            for c in range(3):
+                if i == j and c > r:
+                    continue
+                dst = 9 * b + 3 * r + c
+                if i == j and r == c:
+                    dst |= D["OKIN_ASM_DIAG"]
+                asm_dst.append(dst)
+                asm_con.extend(contrib.get((i, j, r, c), []))
+                asm_ptr.append(len(asm_con))
+    NAT = len(asm_dst)
+
+    g_ptr, g_con = [0], []
+    row_index = {id(row): i for i, row in enumerate(rows)}
+    per_unknown: dict = {}
+    for row in ls_rows:
+        for e, cblk in enumerate(row.eff):
+            for r in range(3):
+                per_unknown.setdefault(3 * pos_of[cblk] + r, []).append(
+                    ((row.rg_off + 3 * e + r) << 16) | row_index[id(row)])
+    for u in range(3 * NF):
+        g_con.extend(per_unknown.get(u, []))
+        g_ptr.append(len(g_con))
+
+    # ---- left-looking update lists, scale tasks -------------------------------
+    cols_with = [[] for _ in range(NF)]        # cols_with[j] = K < j with L_jK != 0
+    for k in range(NF):
+        for i in struct[k]:
+            cols_with[i].append(k)
+    lev_cols = [[j for j in range(NF) if level[j] == lv] for lv in range(NLEV)]
+    lev_upd, upd_dst, upd_ptr, upd_con = [0], [], [0], []
+    lev_scl, scl = [0], []
+    for lv in range(NLEV):
+        for j in lev_cols[lv]:
+            for i in [j] + struct[j]:
+                ks = [k for k in cols_with[j] if i == j or i in struct[k]]
+                if not ks:
+                    continue
+                for r in range(3):
+                    for c in range(3):
+                        if i == j and c > r:
+                            continue
+                        upd_dst.append(boff(i, j) + 3 * r + c)
+                        for k in ks:
+                            upd_con.append(((boff(i, k) + 3 * r) << 16) | (boff(j, k) + 3 * c))
+                        upd_ptr.append(len(upd_con))
+            scl.append([j, boff(j, j), -1, 0])
+            for i in struct[j]:
+                for r in range(3):
+                    scl.append([j, boff(j, j), boff(i, j) + 3 * r, 0])
+        lev_upd.append(len(upd_dst))
+        lev_scl.append(len(scl))
+
+    fw_ptr, fw_con, bw_ptr, bw_con = [0], [], [0], []
+    for j in range(NF):
+        for k in cols_with[j]:
+            fw_con.append((boff(j, k) << 16) | (3 * k))
+        fw_ptr.append(len(fw_con))
+        for i in struct[j]:
+            bw_con.append((boff(i, j) << 16) | (3 * i))
+        bw_ptr.append(len(bw_con))
+    lev_col_ptr, lev_col = [0], []
+    for lv in range(NLEV):
+        lev_col.extend(lev_cols[lv])
+        lev_col_ptr.append(len(lev_col))
+
+    elim_point = [pidx[free_order[order[j]]] for j in range(NF)]
+    elim_col = [order[j] for j in range(NF)]
+
+    # tangent right-hand sides: gradient of each target row scattered to unknowns
+    tgt_sc_ptr, tgt_sc = [0], []
+    for row in ls_rows[trow0:]:
+        for e, cblk in enumerate(row.eff):
+            for r in range(3):
+                tgt_sc.append(((row.rg_off + 3 * e + r) << 16) | (3 * pos_of[cblk] + r))
+        tgt_sc_ptr.append(len(tgt_sc))
+
+    out_keys = list(output_points) if output_points is not None else list(point_keys)
+    for k in out_keys:
+        if k not in pidx:
+            raise ValueError(f"Output point {k!r} is not part of the model")
+
+    # ---- blobs ------------------------------------------------------------------
+    NT = len(targets)
+    N = 3 * NF
+    row_tab = []
+    for row in rows:
+        pts = row.points + [-1] * (4 - len(row.points))
+        rec = [row.fam, *pts, row.cst_off, row.rg_off, len(row.eff), row.rule, *row.slotmap, row.aux]
+        row_tab.append(rec + [0] * (D["OKIN_ROW_STRIDE"] - len(rec)))
+    cst_init = [v for row in rows for v in row.consts]
+
+    isecs = {
+        "OKIN_S_POINT_KIND": kind, "OKIN_S_IN_POINT": [pidx[k] for k in in_keys],
+        "OKIN_S_DOP": dops, "OKIN_S_PAR_MODE": par_mode, "OKIN_S_ADJ": adj_tasks, "OKIN_S_ADJ_CHAIN": adj_chain,
+        "OKIN_S_ROW": row_tab, "OKIN_S_DER": der_desc,
+        "OKIN_S_ASM_PTR": asm_ptr, "OKIN_S_ASM_DST": asm_dst, "OKIN_S_ASM_CON": asm_con,
+        "OKIN_S_G_PTR": g_ptr, "OKIN_S_G_CON": g_con,
+        "OKIN_S_LEV_UPD": lev_upd, "OKIN_S_UPD_DST": upd_dst, "OKIN_S_UPD_PTR": upd_ptr, "OKIN_S_UPD_CON": upd_con,
+        "OKIN_S_LEV_SCL": lev_scl, "OKIN_S_SCL": scl,
+        "OKIN_S_LEV_COL_PTR": lev_col_ptr, "OKIN_S_LEV_COL": lev_col,
+        "OKIN_S_FW_PTR": fw_ptr, "OKIN_S_FW_CON": fw_con, "OKIN_S_BW_PTR": bw_ptr, "OKIN_S_BW_CON": bw_con,
+        "OKIN_S_ELIM_POINT": elim_point, "OKIN_S_ELIM_COL": elim_col,
+        "OKIN_S_TGT_SC_PTR": tgt_sc_ptr, "OKIN_S_TGT_SC": tgt_sc,
+        "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_SETUP_PT": [],
+    }
+    hdr = np.zeros(D["OKIN_HDR_SIZE"], np.int32)
+    chunks, cursor = [], 0
+    for name, data in isecs.items():
+        arr = np.asarray(data, dtype=np.int64).reshape(-1)
+        if arr.size and (arr.max() > 2**31 - 1 or arr.min() < -(2**31)):
+            raise ValueError(f"section {name} overflows int32")
+        s = D[name]
+        hdr[D["OKIN_H_SEC0"] + 2 * s] = cursor
+        hdr[D["OKIN_H_SEC0"] + 2 * s + 1] = arr.size
+        chunks.append(arr.astype(np.int32))
+        cursor += arr.size
+    iblob = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
+    fsecs = {"OKIN_F_PAR_VAL": par_val, "OKIN_F_CST_INIT": cst_init}
+    fchunks, cursor = [], 0
+    for name, data in fsecs.items():
+        arr = np.asarray(data, dtype=np.float64).reshape(-1)
+        s = D[name]
+        hdr[D["OKIN_H_FSEC0"] + 2 * s] = cursor
+        hdr[D["OKIN_H_FSEC0"] + 2 * s + 1] = arr.size
+        fchunks.append(arr)
+        cursor += arr.size
+    fblob = np.concatenate(fchunks) if fchunks else np.zeros(0, np.float64)
+    if fblob.size == 0:
+        fblob = np.zeros(1, np.float64)
+
+    # shared-memory layout (doubles)
+    off = 0
+
+    def take(n: int) -> int:
+        nonlocal off
+        start = off
+        off += n
+        return start
+
+    layout = {
+        "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
+        "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)), "OKIN_H_OFF_LB": take(9 * NB),
+        "OKIN_H_OFF_DFAC": take(9 * NF), "OKIN_H_OFF_VEC": take((1 + NT) * N), "OKIN_H_OFF_XSAVE": take(N),
+        "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)),
+    }
+    counts = {
+        "OKIN_H_MAGIC": D["OKIN_MAGIC"], "OKIN_H_P": P, "OKIN_H_NF": NF, "OKIN_H_NIN": len(in_keys),
+        "OKIN_H_NDOP": len(dops), "OKIN_H_NPAR": len(par_val), "OKIN_H_NROW": NROW, "OKIN_H_NREP": NREP,
+        "OKIN_H_NT": NT, "OKIN_H_NCST": ncst, "OKIN_H_NRG": nrg, "OKIN_H_NAD": len(adj_tasks), "OKIN_H_NDB": ndb,
+        "OKIN_H_NB": NB, "OKIN_H_NLEV": NLEV, "OKIN_H_NAT": NAT, "OKIN_H_NOUT": len(out_keys),
+        "OKIN_H_TROW0": trow0, "OKIN_H_SMEM_DOUBLES": off, **layout,
+    }
+    for name, value in counts.items():
+        hdr[D[name]] = value
+
+    dense_flops = 2 * N**3 // 3
+    stats = {
+        "n_points": P, "n_free": NF, "n_unknowns": N, "n_rows": NROW, "n_report_rows": NREP, "n_targets": NT,
+        "n_blocks": NB, "n_levels": NLEV, "fill_blocks": NB - NF - sum(len(a) for a in adjacency) // 2,
+        "asm_fma": len(asm_con), "g_fma": len(g_con), "update_fma": 3 * len(upd_con),
+        "scale_tasks": len(scl), "solve_fma": 9 * (len(fw_con) + len(bw_con)) + 12 * NF,
+        "smem_doubles": off, "iblob_words": int(iblob.size), "dense_lu_flops": dense_flops,
+    }
+    return TopologyProgram(
+        hdr=hdr, iblob=iblob, fblob=fblob, point_keys=point_keys, free_order=free_order, in_keys=in_keys,
+        out_keys=out_keys, n_constraints=len(constraints), row_source=[r.source for r in rows],
+        target_points=[t.point_id for t in targets], stats=stats,
+    )
+
+
+def compile_suspension(suspension, sweep_config, output_points=None, design_rules: bool = True) -> TopologyProgram:
+    """Compile a built suspension + sweep (first-step targets define the target rows)."""
+    targets = [sweep[0] for sweep in sweep_config.target_sweeps]
+    if output_points is None:
+        output_points = None
+    return compile_topology(
+        suspension.initial_state(), suspension.constraints(), suspension.derived_spec(), targets,
+        output_points=output_points, design_rules=design_rules,
+    )

@@ -1,0 +1,382 @@
+// C ABI (include/okin.h) and the sm_100a kernels behind it.
+//
+// Kernel mapping: one warp per suspension instance, OKIN_WARPS_PER_CTA instances per CTA, each
+// warp working in its own slice of dynamic shared memory; the grid is persistent (a multiple of
+// the SM count times the resident CTAs per SM) and strides over the instance range.  The work
+// is fp64 FMA/issue bound, tens of unknowns per system, so tensor cores
+// and TMA have nothing to act on; the only global traffic is the coalesced instance-major
+// hardpoint read and state write.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/okin.h"
+#include "okin_core.cuh"
+
+#define OKIN_WARPS_PER_CTA 4
+#define OKIN_MAX_DEVICES 16
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define OKIN_CUDA(call)                                                                            \
+  do {                                                                                             \
+    cudaError_t err__ = (call);                                                                    \
+    if (err__ != cudaSuccess)                                                                      \
+      return fail(OKIN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));           \
+  } while (0)
+
+struct DeviceCopy {
+  bool ready = false;
+  int32_t* hdr = nullptr;
+  int32_t* ib = nullptr;
+  double* fb = nullptr;
+  int num_sms = 0;
+  int ctas_per_sm = 0;
+  // grow-only workspace for the host-buffer entry point
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  cudaStream_t stream = nullptr;
+};
+
+}  // namespace
+
+struct okin_topology {
+  std::vector<int32_t> hdr, ib;
+  std::vector<double> fb;
+  DeviceCopy dev[OKIN_MAX_DEVICES];
+  std::mutex mu;
+};
+
+__global__ void __launch_bounds__(OKIN_WARPS_PER_CTA * 32)
+okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
+                  long long n_instances, int n_steps, const double* __restrict__ hardpoints,
+                  const double* __restrict__ tvals, OkinSolverCfg cfg, double* positions, int32_t* iters,
+                  double* max_residual, double* tangents, int32_t* status, int32_t* failed_step) {
+  extern __shared__ double okin_smem[];
+  OkinProgram pr{hdr, ib, fb};
+  const int warp = threadIdx.x >> 5;
+  double* sm = okin_smem + (size_t)warp * hdr[OKIN_H_SMEM_DOUBLES];
+  const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
+  const long long stride = (long long)gridDim.x * OKIN_WARPS_PER_CTA;
+  for (long long i = (long long)blockIdx.x * OKIN_WARPS_PER_CTA + warp; i < n_instances; i += stride) {
+    OkinOutputs out;
+    out.positions = positions ? positions + (size_t)i * n_steps * 3 * nout : nullptr;
+    out.iters = iters ? iters + (size_t)i * n_steps : nullptr;
+    out.max_residual = max_residual ? max_residual + (size_t)i * n_steps : nullptr;
+    out.tangents = tangents ? tangents + (size_t)i * n_steps * nt * n : nullptr;
+    out.status = status + i;
+    out.failed_step = failed_step + i;
+    okin_sweep(pr, sm, hardpoints + (size_t)i * 3 * nin, tvals, n_steps, cfg, out);
+    __syncwarp();
+  }
+}
+
+// fp64 peak: 8 independent dependent-FMA chains per thread, enough threads to fill the chip.
+__global__ void okin_dfma_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+namespace {
+
+int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
+  if (device < 0 || device >= OKIN_MAX_DEVICES) return fail(OKIN_ERR_USAGE, "device id out of range");
+  std::lock_guard<std::mutex> lock(t->mu);
+  DeviceCopy& d = t->dev[device];
+  if (!d.ready) {
+    OKIN_CUDA(cudaSetDevice(device));
+    OKIN_CUDA(cudaMalloc(&d.hdr, t->hdr.size() * sizeof(int32_t)));
+    OKIN_CUDA(cudaMalloc(&d.ib, std::max<size_t>(t->ib.size(), 1) * sizeof(int32_t)));
+    OKIN_CUDA(cudaMalloc(&d.fb, std::max<size_t>(t->fb.size(), 1) * sizeof(double)));
+    OKIN_CUDA(cudaMemcpy(d.hdr, t->hdr.data(), t->hdr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    OKIN_CUDA(cudaMemcpy(d.ib, t->ib.data(), t->ib.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    OKIN_CUDA(cudaMemcpy(d.fb, t->fb.data(), t->fb.size() * sizeof(double), cudaMemcpyHostToDevice));
+    cudaDeviceProp prop;
+    OKIN_CUDA(cudaGetDeviceProperties(&prop, device));
+    d.num_sms = prop.multiProcessorCount;
+    const int smem = OKIN_WARPS_PER_CTA * t->hdr[OKIN_H_SMEM_DOUBLES] * (int)sizeof(double);
+    if ((size_t)smem > prop.sharedMemPerBlockOptin)
+      return fail(OKIN_ERR_USAGE, "topology needs more shared memory per CTA than the device offers");
+    OKIN_CUDA(cudaFuncSetAttribute(okin_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.ctas_per_sm, okin_sweep_kernel,
+                                                            OKIN_WARPS_PER_CTA * 32, smem));
+    if (d.ctas_per_sm < 1) return fail(OKIN_ERR_CUDA, "kernel does not fit on an SM");
+    OKIN_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    d.ready = true;
+  }
+  *out = &d;
+  return OKIN_OK;
+}
+
+int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStream_t stream, int64_t n_instances,
+           int32_t n_steps, const double* hp, const double* tv, double* pos, int32_t* status, int32_t* failed,
+           int32_t* iters, double* maxres, double* tangents) {
+  if (n_instances == 0) return OKIN_OK;
+  OkinSolverCfg c{cfg->step_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter, cfg->use_predictor};
+  const int smem = OKIN_WARPS_PER_CTA * t->hdr[OKIN_H_SMEM_DOUBLES] * (int)sizeof(double);
+  const int64_t needed = (n_instances + OKIN_WARPS_PER_CTA - 1) / OKIN_WARPS_PER_CTA;
+  const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
+  const int grid = (int)std::min<int64_t>(needed, resident);
+  okin_sweep_kernel<<<grid, OKIN_WARPS_PER_CTA * 32, smem, stream>>>(
+      d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, hp, tv, c, pos, iters, maxres, tangents, status, failed);
+  OKIN_CUDA(cudaGetLastError());
+  return OKIN_OK;
+}
+
+int check_common(const okin_topology* t, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
+                 const void* hp, const void* tv, const void* status, const void* failed) {
+  if (!t || !cfg) return fail(OKIN_ERR_USAGE, "null topology or config");
+  if (n_instances < 0 || n_steps < 0) return fail(OKIN_ERR_USAGE, "negative size");
+  if (n_instances > 0 && (!hp || !status || !failed)) return fail(OKIN_ERR_USAGE, "null required buffer");
+  if (n_steps > 0 && t->hdr[OKIN_H_NT] > 0 && !tv) return fail(OKIN_ERR_USAGE, "null target_values");
+  if (cfg->max_iter < 1 || !(cfg->step_tol > 0.0)) return fail(OKIN_ERR_USAGE, "invalid solver config");
+  return OKIN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int okin_last_error(char* buf, int32_t len) {
+  if (!buf || len <= 0) return OKIN_ERR_USAGE;
+  std::snprintf(buf, (size_t)len, "%s", g_last_error.c_str());
+  return OKIN_OK;
+}
+
+int okin_device_count(int* out) {
+  if (!out) return fail(OKIN_ERR_USAGE, "null out");
+  int n = 0;
+  cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess) {
+    *out = 0;
+    return fail(OKIN_ERR_NO_DEVICE, cudaGetErrorString(err));
+  }
+  *out = n;
+  return OKIN_OK;
+}
+
+int okin_default_cfg(okin_solver_cfg* out) {
+  if (!out) return fail(OKIN_ERR_USAGE, "null out");
+  out->step_tol = 1e-9;
+  out->residual_tol = 1e-3;
+  out->mu_init = 1e-3;
+  out->max_iter = 50;
+  out->use_predictor = 1;
+  return OKIN_OK;
+}
+
+int okin_topology_create(const okin_topology_desc* desc, okin_topology** out) {
+  if (!desc || !out || !desc->hdr || !desc->iblob || !desc->fblob) return fail(OKIN_ERR_USAGE, "null descriptor");
+  if (desc->hdr[OKIN_H_MAGIC] != OKIN_MAGIC) return fail(OKIN_ERR_USAGE, "bad topology magic");
+  if (desc->n_iblob < 0 || desc->n_fblob < 0) return fail(OKIN_ERR_USAGE, "negative blob size");
+  // every section must lie inside its blob
+  for (int s = 0; s < OKIN_S_COUNT; ++s) {
+    const int64_t off = desc->hdr[OKIN_H_SEC0 + 2 * s], len = desc->hdr[OKIN_H_SEC0 + 2 * s + 1];
+    if (off < 0 || len < 0 || off + len > desc->n_iblob) return fail(OKIN_ERR_USAGE, "int section out of range");
+  }
+  for (int s = 0; s < OKIN_F_COUNT; ++s) {
+    const int64_t off = desc->hdr[OKIN_H_FSEC0 + 2 * s], len = desc->hdr[OKIN_H_FSEC0 + 2 * s + 1];
+    if (off < 0 || len < 0 || off + len > desc->n_fblob) return fail(OKIN_ERR_USAGE, "double section out of range");
+  }
+  if (desc->hdr[OKIN_H_NT] > OKIN_MAX_TARGETS) return fail(OKIN_ERR_USAGE, "too many targets");
+  okin_topology* t = new okin_topology();
+  t->hdr.assign(desc->hdr, desc->hdr + OKIN_HDR_SIZE);
+  t->ib.assign(desc->iblob, desc->iblob + desc->n_iblob);
+  t->fb.assign(desc->fblob, desc->fblob + desc->n_fblob);
+  *out = t;
+  return OKIN_OK;
+}
+
+int okin_topology_destroy(okin_topology* t) {
+  if (!t) return OKIN_OK;
+  for (int dev = 0; dev < OKIN_MAX_DEVICES; ++dev) {
+    DeviceCopy& d = t->dev[dev];
+    if (!d.ready) continue;
+    cudaSetDevice(dev);
+    cudaFree(d.hdr);
+    cudaFree(d.ib);
+    cudaFree(d.fb);
+    if (d.ws) cudaFree(d.ws);
+    if (d.stream) cudaStreamDestroy(d.stream);
+  }
+  delete t;
+  return OKIN_OK;
+}
+
+int okin_topology_get_info(const okin_topology* t, okin_topology_info* out) {
+  if (!t || !out) return fail(OKIN_ERR_USAGE, "null argument");
+  const int32_t* h = t->hdr.data();
+  out->n_points = h[OKIN_H_P];
+  out->n_in_points = h[OKIN_H_NIN];
+  out->n_out_points = h[OKIN_H_NOUT];
+  out->n_unknowns = 3 * h[OKIN_H_NF];
+  out->n_targets = h[OKIN_H_NT];
+  out->n_rows = h[OKIN_H_NROW];
+  out->smem_bytes_per_instance = h[OKIN_H_SMEM_DOUBLES] * (int32_t)sizeof(double);
+  out->n_levels = h[OKIN_H_NLEV];
+  return OKIN_OK;
+}
+
+int okin_launch_geometry(okin_topology* t, int32_t device, int64_t n_instances, int32_t* grid, int32_t* block,
+                         int32_t* smem_bytes, int32_t* ctas_per_sm) {
+  if (!t) return fail(OKIN_ERR_USAGE, "null topology");
+  DeviceCopy* d = nullptr;
+  int rc = ensure_device(t, device, &d);
+  if (rc) return rc;
+  const int64_t needed = (n_instances + OKIN_WARPS_PER_CTA - 1) / OKIN_WARPS_PER_CTA;
+  if (grid) *grid = (int32_t)std::min<int64_t>(needed, (int64_t)d->num_sms * d->ctas_per_sm);
+  if (block) *block = OKIN_WARPS_PER_CTA * 32;
+  if (smem_bytes) *smem_bytes = OKIN_WARPS_PER_CTA * t->hdr[OKIN_H_SMEM_DOUBLES] * (int32_t)sizeof(double);
+  if (ctas_per_sm) *ctas_per_sm = d->ctas_per_sm;
+  return OKIN_OK;
+}
+
+int okin_solve_batch_device(okin_topology* t, const okin_solver_cfg* cfg, int32_t device, void* stream,
+                            int64_t n_instances, int32_t n_steps, const double* d_hardpoints,
+                            const double* d_target_values, double* d_positions_out, int32_t* d_status_out,
+                            int32_t* d_failed_step_out, int32_t* d_iters_out, double* d_max_residual_out,
+                            double* d_tangents_out) {
+  int rc = check_common(t, cfg, n_instances, n_steps, d_hardpoints, d_target_values, d_status_out, d_failed_step_out);
+  if (rc) return rc;
+  DeviceCopy* d = nullptr;
+  rc = ensure_device(t, device, &d);
+  if (rc) return rc;
+  OKIN_CUDA(cudaSetDevice(device));
+  return launch(t, d, cfg, (cudaStream_t)stream, n_instances, n_steps, d_hardpoints, d_target_values,
+                d_positions_out, d_status_out, d_failed_step_out, d_iters_out, d_max_residual_out, d_tangents_out);
+}
+
+int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
+                     const double* hardpoints, const double* target_values, const int32_t* device_ids,
+                     int32_t n_devices, double* positions_out, int32_t* status_out, int32_t* failed_step_out,
+                     int32_t* iters_out, double* max_residual_out, double* tangents_out) {
+  int rc = check_common(t, cfg, n_instances, n_steps, hardpoints, target_values, status_out, failed_step_out);
+  if (rc) return rc;
+  const int32_t default_dev = 0;
+  if (!device_ids || n_devices <= 0) {
+    device_ids = &default_dev;
+    n_devices = 1;
+  }
+  if (n_devices > OKIN_MAX_DEVICES) return fail(OKIN_ERR_USAGE, "too many devices");
+  const int32_t* h = t->hdr.data();
+  const size_t nin3 = 3 * (size_t)h[OKIN_H_NIN], nout3 = 3 * (size_t)h[OKIN_H_NOUT];
+  const size_t nt = h[OKIN_H_NT], n = 3 * (size_t)h[OKIN_H_NF];
+  const size_t S = (size_t)n_steps;
+
+  struct Shard {
+    DeviceCopy* d;
+    int device;
+    int64_t begin, count;
+    double *hp, *tv, *pos, *maxres, *tan;
+    int32_t *status, *failed, *iters;
+  };
+  std::vector<Shard> shards;
+  // Contiguous instance ranges [k*N/G, (k+1)*N/G): the host-side "gather" is the D2H copies.
+  for (int k = 0; k < n_devices; ++k) {
+    Shard s{};
+    s.device = device_ids[k];
+    s.begin = n_instances * k / n_devices;
+    s.count = n_instances * (k + 1) / n_devices - s.begin;
+    if (s.count == 0) continue;
+    rc = ensure_device(t, s.device, &s.d);
+    if (rc) return rc;
+    shards.push_back(s);
+  }
+  // enqueue everything asynchronously on every device, then wait
+  for (Shard& s : shards) {
+    OKIN_CUDA(cudaSetDevice(s.device));
+    const size_t c = (size_t)s.count;
+    auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_hp = align(c * nin3 * 8), b_tv = align(std::max<size_t>(nt * S, 1) * 8);
+    const size_t b_pos = positions_out ? align(c * S * nout3 * 8) : 0;
+    const size_t b_mr = max_residual_out ? align(c * S * 8) : 0;
+    const size_t b_tan = tangents_out ? align(c * S * nt * n * 8) : 0;
+    const size_t b_it = iters_out ? align(c * S * 4) : 0;
+    const size_t b_st = align(c * 4);
+    const size_t total = b_hp + b_tv + b_pos + b_mr + b_tan + b_it + 2 * b_st;
+    if (total > s.d->ws_bytes) {
+      if (s.d->ws) OKIN_CUDA(cudaFree(s.d->ws));
+      s.d->ws = nullptr;
+      s.d->ws_bytes = 0;
+      OKIN_CUDA(cudaMalloc(&s.d->ws, total));
+      s.d->ws_bytes = total;
+    }
+    char* p = (char*)s.d->ws;
+    s.hp = (double*)p; p += b_hp;
+    s.tv = (double*)p; p += b_tv;
+    s.pos = positions_out ? (double*)p : nullptr; p += b_pos;
+    s.maxres = max_residual_out ? (double*)p : nullptr; p += b_mr;
+    s.tan = tangents_out ? (double*)p : nullptr; p += b_tan;
+    s.iters = iters_out ? (int32_t*)p : nullptr; p += b_it;
+    s.status = (int32_t*)p; p += b_st;
+    s.failed = (int32_t*)p;
+    cudaStream_t st = s.d->stream;
+    OKIN_CUDA(cudaMemcpyAsync(s.hp, hardpoints + (size_t)s.begin * nin3, c * nin3 * 8, cudaMemcpyHostToDevice, st));
+    if (nt * S) OKIN_CUDA(cudaMemcpyAsync(s.tv, target_values, nt * S * 8, cudaMemcpyHostToDevice, st));
+    rc = launch(t, s.d, cfg, st, s.count, n_steps, s.hp, s.tv, s.pos, s.status, s.failed, s.iters, s.maxres, s.tan);
+    if (rc) return rc;
+    const size_t b0 = (size_t)s.begin;
+    if (positions_out)
+      OKIN_CUDA(cudaMemcpyAsync(positions_out + b0 * S * nout3, s.pos, c * S * nout3 * 8, cudaMemcpyDeviceToHost, st));
+    if (max_residual_out)
+      OKIN_CUDA(cudaMemcpyAsync(max_residual_out + b0 * S, s.maxres, c * S * 8, cudaMemcpyDeviceToHost, st));
+    if (tangents_out)
+      OKIN_CUDA(cudaMemcpyAsync(tangents_out + b0 * S * nt * n, s.tan, c * S * nt * n * 8, cudaMemcpyDeviceToHost, st));
+    if (iters_out) OKIN_CUDA(cudaMemcpyAsync(iters_out + b0 * S, s.iters, c * S * 4, cudaMemcpyDeviceToHost, st));
+    OKIN_CUDA(cudaMemcpyAsync(status_out + b0, s.status, c * 4, cudaMemcpyDeviceToHost, st));
+    OKIN_CUDA(cudaMemcpyAsync(failed_step_out + b0, s.failed, c * 4, cudaMemcpyDeviceToHost, st));
+  }
+  for (Shard& s : shards) {
+    OKIN_CUDA(cudaSetDevice(s.device));
+    OKIN_CUDA(cudaStreamSynchronize(s.d->stream));
+  }
+  return OKIN_OK;
+}
+
+int okin_fp64_peak(int32_t device, double* tflops_out) {
+  if (!tflops_out) return fail(OKIN_ERR_USAGE, "null out");
+  OKIN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  OKIN_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int block = 256, grid = prop.multiProcessorCount * 8, iters = 1 << 14;
+  double* buf = nullptr;
+  OKIN_CUDA(cudaMalloc(&buf, (size_t)grid * block * sizeof(double)));
+  cudaEvent_t e0, e1;
+  OKIN_CUDA(cudaEventCreate(&e0));
+  OKIN_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    OKIN_CUDA(cudaEventRecord(e0));
+    okin_dfma_kernel<<<grid, block>>>(buf, iters, 0.999999, 1e-7);
+    OKIN_CUDA(cudaEventRecord(e1));
+    OKIN_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    OKIN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * grid * block;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops_out = best;
+  return OKIN_OK;
+}
+
+}  // extern "C"

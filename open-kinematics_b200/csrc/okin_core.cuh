@@ -1,0 +1,755 @@
+// Per-instance solve core: design-constant setup, residual/Jacobian rows, normal-equation
+// assembly, 3x3-block sparse Cholesky, Gauss-Newton / Levenberg-Marquardt continuation over a
+// sweep, tangent solves.  One *warp* owns one suspension instance; all per-instance state
+// lives in that warp's slice of shared memory and the code is a sequence of *phases*:
+//
+//     OKIN_PHASE_BEGIN  ... body executed by every lane, `lane` in scope ...  OKIN_PHASE_END
+//
+// A phase ends with __syncwarp(); lanes only communicate through shared memory across phase
+// boundaries, and everything outside a phase is warp-uniform.  Under OKIN_LANE_EMU (plain
+// g++, used by tests/ only, never by the product library) a phase is a loop over 32 lanes,
+// which lets the CPU-only CI run this exact source against the oracle.
+//
+// What replaces what in the reference (paths relative to src/kinematics/core/):
+//   okin_setup        <- Suspension.constraints() design constants (suspensions/corner/*.py,
+//                        axle/*.py), convert_targets_to_absolute (solver.py:584-627)
+//   okin_eval_rows    <- ResidualComputer.compute / compute_jacobian (solver.py:226-275, :502-581)
+//   okin_derived_*    <- DerivedPointsManager.update_in_place / compute_point_jacobian
+//                        (points/derived/manager.py:186-197, :271-324), hand-written JVPs
+//   okin_solve_step   <- least_squares(method="lm") call (solver.py:124-169, :717-724)
+//   okin_sweep        <- solve_suspension_sweep loop (solver.py:716-774)
+//   okin_tangents     <- compute_state_tangents (sensitivity.py:57-143) via the Cholesky factor
+#pragma once
+
+#include "okin_defs.h"
+#include "okin_gen_constraints.cuh"
+
+#if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
+#define OKIN_PHASE_BEGIN { const int lane = (int)(threadIdx.x & 31u);
+#define OKIN_PHASE_END } __syncwarp();
+#define OKIN_LDG(p) __ldg(p)
+#else
+#define OKIN_PHASE_BEGIN for (int lane = 0; lane < 32; ++lane) {
+#define OKIN_PHASE_END }
+#define OKIN_LDG(p) (*(p))
+#endif
+
+struct OkinProgram {
+  const int32_t* hdr;  // [OKIN_HDR_SIZE]
+  const int32_t* ib;   // int32 blob
+  const double* fb;    // double blob
+};
+
+struct OkinSolverCfg {
+  double step_tol;      // converged when max|dx| <= step_tol (mm)
+  double residual_tol;  // accept a step when max|r| <= residual_tol   (reference constants.py:20)
+  double mu_init;       // first Marquardt damping factor after a rejected Gauss-Newton step
+  int32_t max_iter;     // linear solves per step before "not converged"
+  int32_t use_predictor;  // warm-start each step along the previous tangents
+};
+
+OKIN_HD const int32_t* okin_sec(const OkinProgram& pr, int s) { return pr.ib + pr.hdr[OKIN_H_SEC0 + 2 * s]; }
+OKIN_HD int okin_sec_len(const OkinProgram& pr, int s) { return pr.hdr[OKIN_H_SEC0 + 2 * s + 1]; }
+OKIN_HD const double* okin_fsec(const OkinProgram& pr, int s) { return pr.fb + pr.hdr[OKIN_H_FSEC0 + 2 * s]; }
+
+// Warp-uniform scalars kept in registers (identical in every lane).
+struct OkinState {
+  double f2;    // ||r||^2 over least-squares rows at the current point
+  double rmax;  // max|r| over all rows at the current point
+  double mu;    // current damping (0 = pure Gauss-Newton)
+  int notpd;    // factorisation hit a non-positive pivot
+};
+
+// ---------------------------------------------------------------------------------------
+// Derived points: value and forward-mode tangent of one op.
+// ---------------------------------------------------------------------------------------
+OKIN_HD void okin_unit_jvp(const double v[3], const double dv[3], double u[3], double du[3], double* inv_len) {
+  const double il = OKIN_RSQRT(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  u[0] = v[0] * il; u[1] = v[1] * il; u[2] = v[2] * il;
+  const double ud = u[0] * dv[0] + u[1] * dv[1] + u[2] * dv[2];
+  du[0] = (dv[0] - u[0] * ud) * il; du[1] = (dv[1] - u[1] * ud) * il; du[2] = (dv[2] - u[2] * ud) * il;
+  *inv_len = il;
+}
+
+// out = f(a, b, c; par); dout = J_a da + J_b db + J_c dc.  (definitions.py:24-180)
+OKIN_HD void okin_dop_eval(int op, double par, const double* a, const double* b, const double* c,
+                           const double* da, const double* db, const double* dc, double out[3], double dout[3]) {
+  if (op == OKIN_DOP_MIDPOINT) {
+    for (int k = 0; k < 3; ++k) { out[k] = a[k] + (b[k] - a[k]) * 0.5; dout[k] = da[k] + (db[k] - da[k]) * 0.5; }
+  } else if (op == OKIN_DOP_ALONG_LINE) {
+    double v[3], dv[3], u[3], du[3], il;
+    for (int k = 0; k < 3; ++k) { v[k] = b[k] - a[k]; dv[k] = db[k] - da[k]; }
+    okin_unit_jvp(v, dv, u, du, &il);
+    for (int k = 0; k < 3; ++k) { out[k] = a[k] + u[k] * par; dout[k] = da[k] + du[k] * par; }
+  } else {  // OKIN_DOP_CONTACT_PATCH: a = wheel centre, b = axle inboard, c = axle outboard
+    double v[3], dv[3], u[3], du[3], il;
+    for (int k = 0; k < 3; ++k) { v[k] = c[k] - b[k]; dv[k] = dc[k] - db[k]; }
+    okin_unit_jvp(v, dv, u, du, &il);
+    // down = (0,0,-1); w = down - (down.u) u
+    const double s = -u[2], ds = -du[2];
+    double w[3], dw[3], q[3], dq[3];
+    for (int k = 0; k < 3; ++k) { w[k] = -s * u[k]; dw[k] = -(ds * u[k] + s * du[k]); }
+    w[2] -= 1.0;
+    okin_unit_jvp(w, dw, q, dq, &il);
+    for (int k = 0; k < 3; ++k) { out[k] = a[k] + q[k] * par; dout[k] = da[k] + dq[k] * par; }
+  }
+}
+
+// Evaluate derived points into pos[].  active_only: only the ops referenced by solve rows.
+template <typename Dummy = void>
+OKIN_HD void okin_derived_update(const OkinProgram& pr, double* sm, bool active_only) {
+  const int32_t* dop = okin_sec(pr, OKIN_S_DOP);
+  const int ndop = pr.hdr[OKIN_H_NDOP];
+  double* pos = sm + pr.hdr[OKIN_H_OFF_POS];
+  const double* par = sm + pr.hdr[OKIN_H_OFF_PAR];
+  OKIN_PHASE_BEGIN
+  if (lane == 0) {
+    const double z[3] = {0.0, 0.0, 0.0};
+    for (int d = 0; d < ndop; ++d) {
+      const int32_t* rec = dop + d * OKIN_DOP_STRIDE;
+      if (active_only && !OKIN_LDG(rec + 7)) continue;
+      const int ia = OKIN_LDG(rec + 2), ib = OKIN_LDG(rec + 3), ic = OKIN_LDG(rec + 4);
+      double out[3], dout[3];
+      okin_dop_eval(OKIN_LDG(rec + 0), par[OKIN_LDG(rec + 5)], pos + 3 * ia, pos + 3 * (ib < 0 ? ia : ib),
+                    pos + 3 * (ic < 0 ? ia : ic), z, z, z, out, dout);
+      const int o = OKIN_LDG(rec + 1);
+      pos[3 * o] = out[0]; pos[3 * o + 1] = out[1]; pos[3 * o + 2] = out[2];
+    }
+  }
+  OKIN_PHASE_END
+}
+
+// Jacobian blocks d(derived)/d(free base point) by seeding one coordinate per task and
+// pushing it through the op chain (manager.py:271-324 does the same with dual numbers).
+template <typename Dummy = void>
+OKIN_HD void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
+  const int nad = pr.hdr[OKIN_H_NAD];
+  if (nad == 0) return;
+  const int32_t* adj = okin_sec(pr, OKIN_S_ADJ);
+  const int32_t* chain = okin_sec(pr, OKIN_S_ADJ_CHAIN);
+  const int32_t* dop = okin_sec(pr, OKIN_S_DOP);
+  const double* pos = sm + pr.hdr[OKIN_H_OFF_POS];
+  const double* par = sm + pr.hdr[OKIN_H_OFF_PAR];
+  double* dblk = sm + pr.hdr[OKIN_H_OFF_DBLK];
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < nad; t += 32) {
+    const int32_t* rec = adj + t * OKIN_ADJ_STRIDE;
+    const int base = OKIN_LDG(rec + 1), comp = OKIN_LDG(rec + 2), off = OKIN_LDG(rec + 3);
+    const int cb = OKIN_LDG(rec + 4), ce = OKIN_LDG(rec + 5);
+    int tp[OKIN_MAX_CHAIN];
+    double tv[OKIN_MAX_CHAIN][3];
+    int nt = 0;
+    double seed[3] = {0.0, 0.0, 0.0};
+    seed[comp] = 1.0;
+    const double z[3] = {0.0, 0.0, 0.0};
+    double dout[3] = {0.0, 0.0, 0.0};
+    for (int q = cb; q < ce; ++q) {
+      const int32_t* op = dop + OKIN_LDG(chain + q) * OKIN_DOP_STRIDE;
+      const int in[3] = {OKIN_LDG(op + 2), OKIN_LDG(op + 3), OKIN_LDG(op + 4)};
+      const double* dv[3];
+      for (int s = 0; s < 3; ++s) {
+        dv[s] = z;
+        if (in[s] == base) dv[s] = seed;
+        for (int k = 0; k < nt; ++k)
+          if (tp[k] == in[s]) dv[s] = tv[k];
+      }
+      double out[3];
+      const int ia = in[0], ib = in[1] < 0 ? in[0] : in[1], ic = in[2] < 0 ? in[0] : in[2];
+      okin_dop_eval(OKIN_LDG(op + 0), par[OKIN_LDG(op + 5)], pos + 3 * ia, pos + 3 * ib, pos + 3 * ic,
+                    dv[0], dv[1], dv[2], out, dout);
+      tp[nt] = OKIN_LDG(op + 1);
+      tv[nt][0] = dout[0]; tv[nt][1] = dout[1]; tv[nt][2] = dout[2];
+      ++nt;
+    }
+    dblk[off + 0 + comp] = dout[0];
+    dblk[off + 3 + comp] = dout[1];
+    dblk[off + 6 + comp] = dout[2];
+  }
+  OKIN_PHASE_END
+}
+
+// ---------------------------------------------------------------------------------------
+// Setup: inputs -> pos, derived parameters, design pose, per-instance constants.
+// ---------------------------------------------------------------------------------------
+template <typename Dummy = void>
+OKIN_HD void okin_setup(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints) {
+  const int32_t* hdr = pr.hdr;
+  double* pos = sm + hdr[OKIN_H_OFF_POS];
+  double* cst = sm + hdr[OKIN_H_OFF_CST];
+  double* par = sm + hdr[OKIN_H_OFF_PAR];
+  const int nin = hdr[OKIN_H_NIN];
+  const int32_t* in_point = okin_sec(pr, OKIN_S_IN_POINT);
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < 3 * nin; t += 32) pos[3 * OKIN_LDG(in_point + t / 3) + t % 3] = hardpoints[t];
+  OKIN_PHASE_END
+
+  // Derived-op parameters.  A design projection reads the *authored* position of the derived
+  // point (macpherson.py:199-204), which is what pos[] still holds at this moment.
+  const int ndop = hdr[OKIN_H_NDOP];
+  const int32_t* dop = okin_sec(pr, OKIN_S_DOP);
+  const int32_t* par_mode = okin_sec(pr, OKIN_S_PAR_MODE);
+  const double* par_val = okin_fsec(pr, OKIN_F_PAR_VAL);
+  OKIN_PHASE_BEGIN
+  for (int d = lane; d < ndop; d += 32) {
+    const int32_t* rec = dop + d * OKIN_DOP_STRIDE;
+    const int p = OKIN_LDG(rec + 5);
+    double value = OKIN_LDG(par_val + p);
+    if (OKIN_LDG(par_mode + p) == OKIN_PAR_DESIGN_PROJECTION) {
+      const double* a = pos + 3 * OKIN_LDG(rec + 2);
+      const double* b = pos + 3 * OKIN_LDG(rec + 3);
+      const double* o = hardpoints + 3 * OKIN_LDG(rec + 6);
+      const double v[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+      const double il = OKIN_RSQRT(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      value = ((o[0] - a[0]) * v[0] + (o[1] - a[1]) * v[1] + (o[2] - a[2]) * v[2]) * il;
+    }
+    par[p] = value;
+  }
+  OKIN_PHASE_END
+
+  okin_derived_update(pr, sm, false);
+
+  // Per-instance constants: each row's own quantity at the design pose (true norms, no
+  // softnorm: vector_utils/geometric.py:17-28, :71-104, :197-214).
+  const int nrows = hdr[OKIN_H_NROW] + hdr[OKIN_H_NREP];
+  const int32_t* rows = okin_sec(pr, OKIN_S_ROW);
+  const double* cst_init = okin_fsec(pr, OKIN_F_CST_INIT);
+  const int ncst = hdr[OKIN_H_NCST];
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < ncst; t += 32) cst[t] = OKIN_LDG(cst_init + t);
+  OKIN_PHASE_END
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < nrows; t += 32) {
+    const int32_t* rec = rows + t * OKIN_ROW_STRIDE;
+    const int rule = OKIN_LDG(rec + OKIN_R_RULE);
+    if (rule == OKIN_RULE_EXPLICIT) continue;
+    const int fam = OKIN_LDG(rec + OKIN_R_FAM);
+    double* c = cst + OKIN_LDG(rec + OKIN_R_CST);
+    const double* p0 = pos + 3 * OKIN_LDG(rec + OKIN_R_P0);
+    if (rule == OKIN_RULE_DESIGN_POINT) {
+      c[0] = p0[0]; c[1] = p0[1]; c[2] = p0[2];
+    } else if (rule == OKIN_RULE_TARGET_BASE) {
+      c[3] = c[0] * p0[0] + c[1] * p0[1] + c[2] * p0[2];
+    } else if (fam == OKIN_FAM_DISTANCE) {
+      const double* p1 = pos + 3 * OKIN_LDG(rec + OKIN_R_P1);
+      const double dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
+      c[0] = sqrt(dx * dx + dy * dy + dz * dz);
+    } else if (fam == OKIN_FAM_ANGLE) {
+      // compute_vector_vector_angle on unit vectors (geometric.py:94-104)
+      const double* p1 = pos + 3 * OKIN_LDG(rec + OKIN_R_P1);
+      const double* p2 = pos + 3 * OKIN_LDG(rec + OKIN_R_P2);
+      const double* p3 = pos + 3 * OKIN_LDG(rec + OKIN_R_P3);
+      double a[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+      double b[3] = {p3[0] - p2[0], p3[1] - p2[1], p3[2] - p2[2]};
+      const double na = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      const double nb = sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+      for (int k = 0; k < 3; ++k) { a[k] /= na; b[k] /= nb; }
+      const double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+      c[0] = atan2(sqrt(cx * cx + cy * cy + cz * cz), a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+    } else if (fam == OKIN_FAM_SCALAR_TRIPLE) {
+      const double* p1 = pos + 3 * OKIN_LDG(rec + OKIN_R_P1);
+      const double* p2 = pos + 3 * OKIN_LDG(rec + OKIN_R_P2);
+      const double* p3 = pos + 3 * OKIN_LDG(rec + OKIN_R_P3);
+      const double a[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+      const double b[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+      const double d[3] = {p3[0] - p0[0], p3[1] - p0[1], p3[2] - p0[2]};
+      const double v = a[0] * (b[1] * d[2] - b[2] * d[1]) + a[1] * (b[2] * d[0] - b[0] * d[2]) +
+                       a[2] * (b[0] * d[1] - b[1] * d[0]);
+      c[0] = v;
+      c[1] = 1.0 / fabs(v);
+    }
+  }
+  OKIN_PHASE_END
+}
+
+// ---------------------------------------------------------------------------------------
+// Row evaluation: residuals (and gradients mapped to effective free blocks).
+// ---------------------------------------------------------------------------------------
+template <typename Dummy = void>
+OKIN_HD void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tval, bool with_grad, OkinState& st) {
+  const int32_t* hdr = pr.hdr;
+  okin_derived_update(pr, sm, true);
+  if (with_grad) okin_derived_jacobians(pr, sm);
+  const int nls = hdr[OKIN_H_NROW];
+  const int nrows = nls + hdr[OKIN_H_NREP];
+  const int32_t* rows = okin_sec(pr, OKIN_S_ROW);
+  const int32_t* der = okin_sec(pr, OKIN_S_DER);
+  const double* pos = sm + hdr[OKIN_H_OFF_POS];
+  const double* cst = sm + hdr[OKIN_H_OFF_CST];
+  const double* dblk = sm + hdr[OKIN_H_OFF_DBLK];
+  double* r = sm + hdr[OKIN_H_OFF_R];
+  double* rg = sm + hdr[OKIN_H_OFF_RG];
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  double sq = 0.0, mx = 0.0;
+  for (int t = lane; t < nrows; t += 32) {
+    const int32_t* rec = rows + t * OKIN_ROW_STRIDE;
+    const int fam = OKIN_LDG(rec + OKIN_R_FAM);
+    const double* c = cst + OKIN_LDG(rec + OKIN_R_CST);
+    double p[12], g[12];
+    int np = 0;
+    for (int s = 0; s < 4; ++s) {
+      const int pi = OKIN_LDG(rec + OKIN_R_P0 + s);
+      if (pi < 0) break;
+      p[3 * s] = pos[3 * pi]; p[3 * s + 1] = pos[3 * pi + 1]; p[3 * s + 2] = pos[3 * pi + 2];
+      np = s + 1;
+    }
+    const bool grad = with_grad && t < nls;
+    double res;
+    if (fam == OKIN_FAM_TARGET) {
+      res = c[0] * p[0] + c[1] * p[1] + c[2] * p[2] - (c[3] + tval[OKIN_LDG(rec + OKIN_R_AUX)]);
+      g[0] = c[0]; g[1] = c[1]; g[2] = c[2];
+    } else if (grad) {
+      res = okin_family_resgrad(fam, p, c, g);
+    } else {
+      res = okin_family_res(fam, p, c);
+    }
+    r[t] = res;
+    const double ar = fabs(res);
+    mx = ar > mx ? ar : mx;
+    if (t < nls) sq += res * res;
+    if (grad) {
+      double* out = rg + OKIN_LDG(rec + OKIN_R_RG);
+      const int neff = OKIN_LDG(rec + OKIN_R_NEFF);
+      for (int e = 0; e < 3 * neff; ++e) out[e] = 0.0;
+      for (int s = 0; s < np; ++s) {
+        const int m = OKIN_LDG(rec + OKIN_R_S0 + s);
+        if (m < 0) continue;
+        const double gx = g[3 * s], gy = g[3 * s + 1], gz = g[3 * s + 2];
+        if (m < OKIN_SLOT_DER) {
+          out[3 * m] += gx; out[3 * m + 1] += gy; out[3 * m + 2] += gz;
+        } else {
+          const int32_t* dd = der + (m - OKIN_SLOT_DER) * OKIN_DER_STRIDE;
+          const int nd = OKIN_LDG(dd);
+          for (int q = 0; q < nd; ++q) {
+            const double* B = dblk + OKIN_LDG(dd + 1 + 2 * q);
+            const int e = OKIN_LDG(dd + 2 + 2 * q);
+            out[3 * e] += gx * B[0] + gy * B[3] + gz * B[6];
+            out[3 * e + 1] += gx * B[1] + gy * B[4] + gz * B[7];
+            out[3 * e + 2] += gx * B[2] + gy * B[5] + gz * B[8];
+          }
+        }
+      }
+    }
+  }
+  red[lane] = sq;
+  red[32 + lane] = mx;
+  OKIN_PHASE_END
+  double f2 = 0.0, rmax = 0.0;
+  for (int k = 0; k < 32; ++k) {
+    f2 += red[k];
+    rmax = red[32 + k] > rmax ? red[32 + k] : rmax;
+  }
+  st.f2 = f2;
+  st.rmax = rmax;
+}
+
+// ---------------------------------------------------------------------------------------
+// Normal equations: A = J^T J (+ mu diag(A)) into the factor storage, g = J^T r into vec[0].
+// ---------------------------------------------------------------------------------------
+template <typename Dummy = void>
+OKIN_HD void okin_assemble(const OkinProgram& pr, double* sm, double mu) {
+  const int32_t* hdr = pr.hdr;
+  const int nat = hdr[OKIN_H_NAT];
+  const int n = 3 * hdr[OKIN_H_NF];
+  const int32_t* aptr = okin_sec(pr, OKIN_S_ASM_PTR);
+  const int32_t* adst = okin_sec(pr, OKIN_S_ASM_DST);
+  const int32_t* acon = okin_sec(pr, OKIN_S_ASM_CON);
+  const int32_t* gptr = okin_sec(pr, OKIN_S_G_PTR);
+  const int32_t* gcon = okin_sec(pr, OKIN_S_G_CON);
+  const double* rg = sm + hdr[OKIN_H_OFF_RG];
+  const double* r = sm + hdr[OKIN_H_OFF_R];
+  double* Lb = sm + hdr[OKIN_H_OFF_LB];
+  double* vec = sm + hdr[OKIN_H_OFF_VEC];
+  const double damp = 1.0 + mu;
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < nat + n; t += 32) {
+    if (t < nat) {
+      const int b = OKIN_LDG(aptr + t), e = OKIN_LDG(aptr + t + 1);
+      double acc = 0.0;
+      for (int q = b; q < e; ++q) {
+        const uint32_t w = (uint32_t)OKIN_LDG(acon + q);
+        acc = fma(rg[w >> 16], rg[w & 0xffffu], acc);
+      }
+      const int dst = OKIN_LDG(adst + t);
+      if (dst & OKIN_ASM_DIAG) acc *= damp;
+      Lb[dst & ~OKIN_ASM_DIAG] = acc;
+    } else {
+      const int u = t - nat;
+      const int b = OKIN_LDG(gptr + u), e = OKIN_LDG(gptr + u + 1);
+      double acc = 0.0;
+      for (int q = b; q < e; ++q) {
+        const uint32_t w = (uint32_t)OKIN_LDG(gcon + q);
+        acc = fma(rg[w >> 16], r[w & 0xffffu], acc);
+      }
+      vec[u] = -acc;  // right-hand side of A h = -g
+    }
+  }
+  OKIN_PHASE_END
+}
+
+// ---------------------------------------------------------------------------------------
+// 3x3-block sparse Cholesky, left-looking, level-scheduled over the elimination tree.
+// Dfac[j] = {l00,l10,l11,l20,l21,l22, 1/l00, 1/l11, 1/l22}.
+// ---------------------------------------------------------------------------------------
+OKIN_HD bool okin_chol3(const double* d, double f[9]) {
+  // d: 3x3 row-major block, lower part valid.
+  const double d00 = d[0], d10 = d[3], d11 = d[4], d20 = d[6], d21 = d[7], d22 = d[8];
+  const double i00 = OKIN_RSQRT(d00);
+  const double l00 = d00 * i00, l10 = d10 * i00, l20 = d20 * i00;
+  const double t11 = d11 - l10 * l10;
+  const double i11 = OKIN_RSQRT(t11);
+  const double l11 = t11 * i11;
+  const double l21 = (d21 - l20 * l10) * i11;
+  const double t22 = d22 - l20 * l20 - l21 * l21;
+  const double i22 = OKIN_RSQRT(t22);
+  const double l22 = t22 * i22;
+  f[0] = l00; f[1] = l10; f[2] = l11; f[3] = l20; f[4] = l21; f[5] = l22; f[6] = i00; f[7] = i11; f[8] = i22;
+  return d00 > 0.0 && t11 > 0.0 && t22 > 0.0;
+}
+
+template <typename Dummy = void>
+OKIN_HD void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
+  const int32_t* hdr = pr.hdr;
+  const int nlev = hdr[OKIN_H_NLEV];
+  const int32_t* lev_upd = okin_sec(pr, OKIN_S_LEV_UPD);
+  const int32_t* udst = okin_sec(pr, OKIN_S_UPD_DST);
+  const int32_t* uptr = okin_sec(pr, OKIN_S_UPD_PTR);
+  const int32_t* ucon = okin_sec(pr, OKIN_S_UPD_CON);
+  const int32_t* lev_scl = okin_sec(pr, OKIN_S_LEV_SCL);
+  const int32_t* scl = okin_sec(pr, OKIN_S_SCL);
+  double* Lb = sm + hdr[OKIN_H_OFF_LB];
+  double* Df = sm + hdr[OKIN_H_OFF_DFAC];
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  red[lane] = 0.0;
+  OKIN_PHASE_END
+  for (int lv = 0; lv < nlev; ++lv) {
+    const int ub = OKIN_LDG(lev_upd + lv), ue = OKIN_LDG(lev_upd + lv + 1);
+    if (ue > ub) {
+      OKIN_PHASE_BEGIN
+      for (int t = ub + lane; t < ue; t += 32) {
+        const int b = OKIN_LDG(uptr + t), e = OKIN_LDG(uptr + t + 1);
+        const int dst = OKIN_LDG(udst + t);
+        double acc = Lb[dst];
+        for (int q = b; q < e; ++q) {
+          const uint32_t w = (uint32_t)OKIN_LDG(ucon + q);
+          const double* x = Lb + (w >> 16);
+          const double* y = Lb + (w & 0xffffu);
+          acc -= x[0] * y[0] + x[1] * y[1] + x[2] * y[2];
+        }
+        Lb[dst] = acc;
+      }
+      OKIN_PHASE_END
+    }
+    const int sb = OKIN_LDG(lev_scl + lv), se = OKIN_LDG(lev_scl + lv + 1);
+    OKIN_PHASE_BEGIN
+    for (int t = sb + lane; t < se; t += 32) {
+      const int32_t* rec = scl + 4 * t;
+      const int j = OKIN_LDG(rec + 0), doff = OKIN_LDG(rec + 1), roff = OKIN_LDG(rec + 2);
+      double f[9];
+      const bool ok = okin_chol3(Lb + doff, f);
+      if (roff < 0) {
+        double* o = Df + 9 * j;
+        for (int k = 0; k < 9; ++k) o[k] = f[k];
+        if (!ok) red[lane] = 1.0;
+      } else {
+        double* b = Lb + roff;
+        const double x0 = b[0] * f[6];
+        const double x1 = (b[1] - x0 * f[1]) * f[7];
+        const double x2 = (b[2] - x0 * f[3] - x1 * f[4]) * f[8];
+        b[0] = x0; b[1] = x1; b[2] = x2;
+      }
+    }
+    OKIN_PHASE_END
+  }
+  double bad = 0.0;
+  for (int k = 0; k < 32; ++k) bad += red[k];
+  st.notpd = bad != 0.0;
+}
+
+// Solve A X = B for nrhs right-hand sides stored at vec[first .. first+nrhs) (elimination order),
+// in place.
+template <typename Dummy = void>
+OKIN_HD void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs) {
+  const int32_t* hdr = pr.hdr;
+  const int nlev = hdr[OKIN_H_NLEV];
+  const int n = 3 * hdr[OKIN_H_NF];
+  const int32_t* lcp = okin_sec(pr, OKIN_S_LEV_COL_PTR);
+  const int32_t* lcol = okin_sec(pr, OKIN_S_LEV_COL);
+  const int32_t* fptr = okin_sec(pr, OKIN_S_FW_PTR);
+  const int32_t* fcon = okin_sec(pr, OKIN_S_FW_CON);
+  const int32_t* bptr = okin_sec(pr, OKIN_S_BW_PTR);
+  const int32_t* bcon = okin_sec(pr, OKIN_S_BW_CON);
+  const double* Lb = sm + hdr[OKIN_H_OFF_LB];
+  const double* Df = sm + hdr[OKIN_H_OFF_DFAC];
+  double* vec = sm + hdr[OKIN_H_OFF_VEC] + first * n;
+  for (int lv = 0; lv < nlev; ++lv) {  // L y = b
+    const int cb = OKIN_LDG(lcp + lv), ce = OKIN_LDG(lcp + lv + 1);
+    OKIN_PHASE_BEGIN
+    for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
+      const int j = OKIN_LDG(lcol + cb + t / nrhs);
+      double* v = vec + (t % nrhs) * n;
+      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2];
+      for (int q = OKIN_LDG(fptr + j); q < OKIN_LDG(fptr + j + 1); ++q) {
+        const uint32_t w = (uint32_t)OKIN_LDG(fcon + q);
+        const double* B = Lb + (w >> 16);
+        const double* y = v + (w & 0xffffu);
+        t0 -= B[0] * y[0] + B[1] * y[1] + B[2] * y[2];
+        t1 -= B[3] * y[0] + B[4] * y[1] + B[5] * y[2];
+        t2 -= B[6] * y[0] + B[7] * y[1] + B[8] * y[2];
+      }
+      const double* f = Df + 9 * j;
+      const double y0 = t0 * f[6];
+      const double y1 = (t1 - f[1] * y0) * f[7];
+      const double y2 = (t2 - f[3] * y0 - f[4] * y1) * f[8];
+      v[3 * j] = y0; v[3 * j + 1] = y1; v[3 * j + 2] = y2;
+    }
+    OKIN_PHASE_END
+  }
+  for (int lv = nlev - 1; lv >= 0; --lv) {  // L^T x = y
+    const int cb = OKIN_LDG(lcp + lv), ce = OKIN_LDG(lcp + lv + 1);
+    OKIN_PHASE_BEGIN
+    for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
+      const int j = OKIN_LDG(lcol + cb + t / nrhs);
+      double* v = vec + (t % nrhs) * n;
+      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2];
+      for (int q = OKIN_LDG(bptr + j); q < OKIN_LDG(bptr + j + 1); ++q) {
+        const uint32_t w = (uint32_t)OKIN_LDG(bcon + q);
+        const double* B = Lb + (w >> 16);
+        const double* x = v + (w & 0xffffu);
+        t0 -= B[0] * x[0] + B[3] * x[1] + B[6] * x[2];
+        t1 -= B[1] * x[0] + B[4] * x[1] + B[7] * x[2];
+        t2 -= B[2] * x[0] + B[5] * x[1] + B[8] * x[2];
+      }
+      const double* f = Df + 9 * j;
+      const double x2 = t2 * f[8];
+      const double x1 = (t1 - f[4] * x2) * f[7];
+      const double x0 = (t0 - f[1] * x1 - f[3] * x2) * f[6];
+      v[3 * j] = x0; v[3 * j + 1] = x1; v[3 * j + 2] = x2;
+    }
+    OKIN_PHASE_END
+  }
+}
+
+// pos[free] += scale * vec[which]; returns max|vec[which]| (warp-uniform).
+template <typename Dummy = void>
+OKIN_HD double okin_apply_step(const OkinProgram& pr, double* sm, int which, double scale, bool save) {
+  const int32_t* hdr = pr.hdr;
+  const int n = 3 * hdr[OKIN_H_NF];
+  const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
+  double* pos = sm + hdr[OKIN_H_OFF_POS];
+  const double* v = sm + hdr[OKIN_H_OFF_VEC] + which * n;
+  double* xs = sm + hdr[OKIN_H_OFF_XSAVE];
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  double mx = 0.0;
+  for (int u = lane; u < n; u += 32) {
+    const int idx = 3 * OKIN_LDG(ep + u / 3) + u % 3;
+    const double x = pos[idx];
+    if (save) xs[u] = x;
+    const double h = v[u];
+    pos[idx] = x + scale * h;
+    const double ah = fabs(h);
+    mx = ah > mx ? ah : mx;
+  }
+  red[lane] = mx;
+  OKIN_PHASE_END
+  double hmax = 0.0;
+  for (int k = 0; k < 32; ++k) hmax = red[k] > hmax ? red[k] : hmax;
+  return hmax;
+}
+
+template <typename Dummy = void>
+OKIN_HD void okin_restore(const OkinProgram& pr, double* sm) {
+  const int32_t* hdr = pr.hdr;
+  const int n = 3 * hdr[OKIN_H_NF];
+  const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
+  double* pos = sm + hdr[OKIN_H_OFF_POS];
+  const double* xs = sm + hdr[OKIN_H_OFF_XSAVE];
+  OKIN_PHASE_BEGIN
+  for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(ep + u / 3) + u % 3] = xs[u];
+  OKIN_PHASE_END
+}
+
+// ---------------------------------------------------------------------------------------
+// One sweep step: Gauss-Newton on the pinned least-squares system, Marquardt damping only
+// after a step that fails to reduce ||r||^2.  Returns the number of residual evaluations
+// (the SolverInfo.nfev analogue); converged is set when max|dx| <= step_tol.
+// On return r[] holds the residuals at the final point and the factor storage holds the
+// Cholesky factor of the last (undamped, whenever possible) normal matrix.
+// ---------------------------------------------------------------------------------------
+template <typename Dummy = void>
+OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tval, const OkinSolverCfg& cfg,
+                            OkinState& st, bool* converged) {
+  int nfev = 0;
+  st.mu = 0.0;
+  double nu = 2.0;
+  okin_eval_rows(pr, sm, tval, true, st);
+  ++nfev;
+  *converged = false;
+  for (int it = 0; it < cfg.max_iter; ++it) {
+    okin_assemble(pr, sm, st.mu);
+    okin_factor(pr, sm, st);
+    if (st.notpd) {  // rank-deficient normal matrix: damp and retry from the same point
+      st.mu = st.mu > 0.0 ? st.mu * 10.0 : cfg.mu_init;
+      if (st.mu > 1e12) break;
+      continue;
+    }
+    okin_solve(pr, sm, 0, 1);
+    const double hmax = okin_apply_step(pr, sm, 0, 1.0, true);
+    if (!(hmax == hmax)) {  // NaN step: invalid geometry
+      okin_restore(pr, sm);
+      break;
+    }
+    if (hmax <= cfg.step_tol && st.mu == 0.0) {
+      okin_eval_rows(pr, sm, tval, false, st);
+      ++nfev;
+      *converged = true;
+      break;
+    }
+    const double f2_old = st.f2;
+    okin_eval_rows(pr, sm, tval, true, st);
+    ++nfev;
+    if (hmax <= cfg.step_tol) {
+      // Tiny step under damping: drop the damping and let a pure Gauss-Newton step confirm.
+      st.mu = 0.0;
+      nu = 2.0;
+    } else if (st.f2 <= f2_old * (1.0 + 1e-12) + 1e-300) {
+      // Accepted; relax the damping towards pure Gauss-Newton.
+      if (st.mu > 0.0) {
+        st.mu *= (1.0 / 3.0);
+        if (st.mu < 1e-10) st.mu = 0.0;
+      }
+      nu = 2.0;
+    } else {
+      okin_restore(pr, sm);
+      okin_eval_rows(pr, sm, tval, true, st);
+      ++nfev;
+      st.mu = st.mu > 0.0 ? st.mu * nu : cfg.mu_init;
+      nu *= 2.0;
+      if (st.mu > 1e12) break;
+    }
+  }
+  return nfev;
+}
+
+// Tangents dq/dt_j = A^{-1} J_target_j^T for every target (sensitivity.py:89-101 solved through
+// the normal equations; with full column rank lstsq(J, e_j) == (J^T J)^{-1} J^T e_j).
+// Requires rg[] / factor from an undamped linearisation at (numerically) the solution.
+template <typename Dummy = void>
+OKIN_HD void okin_tangents(const OkinProgram& pr, double* sm) {
+  const int32_t* hdr = pr.hdr;
+  const int nt = hdr[OKIN_H_NT];
+  const int n = 3 * hdr[OKIN_H_NF];
+  const int32_t* sptr = okin_sec(pr, OKIN_S_TGT_SC_PTR);
+  const int32_t* sc = okin_sec(pr, OKIN_S_TGT_SC);
+  const double* rg = sm + hdr[OKIN_H_OFF_RG];
+  double* vec = sm + hdr[OKIN_H_OFF_VEC] + n;
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < nt * n; t += 32) vec[t] = 0.0;
+  OKIN_PHASE_END
+  OKIN_PHASE_BEGIN
+  for (int j = 0; j < nt; ++j)
+    for (int q = OKIN_LDG(sptr + j) + lane; q < OKIN_LDG(sptr + j + 1); q += 32) {
+      const uint32_t w = (uint32_t)OKIN_LDG(sc + q);
+      vec[j * n + (w & 0xffffu)] = rg[w >> 16];
+    }
+  OKIN_PHASE_END
+  okin_solve(pr, sm, 1, nt);
+}
+
+struct OkinOutputs {
+  double* positions;      // [n_steps][NOUT*3] or null
+  int32_t* iters;         // [n_steps] or null
+  double* max_residual;   // [n_steps] or null
+  double* tangents;       // [n_steps][NT][3*NF] (reference column order) or null
+  int32_t* status;        // [1]
+  int32_t* failed_step;   // [1]
+};
+
+// Whole sweep for one instance (solver.py:716-774).  tvals: [NT][n_steps] relative/absolute
+// sweep values shared by all instances of the launch.
+template <typename Dummy = void>
+OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints,
+                        const double* __restrict__ tvals, int n_steps, const OkinSolverCfg& cfg,
+                        const OkinOutputs& out) {
+  const int32_t* hdr = pr.hdr;
+  const int nt = hdr[OKIN_H_NT];
+  const int n = 3 * hdr[OKIN_H_NF];
+  const int nout = hdr[OKIN_H_NOUT];
+  const int32_t* out_point = okin_sec(pr, OKIN_S_OUT_POINT);
+  const int32_t* ecol = okin_sec(pr, OKIN_S_ELIM_COL);
+  double* pos = sm + hdr[OKIN_H_OFF_POS];
+  double* vec = sm + hdr[OKIN_H_OFF_VEC];
+  okin_setup(pr, sm, hardpoints);
+
+  OkinState st;
+  st.f2 = 0.0; st.rmax = 0.0; st.mu = 0.0; st.notpd = 0;
+  int status = OKIN_STATUS_OK, failed = -1;
+  double tcur[OKIN_MAX_TARGETS], tprev[OKIN_MAX_TARGETS];
+  for (int j = 0; j < OKIN_MAX_TARGETS; ++j) { tcur[j] = 0.0; tprev[j] = 0.0; }
+  bool have_tangent = false;
+
+  for (int s = 0; s < n_steps; ++s) {
+    if (status == OKIN_STATUS_OK) {
+      for (int j = 0; j < nt; ++j) { tprev[j] = tcur[j]; tcur[j] = OKIN_LDG(tvals + j * n_steps + s); }
+      if (cfg.use_predictor && have_tangent) {
+        for (int j = 0; j < nt; ++j) {
+          const double dt = tcur[j] - tprev[j];
+          if (dt != 0.0) okin_apply_step(pr, sm, 1 + j, dt, false);
+        }
+      }
+      bool conv = false;
+      const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv);
+      const bool valid = st.rmax == st.rmax;
+      if (!conv || !valid) {
+        status = valid ? OKIN_STATUS_NOT_CONVERGED : OKIN_STATUS_INVALID_GEOMETRY;
+        failed = s;
+      } else if (st.rmax > cfg.residual_tol) {
+        status = OKIN_STATUS_RESIDUAL_REJECTED;
+        failed = s;
+      }
+      OKIN_PHASE_BEGIN
+      if (lane == 0) {
+        if (out.iters) out.iters[s] = nfev;
+        if (out.max_residual) out.max_residual[s] = st.rmax;
+      }
+      OKIN_PHASE_END
+      if (status == OKIN_STATUS_OK) {
+        okin_derived_update(pr, sm, false);
+        okin_tangents(pr, sm);
+        have_tangent = true;
+      }
+    } else {
+      OKIN_PHASE_BEGIN
+      if (lane == 0) {
+        if (out.iters) out.iters[s] = 0;
+        if (out.max_residual) out.max_residual[s] = NAN;
+      }
+      OKIN_PHASE_END
+    }
+    const bool ok = status == OKIN_STATUS_OK;
+    if (out.positions) {
+      double* dst = out.positions + (size_t)s * 3 * nout;
+      OKIN_PHASE_BEGIN
+      for (int t = lane; t < 3 * nout; t += 32)
+        dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
+      OKIN_PHASE_END
+    }
+    if (out.tangents) {
+      double* dst = out.tangents + (size_t)s * nt * n;
+      OKIN_PHASE_BEGIN
+      for (int t = lane; t < nt * n; t += 32) {
+        const int j = t / n, u = t % n;  // u: elimination-ordered unknown
+        dst[j * n + 3 * OKIN_LDG(ecol + u / 3) + u % 3] = ok ? vec[n + j * n + u] : NAN;
+      }
+      OKIN_PHASE_END
+    }
+  }
+  OKIN_PHASE_BEGIN
+  if (lane == 0) {
+    out.status[0] = status;
+    out.failed_step[0] = failed;
+  }
+  OKIN_PHASE_END
+}

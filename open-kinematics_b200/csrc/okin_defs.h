@@ -1,0 +1,163 @@
+// Shared definitions of the device core, the C ABI and (by value) core/topology.py.
+// Plain C so that include/okin.h users and the g++ lane-emulation test harness can
+// include it too.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OKIN_HD __host__ __device__ __forceinline__
+#else
+#define OKIN_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define OKIN_RSQRT(x) rsqrt(x)
+#else
+#define OKIN_RSQRT(x) (1.0 / sqrt(x))
+#endif
+
+// softnorm(s) = sqrt(s + EPS_SQ) - EPS   (reference core/primitives/soft_math.py:16-27)
+#define OKIN_EPS 1e-6
+#define OKIN_EPS_SQ 1e-12
+
+// Constraint-family codes (order = FAMILIES in tools/generate_jacobians.py).
+#define OKIN_FAM_DISTANCE 0
+#define OKIN_FAM_SPHERICAL 1
+#define OKIN_FAM_ANGLE 2
+#define OKIN_FAM_THREE_POINT_ANGLE 3
+#define OKIN_FAM_VECTORS_PARALLEL 4
+#define OKIN_FAM_VECTORS_PERPENDICULAR 5
+#define OKIN_FAM_EQUAL_DISTANCE 6
+#define OKIN_FAM_POINT_ON_LINE 7
+#define OKIN_FAM_LINEAR_POINT 8
+#define OKIN_FAM_MIDPOINT_ON_PLANE 9
+#define OKIN_FAM_COPLANAR 10
+#define OKIN_FAM_SCALAR_TRIPLE 11
+// Sweep-target row: dir.p - value(step); c = [dir(3), base] with value = base + sweep value.
+#define OKIN_FAM_TARGET 12
+
+// Point kinds.
+#define OKIN_PT_FIXED 0
+#define OKIN_PT_FREE 1
+#define OKIN_PT_DERIVED 2
+
+// Derived-point ops (reference core/points/derived/definitions.py:24-180).
+#define OKIN_DOP_MIDPOINT 1      // out = a + (b - a)/2
+#define OKIN_DOP_ALONG_LINE 2    // out = a + unit(b - a) * param
+#define OKIN_DOP_CONTACT_PATCH 3 // out = a + unit(down - (down.u)u) * param, u = unit(c - b), down = -Z
+
+// Parameter modes of a derived op.
+#define OKIN_PAR_SHARED 0            // value from the topology
+#define OKIN_PAR_DESIGN_PROJECTION 1 // dot(authored_out - a, unit(b - a)) at the design pose
+
+// Per-row design-constant rules evaluated once per instance (setup phase).
+#define OKIN_RULE_EXPLICIT 0     // constants come from the topology (cst_init)
+#define OKIN_RULE_DESIGN_VALUE 1 // family's own quantity at the design pose (length, angle, volume)
+#define OKIN_RULE_DESIGN_POINT 2 // c[0..2] = design position of the row's point (line / pin anchor)
+#define OKIN_RULE_TARGET_BASE 3  // c[3] = dir . design position (relative target), else 0
+
+// Per-instance status (okin_solve_batch status_out).
+#define OKIN_STATUS_OK 0
+#define OKIN_STATUS_NOT_CONVERGED 1
+#define OKIN_STATUS_RESIDUAL_REJECTED 2
+#define OKIN_STATUS_INVALID_GEOMETRY 3
+
+// ---------------------------------------------------------------------------
+// Compiled topology program = int32 header + one int32 blob + one double blob.
+// hdr[0 .. OKIN_H_SEC0)            counts and shared-memory offsets (enum below)
+// hdr[OKIN_H_SEC0 + 2*s, +1]       (offset, length) of int32 section s in the int blob
+// hdr[OKIN_H_FSEC0 + 2*s, +1]      (offset, length) of double section s in the double blob
+// ---------------------------------------------------------------------------
+enum okin_hdr_slot {
+  OKIN_H_MAGIC = 0,
+  OKIN_H_P,        // points
+  OKIN_H_NF,       // free points (unknowns = 3*NF)
+  OKIN_H_NIN,      // input points per instance
+  OKIN_H_NDOP,     // derived ops
+  OKIN_H_NPAR,     // derived-op parameters
+  OKIN_H_NROW,     // least-squares rows (constraints with pins, then targets)
+  OKIN_H_NREP,     // report-only rows (original point-on-line residuals), stored after the LS rows
+  OKIN_H_NT,       // targets
+  OKIN_H_NCST,     // per-instance constants (doubles)
+  OKIN_H_NRG,      // row-gradient storage (doubles)
+  OKIN_H_NAD,      // derived-Jacobian column tasks
+  OKIN_H_NDB,      // derived-Jacobian block storage (doubles)
+  OKIN_H_NB,       // factor blocks (3x3)
+  OKIN_H_NLEV,     // elimination-tree levels
+  OKIN_H_NAT,      // assembly tasks (scalar entries of A)
+  OKIN_H_NOUT,     // output points
+  OKIN_H_TROW0,    // first target row
+  // shared-memory layout (offsets in doubles from the instance's base)
+  OKIN_H_OFF_POS, OKIN_H_OFF_CST, OKIN_H_OFF_R, OKIN_H_OFF_RG, OKIN_H_OFF_DBLK, OKIN_H_OFF_LB,
+  OKIN_H_OFF_DFAC, OKIN_H_OFF_VEC, OKIN_H_OFF_XSAVE, OKIN_H_OFF_RED, OKIN_H_OFF_PAR,
+  OKIN_H_SMEM_DOUBLES, // shared-memory doubles per instance
+  OKIN_H_SEC0 = 32,
+  OKIN_H_FSEC0 = 32 + 2 * 40,
+  OKIN_HDR_SIZE = 32 + 2 * 40 + 2 * 4
+};
+#define OKIN_MAGIC 0x4f4b494e  // "OKIN"
+
+// int32 sections
+enum okin_isec {
+  OKIN_S_POINT_KIND = 0, // [P]
+  OKIN_S_IN_POINT,       // [NIN] input slot -> point
+  OKIN_S_DOP,            // [NDOP][OKIN_DOP_STRIDE]
+  OKIN_S_PAR_MODE,       // [NPAR]
+  OKIN_S_ADJ,            // [NAD][OKIN_ADJ_STRIDE]
+  OKIN_S_ADJ_CHAIN,      // derived-op indices, referenced by ADJ
+  OKIN_S_ROW,            // [NROW+NREP][OKIN_ROW_STRIDE]
+  OKIN_S_DER,            // [..][OKIN_DER_STRIDE]
+  OKIN_S_ASM_PTR,        // [NAT+1]
+  OKIN_S_ASM_DST,        // [NAT] Lb offset | OKIN_ASM_DIAG flag
+  OKIN_S_ASM_CON,        // (ia << 16) | ib  into rg[]
+  OKIN_S_G_PTR,          // [3*NF+1]  (elimination-ordered unknowns)
+  OKIN_S_G_CON,          // (irg << 16) | row
+  OKIN_S_LEV_UPD,        // [NLEV+1] ranges into UPD_DST/UPD_PTR
+  OKIN_S_UPD_DST,        // Lb offset of the entry
+  OKIN_S_UPD_PTR,        // [n_upd+1]
+  OKIN_S_UPD_CON,        // (offA << 16) | offB : sum_t Lb[offA+t]*Lb[offB+t], t<3
+  OKIN_S_LEV_SCL,        // [NLEV+1] ranges into SCL
+  OKIN_S_SCL,            // [..][4] = {elim col j, diag Lb offset, row Lb offset or -1 (write Dfac), 0}
+  OKIN_S_LEV_COL_PTR,    // [NLEV+1]
+  OKIN_S_LEV_COL,        // elimination columns of each level
+  OKIN_S_FW_PTR,         // [NF+1]
+  OKIN_S_FW_CON,         // (Lb block offset << 16) | (3*K)
+  OKIN_S_BW_PTR,         // [NF+1]
+  OKIN_S_BW_CON,         // (Lb block offset << 16) | (3*I)
+  OKIN_S_ELIM_POINT,     // [NF] elimination position -> point index
+  OKIN_S_ELIM_COL,       // [NF] elimination position -> reference column block (sorted free-point order)
+  OKIN_S_TGT_SC_PTR,     // [NT+1]
+  OKIN_S_TGT_SC,         // (rg index << 16) | unknown index (elimination order)
+  OKIN_S_OUT_POINT,      // [NOUT]
+  OKIN_S_SETUP_PT,       // points whose design position feeds OKIN_RULE_* (unused, reserved)
+  OKIN_S_COUNT
+};
+#define OKIN_ASM_DIAG 0x40000000
+
+// double sections
+enum okin_fsec { OKIN_F_PAR_VAL = 0, OKIN_F_CST_INIT, OKIN_F_COUNT };
+
+// Row record: int32[OKIN_ROW_STRIDE]
+enum okin_row_slot {
+  OKIN_R_FAM = 0,
+  OKIN_R_P0, OKIN_R_P1, OKIN_R_P2, OKIN_R_P3, // point indices (-1 unused)
+  OKIN_R_CST,   // offset of the row's constants in cst[]
+  OKIN_R_RG,    // offset of the row's effective-gradient storage in rg[]
+  OKIN_R_NEFF,  // number of effective free blocks
+  OKIN_R_RULE,  // design-constant rule
+  OKIN_R_S0, OKIN_R_S1, OKIN_R_S2, OKIN_R_S3, // slot map: -1 none, <OKIN_SLOT_DER direct eff index, else derived descriptor
+  OKIN_R_AUX,   // target index for target rows
+  OKIN_ROW_STRIDE = 16
+};
+#define OKIN_SLOT_DER 64
+
+// Derived-slot descriptor: int32[8] = {ndeps, dblk_off0, eff0, dblk_off1, eff1, dblk_off2, eff2, 0}
+#define OKIN_DER_STRIDE 8
+// Derived op record: int32[8] = {op, out, a, b, c, par, authored_input_slot, 0}
+#define OKIN_DOP_STRIDE 8
+// Derived-Jacobian column task: int32[8] = {D, B, comp, dblk_off, chain_begin, chain_end, 0, 0}
+#define OKIN_ADJ_STRIDE 8
+#define OKIN_MAX_CHAIN 4
+#define OKIN_MAX_TARGETS 4

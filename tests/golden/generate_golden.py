@@ -1,0 +1,312 @@
+#!/usr/bin/env python3
+"""Generate golden vectors by running the *reference itself* (nickmccleery/open-kinematics,
+mounted read-only at /root/reference in the build container).
+
+    PYTHONPATH=/root/reference/src python tests/golden/generate_golden.py
+
+Writes ``tests/golden/<case>.json`` (inputs + structure) and ``<case>.npz`` (arrays).  The GPU
+box has no /root/reference, so tests only ever read these files.  Nothing here imports the
+product package or the oracle.
+
+Per sweep case:
+  positions_tight    reference solve with SolverConfig(ftol=xtol=gtol=1e-15)   [S, P, 3]
+  positions_default  reference solve with default tolerances                    [S, P, 3]
+  nfev_*, max_residual_*                                                        [S]
+  tangents           compute_state_tangents at the tight states                 [S, T, n]
+  tangent_rank / tangent_sigma_min / tangent_cond                               [S]
+Per family: residual + jacobian rows at seeded random points (core/constraints.py, core/jacobians.py).
+Failure cases: first failed step and failure class for out-of-reach sweeps.
+"""
+
+from __future__ import annotations
+
+import copy
+import json
+import os
+import sys
+
+import numpy as np
+import yaml
+
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(REF, "src"))
+
+from kinematics.core import constraints as C  # noqa: E402
+from kinematics.core import jacobians as JAC  # noqa: E402
+from kinematics.core.enums import Axis, PointID  # noqa: E402
+from kinematics.core.input import build_suspension, build_sweep  # noqa: E402
+from kinematics.core.points.derived.manager import DerivedPointsManager  # noqa: E402
+from kinematics.core.primitives.geometry import Direction3, Point3  # noqa: E402
+from kinematics.core.sensitivity import compute_state_tangents  # noqa: E402
+from kinematics.core.solver import (  # noqa: E402
+    ResidualComputer, SolverConfig, convert_targets_to_absolute, solve_suspension_sweep,
+)
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+TIGHT = SolverConfig(ftol=1e-15, xtol=1e-15, gtol=1e-15)
+
+
+def key_name(k) -> str:
+    return k.name.lower()
+
+
+def load(path):
+    return yaml.safe_load(open(os.path.join(REF, path)))
+
+
+def add_coilovers(geom: dict) -> dict:
+    """BASELINE config 3: the shipped rocker/U-bar axle with coilovers."""
+    g = copy.deepcopy(geom)
+    g["axle_config"]["spring"] = {"type": "coilover"}
+    g["hardpoints"]["left"]["strut_top"] = {"x": 0, "y": 200, "z": 600}
+    g["hardpoints"]["left"]["strut_bottom"] = {"x": 0, "y": 330, "z": 520}
+    return g
+
+
+def roll_sweep(steps: int, amp: float) -> dict:
+    return {"version": 1, "steps": steps, "targets": [
+        {"point": "wheel_center", "side": "left", "direction": {"axis": "z"}, "mode": "relative", "start": -amp, "stop": amp},
+        {"point": "wheel_center", "side": "right", "direction": {"axis": "z"}, "mode": "relative", "start": amp, "stop": -amp},
+        {"point": "trackrod_inboard", "side": "left", "direction": {"axis": "y"}, "mode": "relative", "start": 0, "stop": 0},
+    ]}
+
+
+def bump_sweep(steps: int, lo: float, hi: float) -> dict:
+    return {"version": 1, "steps": steps, "targets": [
+        {"point": "trackrod_inboard", "direction": {"axis": "y"}, "mode": "relative", "start": 0, "stop": 0},
+        {"point": "wheel_center", "direction": {"axis": "z"}, "mode": "relative", "start": lo, "stop": hi}]}
+
+
+CASES = {
+    # BASELINE.json configs[0]
+    "c1_dw_corner_bump": (load("tests/data/geometry.yaml"), load("scripts/bump_sweep.yaml")),
+    # e2e golden sweep of the reference (tests/data/sweep.yaml: bump + steer)
+    "c1_dw_corner_bump_steer": (load("tests/data/geometry.yaml"), load("tests/data/sweep.yaml")),
+    # configs[1] topology
+    "c2_macpherson_bump_steer": (load("tests/data/macpherson_geometry.yaml"), load("tests/data/sweep.yaml")),
+    # configs[2] as shipped and with coilovers (flagship)
+    "c3_rocker_ubar_roll_shipped": (load("tests/data/axle_geometry_rocker.yaml"), load("tests/data/axle_rocker_sweep.yaml")),
+    "c3_rocker_ubar_coilover_roll": (add_coilovers(load("tests/data/axle_geometry_rocker.yaml")), roll_sweep(21, 20.0)),
+    # configs[3] topology family
+    "c4_tbar_roll": (load("tests/data/axle_geometry_t_bar.yaml"), load("tests/data/axle_t_bar_roll_sweep.yaml")),
+    "c4_tbar_bump": (load("tests/data/axle_geometry_t_bar.yaml"), load("tests/data/axle_t_bar_bump_sweep.yaml")),
+    "dw_axle_direct": (load("tests/data/axle_geometry.yaml"), load("tests/data/axle_sweep.yaml")),
+    "macpherson_axle": (load("tests/data/macpherson_axle_geometry.yaml"), load("tests/data/axle_sweep.yaml")),
+    "dw_corner_coilover_direct": (load("tests/data/corner_strut_geometry.yaml"), load("scripts/bump_sweep.yaml")),
+    "dw_corner_rocker": (load("tests/data/corner_rocker_geometry.yaml"), bump_sweep(21, -40.0, 40.0)),
+}
+
+
+def describe_constraints(cons) -> list:
+    out = []
+    for c in cons:
+        rec = {"type": type(c).__name__, "points": [key_name(getattr(c, a)) for a in c._POINT_ATTRS]}
+        for attr in ("target_distance", "target_angle", "target_volume", "scale"):
+            if hasattr(c, attr):
+                rec[attr] = float(getattr(c, attr))
+        if isinstance(c, C.PointOnLineConstraint):
+            rec["line_point"] = c.line_point.data.tolist()
+            rec["line_direction"] = c.line_direction.data.tolist()
+        if isinstance(c, C.MidpointOnPlaneConstraint):
+            rec["plane_point"] = c.plane_point.data.tolist()
+            rec["plane_normal"] = c.plane_normal.data.tolist()
+        out.append(rec)
+    return out
+
+
+def positions_array(states, keys) -> np.ndarray:
+    return np.array([[st.positions[k].data for k in keys] for st in states])
+
+
+def run_case(name: str, geom: dict, sweep: dict, with_default=True) -> None:
+    sus = build_suspension(geom)
+    cfg = build_sweep(sweep, sus)
+    init = sus.initial_state()
+    cons = sus.constraints()
+    keys = sorted(init.positions)
+    arrays, meta = {}, {}
+    dm = DerivedPointsManager(sus.derived_spec())
+    states_t, stats_t = solve_suspension_sweep(init, cons, cfg, dm, TIGHT)
+    arrays["positions_tight"] = positions_array(states_t, keys)
+    arrays["nfev_tight"] = np.array([s.nfev for s in stats_t])
+    arrays["max_residual_tight"] = np.array([s.max_residual for s in stats_t])
+    if with_default:
+        states_d, stats_d = solve_suspension_sweep(init, cons, cfg, DerivedPointsManager(sus.derived_spec()))
+        arrays["positions_default"] = positions_array(states_d, keys)
+        arrays["nfev_default"] = np.array([s.nfev for s in stats_d])
+        arrays["max_residual_default"] = np.array([s.max_residual for s in stats_d])
+    tang, rank, smin, cond = [], [], [], []
+    for step, st in enumerate(states_t):
+        targets = convert_targets_to_absolute([sw[step] for sw in cfg.target_sweeps], init)
+        fields, info = compute_state_tangents(st, cons, dm, targets)
+        free = st.free_points_order
+        tang.append([np.concatenate([f.velocities[k] for k in free]) for f in fields])
+        rank.append(info.rank)
+        smin.append(info.smallest_singular_value)
+        cond.append(info.condition_number)
+    arrays["tangents"] = np.array(tang)
+    arrays["tangent_rank"] = np.array(rank)
+    arrays["tangent_sigma_min"] = np.array(smin)
+    arrays["tangent_cond"] = np.array(cond)
+    arrays["design_positions"] = np.array([init.positions[k].data for k in keys])
+    arrays["sweep_values"] = np.array([[t.value for t in sw] for sw in cfg.target_sweeps])
+    meta.update(
+        geometry=geom, sweep=sweep, point_keys=[key_name(k) for k in keys],
+        free_order=[key_name(k) for k in init.free_points_order],
+        output_points=[key_name(k) for k in sus.output_points()],
+        derived=[key_name(k) for k in dm.update_order],
+        constraints=describe_constraints(cons),
+        targets=[{"point": key_name(sw[0].point_id), "mode": str(sw[0].mode.value)} for sw in cfg.target_sweeps],
+        n_unknowns=3 * len(init.free_points_order), n_residuals=len(cons) + len(cfg.target_sweeps),
+    )
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+    json.dump(meta, open(os.path.join(OUT, name + ".json"), "w"), indent=1)
+    print(f"{name}: S={cfg.n_steps} P={len(keys)} n={meta['n_unknowns']} m={meta['n_residuals']} "
+          f"default-vs-tight {np.abs(arrays.get('positions_default', arrays['positions_tight']) - arrays['positions_tight']).max():.2e}")
+
+
+# --------------------------------------------------------------------------- perturbed batches
+def perturb_geometry(geom: dict, rng: np.random.Generator, sigma: float) -> dict:
+    """Gaussian perturbation of every authored hardpoint coordinate (left + centre for mirrored
+    axles).  MacPherson: strut_bottom is re-projected on the ball-joint -> strut-top line at its
+    nominal axial fraction."""
+    g = copy.deepcopy(geom)
+    blocks = [g["hardpoints"]] if "left" not in g["hardpoints"] else [
+        g["hardpoints"][side] for side in ("left", "right", "center") if g["hardpoints"].get(side)]
+    for block in blocks:
+        nominal = copy.deepcopy(block)
+        for name in sorted(block):
+            for ax in "xyz":
+                block[name][ax] = float(block[name][ax]) + float(rng.normal(0.0, sigma))
+        if g["type"] == "macpherson":
+            lbj0 = np.array([nominal["lower_wishbone_outboard"][a] for a in "xyz"], float)
+            top0 = np.array([nominal["strut_top"][a] for a in "xyz"], float)
+            sb0 = np.array([nominal["strut_bottom"][a] for a in "xyz"], float)
+            frac = float((sb0 - lbj0) @ (top0 - lbj0) / ((top0 - lbj0) @ (top0 - lbj0)))
+            lbj = np.array([block["lower_wishbone_outboard"][a] for a in "xyz"], float)
+            top = np.array([block["strut_top"][a] for a in "xyz"], float)
+            sb = lbj + frac * (top - lbj)
+            block["strut_bottom"] = {"x": float(sb[0]), "y": float(sb[1]), "z": float(sb[2])}
+    return g
+
+
+def run_batch(name: str, geom: dict, sweep: dict, n_inst: int, sigma: float, seed: int) -> None:
+    rng = np.random.default_rng(seed)
+    geoms, pos = [], []
+    for _ in range(n_inst):
+        gi = perturb_geometry(geom, rng, sigma)
+        sus = build_suspension(gi)
+        cfg = build_sweep(sweep, sus)
+        init = sus.initial_state()
+        keys = sorted(init.positions)
+        states, _ = solve_suspension_sweep(init, sus.constraints(), cfg, DerivedPointsManager(sus.derived_spec()), TIGHT)
+        pos.append(positions_array(states, keys))
+        geoms.append(gi)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), positions_tight=np.array(pos))
+    json.dump({"geometries": geoms, "sweep": sweep, "point_keys": [key_name(k) for k in keys],
+               "sigma": sigma, "seed": seed}, open(os.path.join(OUT, name + ".json"), "w"))
+    print(f"{name}: {n_inst} perturbed instances")
+
+
+# --------------------------------------------------------------------------- failure flags
+def first_failure(geom: dict, sweep: dict) -> dict:
+    """Run the reference; on RuntimeError report the failure class and the first failed step."""
+    sus = build_suspension(geom)
+    cfg = build_sweep(sweep, sus)
+    try:
+        solve_suspension_sweep(sus.initial_state(), sus.constraints(), cfg, DerivedPointsManager(sus.derived_spec()))
+        return {"status": 0, "failed_step": -1, "message": ""}
+    except RuntimeError as err:
+        msg = str(err)
+    if "acceptable residual" in msg:
+        return {"status": 2, "failed_step": int(msg.split("sweep step ")[1].split(" ")[0]), "message": msg[:300]}
+    # "Solver failed to converge" carries no step index: bisect over sweep prefixes.
+    values = [[t.value for t in sw] for sw in cfg.target_sweeps]
+    failed = -1
+    for k in range(1, cfg.n_steps + 1):
+        sub = copy.deepcopy(sweep)
+        sub.pop("steps", None)
+        for t, vals in zip(sub["targets"], values):
+            t.pop("start", None), t.pop("stop", None)
+            t["values"] = [float(v) for v in vals[:k]]
+        s2 = build_suspension(geom)
+        try:
+            solve_suspension_sweep(s2.initial_state(), s2.constraints(), build_sweep(sub, s2),
+                                   DerivedPointsManager(s2.derived_spec()))
+        except RuntimeError:
+            failed = k - 1
+            break
+    return {"status": 1, "failed_step": failed, "message": msg[:300]}
+
+
+def run_failures() -> None:
+    c1 = load("tests/data/geometry.yaml")
+    cases = {f"c1_bump_to_{stop:+.0f}": (c1, bump_sweep(41, 0.0, stop)) for stop in (-400.0, 400.0, 500.0, -600.0)}
+    cases["dw_corner_rocker_bump_-60_+80"] = (load("tests/data/corner_rocker_geometry.yaml"), load("scripts/bump_sweep.yaml"))
+    cases["c2_macpherson_bump_to_+400"] = (load("tests/data/macpherson_geometry.yaml"), bump_sweep(41, 0.0, 400.0))
+    out = {}
+    for label, (geom, sweep) in cases.items():
+        rec = first_failure(geom, sweep)
+        out[label] = {"geometry": geom, "sweep": sweep, **rec}
+        print(label, rec["status"], rec["failed_step"])
+    json.dump(out, open(os.path.join(OUT, "failures.json"), "w"), indent=1)
+
+
+# --------------------------------------------------------------------------- family vectors
+def run_families() -> None:
+    rng = np.random.default_rng(1234)
+    K = [PointID(i) for i in range(1, 5)]
+    recs = {}
+    n = 8
+    P = rng.normal(0, 100.0, size=(n, 4, 3))
+    L = rng.uniform(50, 200, size=n)
+    A = rng.uniform(0.2, 2.8, size=n)
+    lp, ld = rng.normal(0, 50, size=(n, 3)), rng.normal(0, 1, size=(n, 3))
+    ld /= np.linalg.norm(ld, axis=1)[:, None]
+
+    def pos(i, k):
+        return {K[j]: Point3(P[i, j]) for j in range(k)}
+
+    def run(fam, k, make, jac, consts):
+        res, grads = [], []
+        for i in range(n):
+            c = make(i)
+            res.append(c.residual(pos(i, k)))
+            grads.append(jac(i))
+        recs[fam] = {"points": P[:, :k].tolist(), "consts": consts, "residual": res,
+                     "jacobian": [np.asarray(g).reshape(k, 3).tolist() for g in grads]}
+
+    run("distance", 2, lambda i: C.DistanceConstraint(K[0], K[1], L[i]), lambda i: JAC.jac_distance(P[i, 0], P[i, 1]), [[v] for v in L])
+    run("spherical", 2, lambda i: C.SphericalJointConstraint(K[0], K[1]), lambda i: JAC.jac_distance(P[i, 0], P[i, 1]), [[] for _ in L])
+    run("angle", 4, lambda i: C.AngleConstraint(*K, A[i]), lambda i: JAC.jac_angle(*P[i]), [[v] for v in A])
+    run("three_point_angle", 3, lambda i: C.ThreePointAngleConstraint(*K[:3], A[i]), lambda i: JAC.jac_three_point_angle(*P[i, :3]), [[v] for v in A])
+    run("vectors_parallel", 4, lambda i: C.VectorsParallelConstraint(*K), lambda i: JAC.jac_vectors_parallel(*P[i]), [[] for _ in L])
+    run("vectors_perpendicular", 4, lambda i: C.VectorsPerpendicularConstraint(*K), lambda i: JAC.jac_vectors_perpendicular(*P[i]), [[] for _ in L])
+    run("equal_distance", 4, lambda i: C.EqualDistanceConstraint(*K), lambda i: JAC.jac_equal_distance(*P[i]), [[] for _ in L])
+    run("point_on_line", 1, lambda i: C.PointOnLineConstraint(K[0], Point3(lp[i]), Direction3(ld[i])),
+        lambda i: JAC.jac_point_on_line(P[i, 0], lp[i], ld[i]), [[*lp[i], *ld[i]] for i in range(n)])
+    run("linear_point", 1, lambda i: C.PointOnPlaneConstraint(K[0], Point3(lp[i]), Direction3(ld[i])),
+        lambda i: JAC.jac_point_on_plane(P[i, 0], lp[i], ld[i]), [[*lp[i], *ld[i]] for i in range(n)])
+    run("midpoint_on_plane", 2, lambda i: C.MidpointOnPlaneConstraint(K[0], K[1], Point3(lp[i]), Direction3(ld[i])),
+        lambda i: np.concatenate([ld[i] / 2, ld[i] / 2]), [[*lp[i], *ld[i]] for i in range(n)])
+    run("coplanar", 4, lambda i: C.CoplanarPointsConstraint(*K), lambda i: JAC.jac_coplanar(*P[i]), [[] for _ in L])
+    V = rng.normal(0, 1e5, size=n)
+    run("scalar_triple", 4, lambda i: C.ScalarTripleProductConstraint(*K, target_volume=V[i], scale=abs(V[i])),
+        lambda i: JAC.jac_coplanar(*P[i]) / abs(V[i]), [[V[i], 1.0 / abs(V[i])] for i in range(n)])
+    json.dump(recs, open(os.path.join(OUT, "families.json"), "w"))
+    print("families:", sorted(recs))
+
+
+if __name__ == "__main__":
+    only = set(sys.argv[1:])
+    for case, (g, s) in CASES.items():
+        if not only or case in only:
+            run_case(case, g, s)
+    if not only or "batches" in only:
+        run_batch("batch_c1", *CASES["c1_dw_corner_bump"], n_inst=6, sigma=0.5, seed=1)
+        run_batch("batch_c2", *CASES["c2_macpherson_bump_steer"], n_inst=6, sigma=0.5, seed=2)
+        run_batch("batch_c3", *CASES["c3_rocker_ubar_coilover_roll"], n_inst=4, sigma=0.5, seed=3)
+    if not only or "failures" in only:
+        run_failures()
+    if not only or "families" in only:
+        run_families()

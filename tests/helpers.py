@@ -1,0 +1,169 @@
+"""Shared test helpers: golden loading, product-model -> oracle-problem adapter,
+lane-emulation build of the device core."""
+
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+from open_kinematics_b200.core import constraints as PC  # noqa: E402
+from open_kinematics_b200.core.enums import PointID  # noqa: E402
+from open_kinematics_b200.core.input import build_suspension, build_sweep  # noqa: E402
+from open_kinematics_b200.core.primitives.point_ref import PointRef, Side  # noqa: E402
+from open_kinematics_b200.core.solver import sweep_target_values  # noqa: E402
+from open_kinematics_b200.core.targeting import resolve_target  # noqa: E402
+from open_kinematics_b200.core.enums import TargetPositionMode  # noqa: E402
+from oracle.solve import OracleConstraint, OracleDerived, OracleProblem, OracleTarget  # noqa: E402
+
+SWEEP_CASES = [
+    "c1_dw_corner_bump", "c1_dw_corner_bump_steer", "c2_macpherson_bump_steer", "c3_rocker_ubar_roll_shipped",
+    "c3_rocker_ubar_coilover_roll", "c4_tbar_roll", "c4_tbar_bump", "dw_axle_direct", "macpherson_axle",
+    "dw_corner_coilover_direct", "dw_corner_rocker",
+]
+
+
+def load_golden(name: str):
+    meta = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    arrays = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    return meta, arrays
+
+
+def key_name(key) -> str:
+    return key.name.lower()
+
+
+def key_from_name(name: str):
+    for side in (Side.LEFT, Side.RIGHT, Side.CENTER):
+        prefix = side.name.lower() + "_"
+        if name.startswith(prefix) and name[len(prefix):].upper() in PointID.__members__:
+            return PointRef(side, PointID[name[len(prefix):].upper()])
+    return PointID[name.upper()]
+
+
+def authored_positions(suspension) -> dict:
+    """Authored (un-derived) position of every non-derived point, keyed like a solved state."""
+    if getattr(suspension, "is_axle", False):
+        out = {PointRef(side, k): p.data.copy() for side, c in suspension.corners.items()
+               for k, p in c.hardpoints.items()}
+        for k, p in suspension.initial_state().positions.items():
+            out.setdefault(k, p.data.copy())
+        return out
+    out = {k: p.data.copy() for k, p in suspension.hardpoints.items()}
+    for k, p in suspension.initial_state().positions.items():
+        out.setdefault(k, p.data.copy())
+    return out
+
+
+_FAMILY = {
+    PC.DistanceConstraint: "distance", PC.SphericalJointConstraint: "spherical", PC.AngleConstraint: "angle",
+    PC.ThreePointAngleConstraint: "three_point_angle", PC.VectorsParallelConstraint: "vectors_parallel",
+    PC.VectorsPerpendicularConstraint: "vectors_perpendicular", PC.EqualDistanceConstraint: "equal_distance",
+    PC.PointOnLineConstraint: "point_on_line", PC.PointOnPlaneConstraint: "linear_point",
+    PC.MidpointOnPlaneConstraint: "midpoint_on_plane", PC.ScalarTripleProductConstraint: "scalar_triple",
+    PC.CoplanarPointsConstraint: "coplanar", PC.FixedAxisConstraint: "linear_point",
+}
+
+
+def oracle_problem(suspension, sweep_config, from_design: bool = True) -> OracleProblem:
+    """Describe a built product model to the oracle (declarations only; no product arithmetic)."""
+    state = suspension.initial_state()
+    cons = []
+    for c in suspension.constraints():
+        fam = _FAMILY[type(c)]
+        if fam == "distance":
+            consts = [c.target_distance]
+        elif fam in ("angle", "three_point_angle"):
+            consts = [c.target_angle]
+        elif fam == "scalar_triple":
+            consts = [c.target_volume, 1.0 / c.scale]
+        elif fam == "point_on_line":
+            consts = [*c.line_point.data, *c.line_direction.data]
+        elif isinstance(c, PC.FixedAxisConstraint):
+            n = np.zeros(3)
+            n[int(c.axis)] = 1.0
+            consts = [*(n * c.value), *n]
+        elif fam in ("linear_point", "midpoint_on_plane"):
+            consts = [*c.plane_point.data, *c.plane_normal.data]
+        else:
+            consts = []
+        design = from_design and fam in ("distance", "angle", "scalar_triple", "point_on_line")
+        cons.append(OracleConstraint(fam, c.point_keys, list(map(float, consts)), design))
+    spec = suspension.derived_spec()
+    from open_kinematics_b200.core.points.derived.manager import DerivedPointsManager
+    derived = []
+    for key in DerivedPointsManager(spec).update_order:
+        fn = spec.functions[key]
+        derived.append(OracleDerived(fn.OP, key, tuple(fn.inputs), float(fn.param),
+                                     fn.design_projection if from_design else None))
+    heads, values = sweep_target_values(sweep_config)
+    targets = [OracleTarget(h.point_id, resolve_target(h.direction).data.copy(),
+                            TargetPositionMode(h.mode) == TargetPositionMode.RELATIVE) for h in heads]
+    return OracleProblem(sorted(state.positions), list(state.free_points_order), cons, derived, targets), values
+
+
+def build_case(meta: dict):
+    sus = build_suspension(meta["geometry"])
+    sweep = build_sweep(meta["sweep"], sus)
+    return sus, sweep
+
+
+# ---------------------------------------------------------------------------
+# Lane-emulation build of csrc/okin_core.cuh (tests only; the product never loads it).
+# ---------------------------------------------------------------------------
+_EMU = None
+
+
+def emu_lib():
+    global _EMU
+    if _EMU is None:
+        src = os.path.join(ROOT, "tests", "emu", "okin_emu.cpp")
+        out = os.path.join(ROOT, "tests", "emu", "libokin_emu.so")
+        csrc = os.path.join(ROOT, "open-kinematics_b200", "csrc")
+        deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".h", ".cuh"))]
+        if not os.path.exists(out) or os.path.getmtime(out) < max(map(os.path.getmtime, deps)):
+            subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", f"-I{csrc}", "-o", out, src], check=True)
+        lib = ctypes.CDLL(out)
+        lib.okin_emu_sweep.restype = ctypes.c_int
+        lib.okin_emu_sweep.argtypes = (
+            [ctypes.c_void_p] * 3 + [ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                     ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+            + [ctypes.c_void_p] * 6)
+        _EMU = lib
+    return _EMU
+
+
+def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, step_tol=1e-9, residual_tol=1e-3,
+              mu_init=1e-3, max_iter=50, use_predictor=1) -> dict:
+    hp = np.ascontiguousarray(hardpoints, dtype=np.float64).reshape(-1, 3 * program.n_in)
+    tv = np.ascontiguousarray(values, dtype=np.float64)
+    n_inst, n_steps, nt, n = hp.shape[0], tv.shape[1], tv.shape[0], program.n_unknowns
+    out = {
+        "positions": np.zeros((n_inst, n_steps, program.n_out, 3)), "iters": np.zeros((n_inst, n_steps), np.int32),
+        "max_residual": np.zeros((n_inst, n_steps)), "tangents": np.zeros((n_inst, n_steps, nt, n)),
+        "status": np.zeros(n_inst, np.int32), "failed_step": np.zeros(n_inst, np.int32),
+    }
+    hdr = np.ascontiguousarray(program.hdr)
+    rc = emu_lib().okin_emu_sweep(
+        hdr.ctypes.data, program.iblob.ctypes.data, program.fblob.ctypes.data, n_inst, n_steps,
+        hp.ctypes.data, tv.ctypes.data, step_tol, residual_tol, mu_init, max_iter, use_predictor,
+        out["positions"].ctypes.data, out["iters"].ctypes.data, out["max_residual"].ctypes.data,
+        out["tangents"].ctypes.data, out["status"].ctypes.data, out["failed_step"].ctypes.data)
+    assert rc == 0
+    return out
+
+
+def perturbed_hardpoints(meta_batch: dict, program) -> np.ndarray:
+    """Hardpoint rows (input-slot order) for the perturbed geometries of a golden batch."""
+    rows = []
+    for geom in meta_batch["geometries"]:
+        sus = build_suspension(geom)
+        auth = authored_positions(sus)
+        rows.append(np.concatenate([auth[k] for k in program.in_keys]))
+    return np.array(rows)
