@@ -67,7 +67,8 @@ typedef struct okin_topology_desc {
  * MINPACK ftol/xtol/gtol of the reference have no counterpart: the device solve always runs its
  * Gauss-Newton iteration to max|dx| <= step_tol. */
 typedef struct okin_solver_cfg {
-  double step_tol;       /* mm; default 1e-9 */
+  double step_tol;       /* mm; a Gauss-Newton step with max|dx| <= step_tol is applied and ends the
+                            iteration (the error left is second order in it); default 1e-6 */
   double residual_tol;   /* default 1e-3 */
   double mu_init;        /* first Marquardt damping after a rejected step; default 1e-3 */
   int32_t max_iter;      /* linear solves per step; default 50 */

@@ -187,22 +187,82 @@ def _constraint_rows(index: int, c: Constraint, pidx: dict, design_rules: bool) 
     raise TypeError(f"No device lowering for {type(c).__name__}")
 
 
-def _min_degree(nf: int, adjacency: list) -> tuple:
-    """Greedy minimum-degree ordering with symbolic elimination.  Returns
-    (order, struct) where struct[v] is the set of later-eliminated neighbours of v."""
+def _min_degree(nodes, adjacency: list) -> tuple:
+    """Greedy minimum-degree ordering of ``nodes`` with symbolic elimination on a copy of the
+    graph.  Returns (order, adjacency after eliminating ``nodes``)."""
     adj = [set(a) for a in adjacency]
-    alive = set(range(nf))
-    order, struct = [], {}
+    alive = set(nodes)
+    order = []
     while alive:
         v = min(alive, key=lambda u: (len(adj[u]), u))
         nbrs = set(adj[v])
-        struct[v] = nbrs
         order.append(v)
         alive.discard(v)
         for u in nbrs:
             adj[u] |= nbrs - {u}
             adj[u].discard(v)
-    return order, struct
+        adj[v] = set()
+    return order, adj
+
+
+def _components(nodes: set, adjacency: list) -> list:
+    comps, seen = [], set()
+    for start in sorted(nodes):
+        if start in seen:
+            continue
+        comp, stack = set(), [start]
+        while stack:
+            v = stack.pop()
+            if v in comp:
+                continue
+            comp.add(v)
+            stack.extend(u for u in adjacency[v] if u in nodes and u not in comp)
+        seen |= comp
+        comps.append(comp)
+    return comps
+
+
+def _symbolic(nf: int, adjacency: list, order: list) -> dict:
+    """Symbolic block Cholesky for a given elimination order: structure, levels, cost."""
+    adj = [set(a) for a in adjacency]
+    pos_of = {v: i for i, v in enumerate(order)}
+    struct = []
+    for v in order:
+        nbrs = {u for u in adj[v] if pos_of[u] > pos_of[v]}
+        struct.append(sorted(pos_of[u] for u in nbrs))
+        for u in nbrs:
+            adj[u] |= nbrs - {u}
+            adj[u].discard(v)
+    parent = [s[0] if s else -1 for s in struct]
+    level = [0] * nf
+    for j in range(nf):
+        if parent[j] >= 0:
+            level[parent[j]] = max(level[parent[j]], level[j] + 1)
+    nlev = max(level) + 1 if nf else 0
+    return {"order": order, "struct": struct, "level": level, "nlev": nlev,
+            "blocks": nf + sum(len(s) for s in struct)}
+
+
+def _best_order(nf: int, adjacency: list) -> dict:
+    """Choose between plain minimum degree and a one-level nested dissection (separator of at
+    most two block vertices eliminated last).  The kernel pays one warp synchronisation per
+    elimination-tree level in every factor/solve phase, so fewer levels wins; ties go to the
+    smaller factor."""
+    nodes = set(range(nf))
+    candidates = [_symbolic(nf, adjacency, _min_degree(nodes, adjacency)[0])]
+    seps = [(v,) for v in range(nf)] + [(u, v) for u in range(nf) for v in range(u + 1, nf)]
+    for sep in seps:
+        rest = nodes - set(sep)
+        comps = _components(rest, adjacency)
+        if len(comps) < 2 or max(map(len, comps)) > 0.7 * nf:
+            continue
+        order, adj = [], adjacency
+        for comp in comps:
+            part, adj = _min_degree(comp, adj)
+            order += part
+        tail, _ = _min_degree(set(sep), adj)
+        candidates.append(_symbolic(nf, adjacency, order + tail))
+    return min(candidates, key=lambda c: (c["nlev"], c["blocks"]))
 
 
 def compile_topology(
@@ -381,15 +441,9 @@ def compile_topology(
             for b in row.eff:
                 if a != b:
                     adjacency[a].add(b)
-    order, struct_by_col = _min_degree(NF, adjacency)
+    sym = _best_order(NF, adjacency)
+    order, struct, level, NLEV = sym["order"], sym["struct"], sym["level"], sym["nlev"]
     pos_of = {v: i for i, v in enumerate(order)}             # column block -> elimination position
-    struct = [sorted(pos_of[u] for u in struct_by_col[order[j]]) for j in range(NF)]
-    parent = [s[0] if s else -1 for s in struct]
-    level = [0] * NF
-    for j in range(NF):
-        if parent[j] >= 0:
-            level[parent[j]] = max(level[parent[j]], level[j] + 1)
-    NLEV = max(level) + 1 if NF else 0
 
     block_id = {}
     for j in range(NF):

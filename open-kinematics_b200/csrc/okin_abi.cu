@@ -174,7 +174,7 @@ int okin_device_count(int* out) {
 
 int okin_default_cfg(okin_solver_cfg* out) {
   if (!out) return fail(OKIN_ERR_USAGE, "null out");
-  out->step_tol = 1e-9;
+  out->step_tol = 1e-6;
   out->residual_tol = 1e-3;
   out->mu_init = 1e-3;
   out->max_iter = 50;

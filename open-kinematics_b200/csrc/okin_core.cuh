@@ -24,6 +24,14 @@
 #include "okin_defs.h"
 #include "okin_gen_constraints.cuh"
 
+// Phase functions are kept out of line on the device: inlining all of them into the sweep loop
+// (each is called from several places) costs registers (255/thread) and instruction cache.
+#if defined(__CUDACC__) && !defined(OKIN_LANE_EMU)
+#define OKIN_FN __host__ __device__ __noinline__
+#else
+#define OKIN_FN inline
+#endif
+
 #if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
 #define OKIN_PHASE_BEGIN { const int lane = (int)(threadIdx.x & 31u);
 #define OKIN_PHASE_END } __syncwarp();
@@ -97,7 +105,7 @@ OKIN_HD void okin_dop_eval(int op, double par, const double* a, const double* b,
 
 // Evaluate derived points into pos[].  active_only: only the ops referenced by solve rows.
 template <typename Dummy = void>
-OKIN_HD void okin_derived_update(const OkinProgram& pr, double* sm, bool active_only) {
+OKIN_FN void okin_derived_update(const OkinProgram& pr, double* sm, bool active_only) {
   const int32_t* dop = okin_sec(pr, OKIN_S_DOP);
   const int ndop = pr.hdr[OKIN_H_NDOP];
   double* pos = sm + pr.hdr[OKIN_H_OFF_POS];
@@ -122,7 +130,7 @@ OKIN_HD void okin_derived_update(const OkinProgram& pr, double* sm, bool active_
 // Jacobian blocks d(derived)/d(free base point) by seeding one coordinate per task and
 // pushing it through the op chain (manager.py:271-324 does the same with dual numbers).
 template <typename Dummy = void>
-OKIN_HD void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
+OKIN_FN void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
   const int nad = pr.hdr[OKIN_H_NAD];
   if (nad == 0) return;
   const int32_t* adj = okin_sec(pr, OKIN_S_ADJ);
@@ -172,7 +180,7 @@ OKIN_HD void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
 // Setup: inputs -> pos, derived parameters, design pose, per-instance constants.
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
-OKIN_HD void okin_setup(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints) {
+OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints) {
   const int32_t* hdr = pr.hdr;
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* cst = sm + hdr[OKIN_H_OFF_CST];
@@ -265,7 +273,7 @@ OKIN_HD void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
 // Row evaluation: residuals (and gradients mapped to effective free blocks).
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
-OKIN_HD void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tval, bool with_grad, OkinState& st) {
+OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tval, bool with_grad, OkinState& st) {
   const int32_t* hdr = pr.hdr;
   okin_derived_update(pr, sm, true);
   if (with_grad) okin_derived_jacobians(pr, sm);
@@ -347,7 +355,7 @@ OKIN_HD void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
 // Normal equations: A = J^T J (+ mu diag(A)) into the factor storage, g = J^T r into vec[0].
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
-OKIN_HD void okin_assemble(const OkinProgram& pr, double* sm, double mu) {
+OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu) {
   const int32_t* hdr = pr.hdr;
   const int nat = hdr[OKIN_H_NAT];
   const int n = 3 * hdr[OKIN_H_NF];
@@ -408,7 +416,7 @@ OKIN_HD bool okin_chol3(const double* d, double f[9]) {
 }
 
 template <typename Dummy = void>
-OKIN_HD void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
+OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
   const int32_t* hdr = pr.hdr;
   const int nlev = hdr[OKIN_H_NLEV];
   const int32_t* lev_upd = okin_sec(pr, OKIN_S_LEV_UPD);
@@ -470,7 +478,7 @@ OKIN_HD void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
 // Solve A X = B for nrhs right-hand sides stored at vec[first .. first+nrhs) (elimination order),
 // in place.
 template <typename Dummy = void>
-OKIN_HD void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs) {
+OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs) {
   const int32_t* hdr = pr.hdr;
   const int nlev = hdr[OKIN_H_NLEV];
   const int n = 3 * hdr[OKIN_H_NF];
@@ -533,7 +541,7 @@ OKIN_HD void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs) 
 
 // pos[free] += scale * vec[which]; returns max|vec[which]| (warp-uniform).
 template <typename Dummy = void>
-OKIN_HD double okin_apply_step(const OkinProgram& pr, double* sm, int which, double scale, bool save) {
+OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, double scale, bool save) {
   const int32_t* hdr = pr.hdr;
   const int n = 3 * hdr[OKIN_H_NF];
   const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
@@ -560,7 +568,7 @@ OKIN_HD double okin_apply_step(const OkinProgram& pr, double* sm, int which, dou
 }
 
 template <typename Dummy = void>
-OKIN_HD void okin_restore(const OkinProgram& pr, double* sm) {
+OKIN_FN void okin_restore(const OkinProgram& pr, double* sm) {
   const int32_t* hdr = pr.hdr;
   const int n = 3 * hdr[OKIN_H_NF];
   const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
@@ -615,7 +623,12 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       st.mu = 0.0;
       nu = 2.0;
     } else if (st.f2 <= f2_old * (1.0 + 1e-12) + 1e-300) {
-      // Accepted; relax the damping towards pure Gauss-Newton.
+      // Accepted.  A damped step that no longer reduces ||r||^2 means the iteration sits at a
+      // least-squares compromise of an unreachable target (MINPACK's ftol exit, reference
+      // SolverConfig.ftol); report it converged so that the residual test rejects the state
+      // exactly like solver.py:735-747.
+      if (st.mu > 0.0 && f2_old - st.f2 <= 1e-7 * f2_old) { *converged = true; break; }
+      // Relax the damping towards pure Gauss-Newton.
       if (st.mu > 0.0) {
         st.mu *= (1.0 / 3.0);
         if (st.mu < 1e-10) st.mu = 0.0;
@@ -637,7 +650,7 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
 // the normal equations; with full column rank lstsq(J, e_j) == (J^T J)^{-1} J^T e_j).
 // Requires rg[] / factor from an undamped linearisation at (numerically) the solution.
 template <typename Dummy = void>
-OKIN_HD void okin_tangents(const OkinProgram& pr, double* sm) {
+OKIN_FN void okin_tangents(const OkinProgram& pr, double* sm) {
   const int32_t* hdr = pr.hdr;
   const int nt = hdr[OKIN_H_NT];
   const int n = 3 * hdr[OKIN_H_NF];
