@@ -65,14 +65,16 @@ typedef struct okin_topology_desc {
 
 /* Solver controls.  residual_tol mirrors SolverConfig.residual_tolerance (solver.py:80); the
  * MINPACK ftol/xtol/gtol of the reference have no counterpart: the device solve always runs its
- * Gauss-Newton iteration to max|dx| <= step_tol. */
+ * Gauss-Newton iteration until a verification step is below step_tol. */
 typedef struct okin_solver_cfg {
-  double step_tol;       /* mm; a Gauss-Newton step with max|dx| <= step_tol is applied and ends the
-                            iteration (the error left is second order in it); default 1e-6 */
+  double step_tol;       /* mm; the iteration ends when the verification (chord) step, which is also
+                            applied, has max|dx| <= step_tol; default 1e-6 (typical size 1e-9) */
+  double coarse_tol;     /* mm; an undamped Gauss-Newton step this small triggers the chord step;
+                            default 1e-3 */
   double residual_tol;   /* default 1e-3 */
   double mu_init;        /* first Marquardt damping after a rejected step; default 1e-3 */
-  int32_t max_iter;      /* linear solves per step; default 50 */
-  int32_t use_predictor; /* 1: warm-start each step along the previous tangents */
+  int32_t max_iter;      /* factorisations per step; default 50 */
+  int32_t use_predictor; /* 0 warm start only, 1 first-order tangent predictor, 2 second order (default) */
 } okin_solver_cfg;
 
 typedef struct okin_topology_info {

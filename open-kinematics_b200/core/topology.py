@@ -617,7 +617,7 @@ def compile_topology(
         "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
         "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)), "OKIN_H_OFF_LB": take(9 * NB),
         "OKIN_H_OFF_DFAC": take(9 * NF), "OKIN_H_OFF_VEC": take((1 + NT) * N), "OKIN_H_OFF_XSAVE": take(N),
-        "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)),
+        "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)), "OKIN_H_OFF_PPREV": take(N),
     }
     counts = {
         "OKIN_H_MAGIC": D["OKIN_MAGIC"], "OKIN_H_P": P, "OKIN_H_NF": NF, "OKIN_H_NIN": len(in_keys),

@@ -129,7 +129,7 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
            int32_t n_steps, const double* hp, const double* tv, double* pos, int32_t* status, int32_t* failed,
            int32_t* iters, double* maxres, double* tangents) {
   if (n_instances == 0) return OKIN_OK;
-  OkinSolverCfg c{cfg->step_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter, cfg->use_predictor};
+  OkinSolverCfg c{cfg->step_tol, cfg->coarse_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter, cfg->use_predictor};
   const int smem = OKIN_WARPS_PER_CTA * t->hdr[OKIN_H_SMEM_DOUBLES] * (int)sizeof(double);
   const int64_t needed = (n_instances + OKIN_WARPS_PER_CTA - 1) / OKIN_WARPS_PER_CTA;
   const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
@@ -146,7 +146,7 @@ int check_common(const okin_topology* t, const okin_solver_cfg* cfg, int64_t n_i
   if (n_instances < 0 || n_steps < 0) return fail(OKIN_ERR_USAGE, "negative size");
   if (n_instances > 0 && (!hp || !status || !failed)) return fail(OKIN_ERR_USAGE, "null required buffer");
   if (n_steps > 0 && t->hdr[OKIN_H_NT] > 0 && !tv) return fail(OKIN_ERR_USAGE, "null target_values");
-  if (cfg->max_iter < 1 || !(cfg->step_tol > 0.0)) return fail(OKIN_ERR_USAGE, "invalid solver config");
+  if (cfg->max_iter < 1 || !(cfg->step_tol > 0.0) || !(cfg->coarse_tol >= cfg->step_tol)) return fail(OKIN_ERR_USAGE, "invalid solver config");
   return OKIN_OK;
 }
 
@@ -175,10 +175,11 @@ int okin_device_count(int* out) {
 int okin_default_cfg(okin_solver_cfg* out) {
   if (!out) return fail(OKIN_ERR_USAGE, "null out");
   out->step_tol = 1e-6;
+  out->coarse_tol = 1e-3;
   out->residual_tol = 1e-3;
   out->mu_init = 1e-3;
   out->max_iter = 50;
-  out->use_predictor = 1;
+  out->use_predictor = 2;
   return OKIN_OK;
 }
 

@@ -49,11 +49,12 @@ struct OkinProgram {
 };
 
 struct OkinSolverCfg {
-  double step_tol;      // converged when max|dx| <= step_tol (mm)
-  double residual_tol;  // accept a step when max|r| <= residual_tol   (reference constants.py:20)
+  double step_tol;      // converged when the verification (chord) step has max|dx| <= step_tol (mm)
+  double coarse_tol;    // a Gauss-Newton step with max|dx| <= coarse_tol is followed by the chord step
+  double residual_tol;  // accept a state when max|r| <= residual_tol   (reference constants.py:20)
   double mu_init;       // first Marquardt damping factor after a rejected Gauss-Newton step
-  int32_t max_iter;     // linear solves per step before "not converged"
-  int32_t use_predictor;  // warm-start each step along the previous tangents
+  int32_t max_iter;     // factorisations per step before "not converged"
+  int32_t use_predictor;  // 0: warm start only; 1: first-order tangent predictor; 2: second order
 };
 
 OKIN_HD const int32_t* okin_sec(const OkinProgram& pr, int s) { return pr.ib + pr.hdr[OKIN_H_SEC0 + 2 * s]; }
@@ -355,7 +356,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
 // Normal equations: A = J^T J (+ mu diag(A)) into the factor storage, g = J^T r into vec[0].
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
-OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu) {
+OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_only) {
   const int32_t* hdr = pr.hdr;
   const int nat = hdr[OKIN_H_NAT];
   const int n = 3 * hdr[OKIN_H_NF];
@@ -370,7 +371,7 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu) {
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
   const double damp = 1.0 + mu;
   OKIN_PHASE_BEGIN
-  for (int t = lane; t < nat + n; t += 32) {
+  for (int t = (g_only ? nat : 0) + lane; t < nat + n; t += 32) {
     if (t < nat) {
       const int b = OKIN_LDG(aptr + t), e = OKIN_LDG(aptr + t + 1);
       double acc = 0.0;
@@ -579,12 +580,53 @@ OKIN_FN void okin_restore(const OkinProgram& pr, double* sm) {
   OKIN_PHASE_END
 }
 
+// max|vec[which]| (warp-uniform).
+template <typename Dummy = void>
+OKIN_FN double okin_vec_max(const OkinProgram& pr, double* sm, int which) {
+  const int n = 3 * pr.hdr[OKIN_H_NF];
+  const double* v = sm + pr.hdr[OKIN_H_OFF_VEC] + which * n;
+  double* red = sm + pr.hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  double mx = 0.0;
+  for (int u = lane; u < n; u += 32) {
+    const double a = fabs(v[u]);
+    mx = (a > mx || a != a) ? a : mx;
+  }
+  red[lane] = mx;
+  OKIN_PHASE_END
+  double out = 0.0;
+  for (int k = 0; k < 32; ++k) out = (red[k] > out || red[k] != red[k]) ? red[k] : out;
+  return out;
+}
+
+// Continuation predictor: x += p + (second ? (p - p_prev)/2 : 0), p = sum_j V_j dt_j, where V_j
+// are the tangents of the previous state.  p is kept for the next step's curvature term.
+template <typename Dummy = void>
+OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, bool second) {
+  const int32_t* hdr = pr.hdr;
+  const int n = 3 * hdr[OKIN_H_NF];
+  const int nt = hdr[OKIN_H_NT];
+  const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
+  double* pos = sm + hdr[OKIN_H_OFF_POS];
+  const double* V = sm + hdr[OKIN_H_OFF_VEC] + n;
+  double* pprev = sm + hdr[OKIN_H_OFF_PPREV];
+  OKIN_PHASE_BEGIN
+  for (int u = lane; u < n; u += 32) {
+    double p = 0.0;
+    for (int j = 0; j < nt; ++j) p = fma(V[j * n + u], dt[j], p);
+    const double step = second ? p + 0.5 * (p - pprev[u]) : p;
+    pprev[u] = p;
+    pos[3 * OKIN_LDG(ep + u / 3) + u % 3] += step;
+  }
+  OKIN_PHASE_END
+}
+
 // ---------------------------------------------------------------------------------------
 // One sweep step: Gauss-Newton on the pinned least-squares system, Marquardt damping only
-// after a step that fails to reduce ||r||^2.  Returns the number of residual evaluations
-// (the SolverInfo.nfev analogue); converged is set when max|dx| <= step_tol.
-// On return r[] holds the residuals at the final point and the factor storage holds the
-// Cholesky factor of the last (undamped, whenever possible) normal matrix.
+// after a step that fails to reduce ||r||^2, and a chord step that both verifies and finishes the
+// convergence.  Returns the number of residual evaluations (the SolverInfo.nfev analogue).
+// On return r[] holds the residuals one chord step (<= step_tol) before the final point, rg[]
+// and the factor storage the last undamped linearisation (used for the tangents).
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
 OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tval, const OkinSolverCfg& cfg,
@@ -596,7 +638,7 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
   ++nfev;
   *converged = false;
   for (int it = 0; it < cfg.max_iter; ++it) {
-    okin_assemble(pr, sm, st.mu);
+    okin_assemble(pr, sm, st.mu, false);
     okin_factor(pr, sm, st);
     if (st.notpd) {  // rank-deficient normal matrix: damp and retry from the same point
       st.mu = st.mu > 0.0 ? st.mu * 10.0 : cfg.mu_init;
@@ -609,17 +651,30 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       okin_restore(pr, sm);
       break;
     }
-    if (hmax <= cfg.step_tol && st.mu == 0.0) {
+    const double f2_old = st.f2;
+    if (st.mu == 0.0 && hmax <= cfg.coarse_tol) {
+      // Small undamped step: verify with a chord step h2 = -(J0^T J0)^{-1} J0^T r(x1) that reuses
+      // the factor and the row gradients of the previous linearisation (residual-only
+      // evaluation, g-only assembly, one triangular solve).  Near the solution |h2| ~ k |h1|^2.
       okin_eval_rows(pr, sm, tval, false, st);
       ++nfev;
-      *converged = true;
-      break;
+      okin_assemble(pr, sm, 0.0, true);
+      okin_solve(pr, sm, 0, 1);
+      const double h2 = okin_vec_max(pr, sm, 0);
+      if (h2 <= cfg.step_tol) {
+        okin_apply_step(pr, sm, 0, 1.0, false);
+        *converged = true;
+        break;
+      }
+      // Not contracting fast enough: relinearise at the current point.
+      okin_eval_rows(pr, sm, tval, true, st);
+      ++nfev;
+      continue;
     }
-    const double f2_old = st.f2;
     okin_eval_rows(pr, sm, tval, true, st);
     ++nfev;
     if (hmax <= cfg.step_tol) {
-      // Tiny step under damping: drop the damping and let a pure Gauss-Newton step confirm.
+      // Tiny step under damping: drop the damping and let undamped steps confirm.
       st.mu = 0.0;
       nu = 2.0;
     } else if (st.f2 <= f2_old * (1.0 + 1e-12) + 1e-300) {
@@ -701,16 +756,23 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   int status = OKIN_STATUS_OK, failed = -1;
   double tcur[OKIN_MAX_TARGETS], tprev[OKIN_MAX_TARGETS];
   for (int j = 0; j < OKIN_MAX_TARGETS; ++j) { tcur[j] = 0.0; tprev[j] = 0.0; }
-  bool have_tangent = false;
+  bool have_tangent = false, have_pprev = false;
+  double dtprev[OKIN_MAX_TARGETS];
+  for (int j = 0; j < OKIN_MAX_TARGETS; ++j) dtprev[j] = 0.0;
 
   for (int s = 0; s < n_steps; ++s) {
     if (status == OKIN_STATUS_OK) {
       for (int j = 0; j < nt; ++j) { tprev[j] = tcur[j]; tcur[j] = OKIN_LDG(tvals + j * n_steps + s); }
       if (cfg.use_predictor && have_tangent) {
-        for (int j = 0; j < nt; ++j) {
-          const double dt = tcur[j] - tprev[j];
-          if (dt != 0.0) okin_apply_step(pr, sm, 1 + j, dt, false);
+        double dt[OKIN_MAX_TARGETS];
+        bool same = have_pprev;
+        for (int j = 0; j < OKIN_MAX_TARGETS; ++j) {
+          dt[j] = tcur[j] - tprev[j];
+          if (fabs(dt[j] - dtprev[j]) > 1e-9 * (fabs(dt[j]) + fabs(dtprev[j]))) same = false;
+          dtprev[j] = dt[j];
         }
+        okin_predict(pr, sm, dt, same && cfg.use_predictor > 1);
+        have_pprev = true;
       }
       bool conv = false;
       const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv);
@@ -729,6 +791,14 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
       if (status == OKIN_STATUS_OK) {
+        if (out.tangents) {
+          // Exported tangents are taken at the solution itself: relinearise there.  (For the
+          // predictor alone the factor of the last Gauss-Newton point, <= coarse_tol away, is
+          // enough and costs nothing.)
+          okin_eval_rows(pr, sm, tcur, true, st);
+          okin_assemble(pr, sm, 0.0, false);
+          okin_factor(pr, sm, st);
+        }
         okin_derived_update(pr, sm, false);
         okin_tangents(pr, sm);
         have_tangent = true;
