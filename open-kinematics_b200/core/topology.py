@@ -309,6 +309,13 @@ def compile_topology(
     in_keys = [k for k in point_keys if k not in derived_spec.functions]
     dops, par_mode, par_val = [], [], []
     dop_of = {}
+    # derived points ordered by dependency level so that one level is one parallel phase
+    dlevel: dict = {}
+    for key in derived_keys:
+        deps = [d for d in derived_spec.dependencies[key] if d in derived_spec.functions]
+        dlevel[key] = 1 + max((dlevel[d] for d in deps), default=-1)
+    derived_keys = sorted(derived_keys, key=lambda k: dlevel[k])   # stable: keeps topological order
+    dop_lev = [0]
     for key in derived_keys:
         fn = derived_spec.functions[key]
         if fn.OP not in _DOP_CODE:
@@ -324,6 +331,9 @@ def compile_topology(
         par_val.append(float(fn.param))
         dop_of[key] = len(dops)
         dops.append([_DOP_CODE[fn.OP], pidx[key], ins[0], ins[1], ins[2], len(par_val) - 1, authored, 0])
+        while len(dop_lev) <= dlevel[key]:
+            dop_lev.append(len(dops) - 1)
+    dop_lev.append(len(dops))
     in_keys = sorted(in_keys)
     in_slot = {k: i for i, k in enumerate(in_keys)}
     for key in derived_keys:
@@ -457,47 +467,40 @@ def compile_topology(
     def boff(i, j) -> int:
         return 9 * block_id[(i, j)]
 
-    # ---- assembly gather lists (A = J^T J) -----------------------------------
+    # ---- assembly gather lists (A = J^T J), one task per 3x3 block ----------------
+    # contribution = (rg offset of the row's gradient w.r.t. the block-row point) << 16 |
+    #                (rg offset of its gradient w.r.t. the block-column point)
     contrib: dict = {}
     for row in ls_rows:
         for ea, ca in enumerate(row.eff):
             for eb, cb in enumerate(row.eff):
                 pa, pb = pos_of[ca], pos_of[cb]
-                if pa < pb:
+                if pa < pb or (pa == pb and ea != eb):
                     continue
-                for r in range(3):
-                    for c in range(3):
-                        if pa == pb and (ea != eb or c > r):
-                            continue
-                        contrib.setdefault((pa, pb, r, c), []).append(
-                            ((row.rg_off + 3 * ea + r) << 16) | (row.rg_off + 3 * eb + c))
-    asm_ptr, asm_dst, asm_con = [0], [], []
-    for (i, j), b in block_id.items():
-        for r in range(3):
-            for c in range(3):
-                if i == j and c > r:
-                    continue
-                dst = 9 * b + 3 * r + c
-                if i == j and r == c:
-                    dst |= D["OKIN_ASM_DIAG"]
-                asm_dst.append(dst)
-                asm_con.extend(contrib.get((i, j, r, c), []))
-                asm_ptr.append(len(asm_con))
-    NAT = len(asm_dst)
+                contrib.setdefault((pa, pb), []).append(((row.rg_off + 3 * ea) << 16) | (row.rg_off + 3 * eb))
+    tasks = sorted(block_id.items(), key=lambda kv: (-len(contrib.get(kv[0], [])), kv[1]))
+    asm_ptr, asm_task, asm_con = [0], [], []
+    for (i, j), b in tasks:       # heaviest first: lanes take tasks round-robin
+        asm_task.append(b | (D["OKIN_ASM_DIAG"] if i == j else 0))
+        asm_con.extend(contrib.get((i, j), []))
+        asm_ptr.append(len(asm_con))
+    NAT = len(asm_task)
 
     g_ptr, g_con = [0], []
     row_index = {id(row): i for i, row in enumerate(rows)}
-    per_unknown: dict = {}
+    per_block: dict = {}
     for row in ls_rows:
         for e, cblk in enumerate(row.eff):
-            for r in range(3):
-                per_unknown.setdefault(3 * pos_of[cblk] + r, []).append(
-                    ((row.rg_off + 3 * e + r) << 16) | row_index[id(row)])
-    for u in range(3 * NF):
-        g_con.extend(per_unknown.get(u, []))
+            per_block.setdefault(pos_of[cblk], []).append(((row.rg_off + 3 * e) << 16) | row_index[id(row)])
+    for j in range(NF):
+        g_con.extend(per_block.get(j, []))
         g_ptr.append(len(g_con))
 
     # ---- left-looking update lists, scale tasks -------------------------------
+    # One task per block *row* (3 entries): acc[c] -= a . B[c][:] for every earlier column K,
+    # a = row r of L_iK, B = L_jK.  The right-hand side of the step equation is carried as one
+    # extra block-row of the factor (a = y_K), which makes the forward substitution part of the
+    # factorisation.  Offsets are relative to the instance's shared-memory base.
     cols_with = [[] for _ in range(NF)]        # cols_with[j] = K < j with L_jK != 0
     for k in range(NF):
         for i in struct[k]:
@@ -505,6 +508,7 @@ def compile_topology(
     lev_cols = [[j for j in range(NF) if level[j] == lv] for lv in range(NLEV)]
     lev_upd, upd_dst, upd_ptr, upd_con = [0], [], [0], []
     lev_scl, scl = [0], []
+    LB, VEC = "LB", "VEC"      # symbolic bases, resolved once the layout is known
     for lv in range(NLEV):
         for j in lev_cols[lv]:
             for i in [j] + struct[j]:
@@ -512,27 +516,30 @@ def compile_topology(
                 if not ks:
                     continue
                 for r in range(3):
-                    for c in range(3):
-                        if i == j and c > r:
-                            continue
-                        upd_dst.append(boff(i, j) + 3 * r + c)
-                        for k in ks:
-                            upd_con.append(((boff(i, k) + 3 * r) << 16) | (boff(j, k) + 3 * c))
-                        upd_ptr.append(len(upd_con))
-            scl.append([j, boff(j, j), -1, 0])
+                    upd_dst.append((LB, boff(i, j) + 3 * r))
+                    for k in ks:
+                        upd_con.append(((LB, boff(i, k) + 3 * r), (LB, boff(j, k))))
+                    upd_ptr.append(len(upd_con))
+            if cols_with[j]:
+                upd_dst.append((VEC, 3 * j))
+                for k in cols_with[j]:
+                    upd_con.append(((VEC, 3 * k), (LB, boff(j, k))))
+                upd_ptr.append(len(upd_con))
+            scl.append([j, (LB, boff(j, j)), -1, 0])
             for i in struct[j]:
                 for r in range(3):
-                    scl.append([j, boff(j, j), boff(i, j) + 3 * r, 0])
+                    scl.append([j, (LB, boff(j, j)), (LB, boff(i, j) + 3 * r), 0])
+            scl.append([j, (LB, boff(j, j)), (VEC, 3 * j), 0])
         lev_upd.append(len(upd_dst))
         lev_scl.append(len(scl))
 
     fw_ptr, fw_con, bw_ptr, bw_con = [0], [], [0], []
     for j in range(NF):
         for k in cols_with[j]:
-            fw_con.append((boff(j, k) << 16) | (3 * k))
+            fw_con.append(((LB, boff(j, k)), 3 * k))
         fw_ptr.append(len(fw_con))
         for i in struct[j]:
-            bw_con.append((boff(i, j) << 16) | (3 * i))
+            bw_con.append(((LB, boff(i, j)), 3 * i))
         bw_ptr.append(len(bw_con))
     lev_col_ptr, lev_col = [0], []
     for lv in range(NLEV):
@@ -555,9 +562,41 @@ def compile_topology(
         if k not in pidx:
             raise ValueError(f"Output point {k!r} is not part of the model")
 
-    # ---- blobs ------------------------------------------------------------------
+    # ---- evaluation order: rows of one family are adjacent so that a 32-row round of the
+    # evaluation phase runs (mostly) one code path
+    row_order = sorted(range(len(rows)), key=lambda i: (rows[i].fam, i))
+
+    # ---- shared-memory layout (doubles) -----------------------------------------------
     NT = len(targets)
     N = 3 * NF
+    off = 0
+
+    def take(n: int) -> int:
+        nonlocal off
+        start = off
+        off += n
+        return start
+
+    layout = {
+        "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
+        "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)), "OKIN_H_OFF_LB": take(9 * NB),
+        "OKIN_H_OFF_DFAC": take(9 * NF), "OKIN_H_OFF_VEC": take((1 + NT) * N), "OKIN_H_OFF_XSAVE": take(N),
+        "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)), "OKIN_H_OFF_PPREV": take(N),
+    }
+    if off >= 65536:
+        raise ValueError("Per-instance state exceeds the 16-bit shared-memory offset range")
+    base = {LB: layout["OKIN_H_OFF_LB"], VEC: layout["OKIN_H_OFF_VEC"]}
+
+    def sm(ref) -> int:
+        return base[ref[0]] + ref[1]
+
+    upd_dst = [sm(d) for d in upd_dst]
+    upd_con = [(sm(a) << 16) | sm(b) for a, b in upd_con]
+    scl = [[j, sm(d), (-1 if r == -1 else sm(r)), z] for j, d, r, z in scl]
+    fw_con = [(sm(b) << 16) | v for b, v in fw_con]
+    bw_con = [(sm(b) << 16) | v for b, v in bw_con]
+
+    # ---- blobs ------------------------------------------------------------------
     row_tab = []
     for row in rows:
         pts = row.points + [-1] * (4 - len(row.points))
@@ -569,7 +608,7 @@ def compile_topology(
         "OKIN_S_POINT_KIND": kind, "OKIN_S_IN_POINT": [pidx[k] for k in in_keys],
         "OKIN_S_DOP": dops, "OKIN_S_PAR_MODE": par_mode, "OKIN_S_ADJ": adj_tasks, "OKIN_S_ADJ_CHAIN": adj_chain,
         "OKIN_S_ROW": row_tab, "OKIN_S_DER": der_desc,
-        "OKIN_S_ASM_PTR": asm_ptr, "OKIN_S_ASM_DST": asm_dst, "OKIN_S_ASM_CON": asm_con,
+        "OKIN_S_ASM_PTR": asm_ptr, "OKIN_S_ASM_TASK": asm_task, "OKIN_S_ASM_CON": asm_con,
         "OKIN_S_G_PTR": g_ptr, "OKIN_S_G_CON": g_con,
         "OKIN_S_LEV_UPD": lev_upd, "OKIN_S_UPD_DST": upd_dst, "OKIN_S_UPD_PTR": upd_ptr, "OKIN_S_UPD_CON": upd_con,
         "OKIN_S_LEV_SCL": lev_scl, "OKIN_S_SCL": scl,
@@ -577,7 +616,8 @@ def compile_topology(
         "OKIN_S_FW_PTR": fw_ptr, "OKIN_S_FW_CON": fw_con, "OKIN_S_BW_PTR": bw_ptr, "OKIN_S_BW_CON": bw_con,
         "OKIN_S_ELIM_POINT": elim_point, "OKIN_S_ELIM_COL": elim_col,
         "OKIN_S_TGT_SC_PTR": tgt_sc_ptr, "OKIN_S_TGT_SC": tgt_sc,
-        "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_SETUP_PT": [],
+        "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_ROW_ORDER": row_order,
+        "OKIN_S_DOP_LEV": dop_lev,
     }
     hdr = np.zeros(D["OKIN_HDR_SIZE"], np.int32)
     chunks, cursor = [], 0
@@ -604,21 +644,6 @@ def compile_topology(
     if fblob.size == 0:
         fblob = np.zeros(1, np.float64)
 
-    # shared-memory layout (doubles)
-    off = 0
-
-    def take(n: int) -> int:
-        nonlocal off
-        start = off
-        off += n
-        return start
-
-    layout = {
-        "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
-        "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)), "OKIN_H_OFF_LB": take(9 * NB),
-        "OKIN_H_OFF_DFAC": take(9 * NF), "OKIN_H_OFF_VEC": take((1 + NT) * N), "OKIN_H_OFF_XSAVE": take(N),
-        "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)), "OKIN_H_OFF_PPREV": take(N),
-    }
     counts = {
         "OKIN_H_MAGIC": D["OKIN_MAGIC"], "OKIN_H_P": P, "OKIN_H_NF": NF, "OKIN_H_NIN": len(in_keys),
         "OKIN_H_NDOP": len(dops), "OKIN_H_NPAR": len(par_val), "OKIN_H_NROW": NROW, "OKIN_H_NREP": NREP,
@@ -633,7 +658,7 @@ def compile_topology(
     stats = {
         "n_points": P, "n_free": NF, "n_unknowns": N, "n_rows": NROW, "n_report_rows": NREP, "n_targets": NT,
         "n_blocks": NB, "n_levels": NLEV, "fill_blocks": NB - NF - sum(len(a) for a in adjacency) // 2,
-        "asm_fma": len(asm_con), "g_fma": len(g_con), "update_fma": 3 * len(upd_con),
+        "asm_fma": 9 * len(asm_con), "g_fma": 3 * len(g_con), "update_fma": 9 * len(upd_con),
         "scale_tasks": len(scl), "solve_fma": 9 * (len(fw_con) + len(bw_con)) + 12 * NF,
         "smem_doubles": off, "iblob_words": int(iblob.size), "dense_lu_flops": dense_flops,
     }

@@ -104,19 +104,22 @@ OKIN_HD void okin_dop_eval(int op, double par, const double* a, const double* b,
   }
 }
 
-// Evaluate derived points into pos[].  active_only: only the ops referenced by solve rows.
+// Evaluate derived points into pos[], one dependency level per phase, one lane per op.
+// active_only: only the ops referenced by solve rows (wheel centre, strut clamp).
 template <typename Dummy = void>
 OKIN_FN void okin_derived_update(const OkinProgram& pr, double* sm, bool active_only) {
   const int32_t* dop = okin_sec(pr, OKIN_S_DOP);
-  const int ndop = pr.hdr[OKIN_H_NDOP];
+  const int32_t* lev = okin_sec(pr, OKIN_S_DOP_LEV);
+  const int nlev = okin_sec_len(pr, OKIN_S_DOP_LEV) - 1;
   double* pos = sm + pr.hdr[OKIN_H_OFF_POS];
   const double* par = sm + pr.hdr[OKIN_H_OFF_PAR];
-  OKIN_PHASE_BEGIN
-  if (lane == 0) {
-    const double z[3] = {0.0, 0.0, 0.0};
-    for (int d = 0; d < ndop; ++d) {
+  for (int lv = 0; lv < nlev; ++lv) {
+    const int b = OKIN_LDG(lev + lv), e = OKIN_LDG(lev + lv + 1);
+    OKIN_PHASE_BEGIN
+    for (int d = b + lane; d < e; d += 32) {
       const int32_t* rec = dop + d * OKIN_DOP_STRIDE;
       if (active_only && !OKIN_LDG(rec + 7)) continue;
+      const double z[3] = {0.0, 0.0, 0.0};
       const int ia = OKIN_LDG(rec + 2), ib = OKIN_LDG(rec + 3), ic = OKIN_LDG(rec + 4);
       double out[3], dout[3];
       okin_dop_eval(OKIN_LDG(rec + 0), par[OKIN_LDG(rec + 5)], pos + 3 * ia, pos + 3 * (ib < 0 ? ia : ib),
@@ -124,8 +127,8 @@ OKIN_FN void okin_derived_update(const OkinProgram& pr, double* sm, bool active_
       const int o = OKIN_LDG(rec + 1);
       pos[3 * o] = out[0]; pos[3 * o + 1] = out[1]; pos[3 * o + 2] = out[2];
     }
+    OKIN_PHASE_END
   }
-  OKIN_PHASE_END
 }
 
 // Jacobian blocks d(derived)/d(free base point) by seeding one coordinate per task and
@@ -288,9 +291,11 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   double* r = sm + hdr[OKIN_H_OFF_R];
   double* rg = sm + hdr[OKIN_H_OFF_RG];
   double* red = sm + hdr[OKIN_H_OFF_RED];
+  const int32_t* order = okin_sec(pr, OKIN_S_ROW_ORDER);
   OKIN_PHASE_BEGIN
   double sq = 0.0, mx = 0.0;
-  for (int t = lane; t < nrows; t += 32) {
+  for (int slot = lane; slot < nrows; slot += 32) {
+    const int t = OKIN_LDG(order + slot);
     const int32_t* rec = rows + t * OKIN_ROW_STRIDE;
     const int fam = OKIN_LDG(rec + OKIN_R_FAM);
     const double* c = cst + OKIN_LDG(rec + OKIN_R_CST);
@@ -359,9 +364,9 @@ template <typename Dummy = void>
 OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_only) {
   const int32_t* hdr = pr.hdr;
   const int nat = hdr[OKIN_H_NAT];
-  const int n = 3 * hdr[OKIN_H_NF];
+  const int nf = hdr[OKIN_H_NF];
   const int32_t* aptr = okin_sec(pr, OKIN_S_ASM_PTR);
-  const int32_t* adst = okin_sec(pr, OKIN_S_ASM_DST);
+  const int32_t* atask = okin_sec(pr, OKIN_S_ASM_TASK);
   const int32_t* acon = okin_sec(pr, OKIN_S_ASM_CON);
   const int32_t* gptr = okin_sec(pr, OKIN_S_G_PTR);
   const int32_t* gcon = okin_sec(pr, OKIN_S_G_CON);
@@ -371,26 +376,36 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
   const double damp = 1.0 + mu;
   OKIN_PHASE_BEGIN
-  for (int t = (g_only ? nat : 0) + lane; t < nat + n; t += 32) {
+  for (int t = (g_only ? nat : 0) + lane; t < nat + nf; t += 32) {
     if (t < nat) {
+      // one 3x3 block of A: sum of outer products ga gb^T over the rows coupling the two points
       const int b = OKIN_LDG(aptr + t), e = OKIN_LDG(aptr + t + 1);
-      double acc = 0.0;
+      double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(acon + q);
-        acc = fma(rg[w >> 16], rg[w & 0xffffu], acc);
+        const double* ga = rg + (w >> 16);
+        const double* gb = rg + (w & 0xffffu);
+        const double x0 = ga[0], x1 = ga[1], x2 = ga[2], y0 = gb[0], y1 = gb[1], y2 = gb[2];
+        a00 = fma(x0, y0, a00); a01 = fma(x0, y1, a01); a02 = fma(x0, y2, a02);
+        a10 = fma(x1, y0, a10); a11 = fma(x1, y1, a11); a12 = fma(x1, y2, a12);
+        a20 = fma(x2, y0, a20); a21 = fma(x2, y1, a21); a22 = fma(x2, y2, a22);
       }
-      const int dst = OKIN_LDG(adst + t);
-      if (dst & OKIN_ASM_DIAG) acc *= damp;
-      Lb[dst & ~OKIN_ASM_DIAG] = acc;
+      const int task = OKIN_LDG(atask + t);
+      if (task & OKIN_ASM_DIAG) { a00 *= damp; a11 *= damp; a22 *= damp; }
+      double* dst = Lb + 9 * (task & 0xffff);
+      dst[0] = a00; dst[1] = a01; dst[2] = a02; dst[3] = a10; dst[4] = a11; dst[5] = a12;
+      dst[6] = a20; dst[7] = a21; dst[8] = a22;
     } else {
-      const int u = t - nat;
-      const int b = OKIN_LDG(gptr + u), e = OKIN_LDG(gptr + u + 1);
-      double acc = 0.0;
+      const int j = t - nat;
+      const int b = OKIN_LDG(gptr + j), e = OKIN_LDG(gptr + j + 1);
+      double g0 = 0, g1 = 0, g2 = 0;
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(gcon + q);
-        acc = fma(rg[w >> 16], r[w & 0xffffu], acc);
+        const double* ga = rg + (w >> 16);
+        const double res = r[w & 0xffffu];
+        g0 = fma(ga[0], res, g0); g1 = fma(ga[1], res, g1); g2 = fma(ga[2], res, g2);
       }
-      vec[u] = -acc;  // right-hand side of A h = -g
+      vec[3 * j] = -g0; vec[3 * j + 1] = -g1; vec[3 * j + 2] = -g2;  // right-hand side of A h = -g
     }
   }
   OKIN_PHASE_END
@@ -426,7 +441,6 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
   const int32_t* ucon = okin_sec(pr, OKIN_S_UPD_CON);
   const int32_t* lev_scl = okin_sec(pr, OKIN_S_LEV_SCL);
   const int32_t* scl = okin_sec(pr, OKIN_S_SCL);
-  double* Lb = sm + hdr[OKIN_H_OFF_LB];
   double* Df = sm + hdr[OKIN_H_OFF_DFAC];
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
@@ -435,18 +449,22 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
   for (int lv = 0; lv < nlev; ++lv) {
     const int ub = OKIN_LDG(lev_upd + lv), ue = OKIN_LDG(lev_upd + lv + 1);
     if (ue > ub) {
+      // left-looking update of one block row (or of the carried right-hand side)
       OKIN_PHASE_BEGIN
       for (int t = ub + lane; t < ue; t += 32) {
         const int b = OKIN_LDG(uptr + t), e = OKIN_LDG(uptr + t + 1);
-        const int dst = OKIN_LDG(udst + t);
-        double acc = Lb[dst];
+        double* dst = sm + OKIN_LDG(udst + t);
+        double c0 = dst[0], c1 = dst[1], c2 = dst[2];
         for (int q = b; q < e; ++q) {
           const uint32_t w = (uint32_t)OKIN_LDG(ucon + q);
-          const double* x = Lb + (w >> 16);
-          const double* y = Lb + (w & 0xffffu);
-          acc -= x[0] * y[0] + x[1] * y[1] + x[2] * y[2];
+          const double* a = sm + (w >> 16);
+          const double* B = sm + (w & 0xffffu);
+          const double a0 = a[0], a1 = a[1], a2 = a[2];
+          c0 -= a0 * B[0] + a1 * B[1] + a2 * B[2];
+          c1 -= a0 * B[3] + a1 * B[4] + a2 * B[5];
+          c2 -= a0 * B[6] + a1 * B[7] + a2 * B[8];
         }
-        Lb[dst] = acc;
+        dst[0] = c0; dst[1] = c1; dst[2] = c2;
       }
       OKIN_PHASE_END
     }
@@ -456,13 +474,13 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
       const int32_t* rec = scl + 4 * t;
       const int j = OKIN_LDG(rec + 0), doff = OKIN_LDG(rec + 1), roff = OKIN_LDG(rec + 2);
       double f[9];
-      const bool ok = okin_chol3(Lb + doff, f);
+      const bool ok = okin_chol3(sm + doff, f);
       if (roff < 0) {
         double* o = Df + 9 * j;
         for (int k = 0; k < 9; ++k) o[k] = f[k];
         if (!ok) red[lane] = 1.0;
       } else {
-        double* b = Lb + roff;
+        double* b = sm + roff;
         const double x0 = b[0] * f[6];
         const double x1 = (b[1] - x0 * f[1]) * f[7];
         const double x2 = (b[2] - x0 * f[3] - x1 * f[4]) * f[8];
@@ -477,9 +495,10 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
 }
 
 // Solve A X = B for nrhs right-hand sides stored at vec[first .. first+nrhs) (elimination order),
-// in place.
+// in place.  skip_forward: vec[first] already holds L^{-1} b (the factorisation carries vec[0]
+// as an extra row).
 template <typename Dummy = void>
-OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs) {
+OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, bool skip_forward) {
   const int32_t* hdr = pr.hdr;
   const int nlev = hdr[OKIN_H_NLEV];
   const int n = 3 * hdr[OKIN_H_NF];
@@ -489,10 +508,10 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs) 
   const int32_t* fcon = okin_sec(pr, OKIN_S_FW_CON);
   const int32_t* bptr = okin_sec(pr, OKIN_S_BW_PTR);
   const int32_t* bcon = okin_sec(pr, OKIN_S_BW_CON);
-  const double* Lb = sm + hdr[OKIN_H_OFF_LB];
+  const double* Lb = sm;
   const double* Df = sm + hdr[OKIN_H_OFF_DFAC];
   double* vec = sm + hdr[OKIN_H_OFF_VEC] + first * n;
-  for (int lv = 0; lv < nlev; ++lv) {  // L y = b
+  for (int lv = 0; lv < (skip_forward ? 0 : nlev); ++lv) {  // L y = b
     const int cb = OKIN_LDG(lcp + lv), ce = OKIN_LDG(lcp + lv + 1);
     OKIN_PHASE_BEGIN
     for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
@@ -621,6 +640,30 @@ OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, b
   OKIN_PHASE_END
 }
 
+// Right-hand sides of the tangent systems A dq/dt_j = J_target_j^T into vec[1..NT]
+// (sensitivity.py:89-101 solved through the normal equations: with full column rank
+// lstsq([J; pins], e_j) == (J^T J)^{-1} J^T e_j).  Uses the target rows of rg[].
+template <typename Dummy = void>
+OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
+  const int32_t* hdr = pr.hdr;
+  const int nt = hdr[OKIN_H_NT];
+  const int n = 3 * hdr[OKIN_H_NF];
+  const int32_t* sptr = okin_sec(pr, OKIN_S_TGT_SC_PTR);
+  const int32_t* sc = okin_sec(pr, OKIN_S_TGT_SC);
+  const double* rg = sm + hdr[OKIN_H_OFF_RG];
+  double* vec = sm + hdr[OKIN_H_OFF_VEC] + n;
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < nt * n; t += 32) vec[t] = 0.0;
+  OKIN_PHASE_END
+  OKIN_PHASE_BEGIN
+  for (int j = 0; j < nt; ++j)
+    for (int q = OKIN_LDG(sptr + j) + lane; q < OKIN_LDG(sptr + j + 1); q += 32) {
+      const uint32_t w = (uint32_t)OKIN_LDG(sc + q);
+      vec[j * n + (w & 0xffffu)] = rg[w >> 16];
+    }
+  OKIN_PHASE_END
+}
+
 // ---------------------------------------------------------------------------------------
 // One sweep step: Gauss-Newton on the pinned least-squares system, Marquardt damping only
 // after a step that fails to reduce ||r||^2, and a chord step that both verifies and finishes the
@@ -630,8 +673,9 @@ OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, b
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
 OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tval, const OkinSolverCfg& cfg,
-                            OkinState& st, bool* converged) {
+                            OkinState& st, bool* converged, bool* tangents_ready) {
   int nfev = 0;
+  *tangents_ready = false;
   st.mu = 0.0;
   double nu = 2.0;
   okin_eval_rows(pr, sm, tval, true, st);
@@ -645,7 +689,7 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       if (st.mu > 1e12) break;
       continue;
     }
-    okin_solve(pr, sm, 0, 1);
+    okin_solve(pr, sm, 0, 1, true);  // forward substitution was carried by the factorisation
     const double hmax = okin_apply_step(pr, sm, 0, 1.0, true);
     if (!(hmax == hmax)) {  // NaN step: invalid geometry
       okin_restore(pr, sm);
@@ -658,12 +702,15 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       // evaluation, g-only assembly, one triangular solve).  Near the solution |h2| ~ k |h1|^2.
       okin_eval_rows(pr, sm, tval, false, st);
       ++nfev;
+      // The tangent systems share the factor: solve them in the same pass (1 + NT right-hand sides).
       okin_assemble(pr, sm, 0.0, true);
-      okin_solve(pr, sm, 0, 1);
+      okin_tangent_rhs(pr, sm);
+      okin_solve(pr, sm, 0, 1 + pr.hdr[OKIN_H_NT], false);
       const double h2 = okin_vec_max(pr, sm, 0);
       if (h2 <= cfg.step_tol) {
         okin_apply_step(pr, sm, 0, 1.0, false);
         *converged = true;
+        *tangents_ready = true;
         break;
       }
       // Not contracting fast enough: relinearise at the current point.
@@ -699,31 +746,6 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
     }
   }
   return nfev;
-}
-
-// Tangents dq/dt_j = A^{-1} J_target_j^T for every target (sensitivity.py:89-101 solved through
-// the normal equations; with full column rank lstsq(J, e_j) == (J^T J)^{-1} J^T e_j).
-// Requires rg[] / factor from an undamped linearisation at (numerically) the solution.
-template <typename Dummy = void>
-OKIN_FN void okin_tangents(const OkinProgram& pr, double* sm) {
-  const int32_t* hdr = pr.hdr;
-  const int nt = hdr[OKIN_H_NT];
-  const int n = 3 * hdr[OKIN_H_NF];
-  const int32_t* sptr = okin_sec(pr, OKIN_S_TGT_SC_PTR);
-  const int32_t* sc = okin_sec(pr, OKIN_S_TGT_SC);
-  const double* rg = sm + hdr[OKIN_H_OFF_RG];
-  double* vec = sm + hdr[OKIN_H_OFF_VEC] + n;
-  OKIN_PHASE_BEGIN
-  for (int t = lane; t < nt * n; t += 32) vec[t] = 0.0;
-  OKIN_PHASE_END
-  OKIN_PHASE_BEGIN
-  for (int j = 0; j < nt; ++j)
-    for (int q = OKIN_LDG(sptr + j) + lane; q < OKIN_LDG(sptr + j + 1); q += 32) {
-      const uint32_t w = (uint32_t)OKIN_LDG(sc + q);
-      vec[j * n + (w & 0xffffu)] = rg[w >> 16];
-    }
-  OKIN_PHASE_END
-  okin_solve(pr, sm, 1, nt);
 }
 
 struct OkinOutputs {
@@ -774,8 +796,8 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
         okin_predict(pr, sm, dt, same && cfg.use_predictor > 1);
         have_pprev = true;
       }
-      bool conv = false;
-      const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv);
+      bool conv = false, tangents_ready = false;
+      const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready);
       const bool valid = st.rmax == st.rmax;
       if (!conv || !valid) {
         status = valid ? OKIN_STATUS_NOT_CONVERGED : OKIN_STATUS_INVALID_GEOMETRY;
@@ -791,16 +813,19 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
       if (status == OKIN_STATUS_OK) {
-        if (out.tangents) {
+        if (out.tangents || !tangents_ready) {
           // Exported tangents are taken at the solution itself: relinearise there.  (For the
           // predictor alone the factor of the last Gauss-Newton point, <= coarse_tol away, is
-          // enough and costs nothing.)
+          // enough and was solved together with the chord step.)
+          const double rmax = st.rmax;
           okin_eval_rows(pr, sm, tcur, true, st);
+          st.rmax = rmax;
           okin_assemble(pr, sm, 0.0, false);
           okin_factor(pr, sm, st);
+          okin_tangent_rhs(pr, sm);
+          okin_solve(pr, sm, 1, nt, false);
         }
         okin_derived_update(pr, sm, false);
-        okin_tangents(pr, sm);
         have_tangent = true;
       }
     } else {

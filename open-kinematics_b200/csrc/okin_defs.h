@@ -109,29 +109,30 @@ enum okin_isec {
   OKIN_S_ADJ_CHAIN,      // derived-op indices, referenced by ADJ
   OKIN_S_ROW,            // [NROW+NREP][OKIN_ROW_STRIDE]
   OKIN_S_DER,            // [..][OKIN_DER_STRIDE]
-  OKIN_S_ASM_PTR,        // [NAT+1]
-  OKIN_S_ASM_DST,        // [NAT] Lb offset | OKIN_ASM_DIAG flag
-  OKIN_S_ASM_CON,        // (ia << 16) | ib  into rg[]
-  OKIN_S_G_PTR,          // [3*NF+1]  (elimination-ordered unknowns)
-  OKIN_S_G_CON,          // (irg << 16) | row
+  OKIN_S_ASM_PTR,        // [NAT+1] contribution ranges per assembly task (one task per 3x3 block)
+  OKIN_S_ASM_TASK,       // [NAT] block id | OKIN_ASM_DIAG flag, heaviest task first
+  OKIN_S_ASM_CON,        // (ia << 16) | ib: rg[] offsets of the two 3-vectors whose outer product is added
+  OKIN_S_G_PTR,          // [NF+1]  (elimination-ordered block columns)
+  OKIN_S_G_CON,          // (irg << 16) | row: g_j += rg[irg..irg+3) * r[row]
   OKIN_S_LEV_UPD,        // [NLEV+1] ranges into UPD_DST/UPD_PTR
-  OKIN_S_UPD_DST,        // Lb offset of the entry
+  OKIN_S_UPD_DST,        // shared-memory offset of the 3-entry row being updated
   OKIN_S_UPD_PTR,        // [n_upd+1]
-  OKIN_S_UPD_CON,        // (offA << 16) | offB : sum_t Lb[offA+t]*Lb[offB+t], t<3
+  OKIN_S_UPD_CON,        // (offA << 16) | offB : acc[c] -= sum_t sm[offA+t]*sm[offB+3c+t]
   OKIN_S_LEV_SCL,        // [NLEV+1] ranges into SCL
-  OKIN_S_SCL,            // [..][4] = {elim col j, diag Lb offset, row Lb offset or -1 (write Dfac), 0}
+  OKIN_S_SCL,            // [..][4] = {elim col j, diag block offset, row offset or -1 (write Dfac), 0}
   OKIN_S_LEV_COL_PTR,    // [NLEV+1]
   OKIN_S_LEV_COL,        // elimination columns of each level
   OKIN_S_FW_PTR,         // [NF+1]
-  OKIN_S_FW_CON,         // (Lb block offset << 16) | (3*K)
+  OKIN_S_FW_CON,         // (block offset << 16) | (3*K)
   OKIN_S_BW_PTR,         // [NF+1]
-  OKIN_S_BW_CON,         // (Lb block offset << 16) | (3*I)
+  OKIN_S_BW_CON,         // (block offset << 16) | (3*I)
   OKIN_S_ELIM_POINT,     // [NF] elimination position -> point index
   OKIN_S_ELIM_COL,       // [NF] elimination position -> reference column block (sorted free-point order)
   OKIN_S_TGT_SC_PTR,     // [NT+1]
   OKIN_S_TGT_SC,         // (rg index << 16) | unknown index (elimination order)
   OKIN_S_OUT_POINT,      // [NOUT]
-  OKIN_S_SETUP_PT,       // points whose design position feeds OKIN_RULE_* (unused, reserved)
+  OKIN_S_ROW_ORDER,      // [NROW+NREP] evaluation order (rows grouped by family)
+  OKIN_S_DOP_LEV,        // [n_derived_levels+1] ranges of DOP evaluated in one parallel phase
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000
@@ -155,7 +156,7 @@ enum okin_row_slot {
 
 // Derived-slot descriptor: int32[8] = {ndeps, dblk_off0, eff0, dblk_off1, eff1, dblk_off2, eff2, 0}
 #define OKIN_DER_STRIDE 8
-// Derived op record: int32[8] = {op, out, a, b, c, par, authored_input_slot, 0}
+// Derived op record: int32[8] = {op, out, a, b, c, par, authored_input_slot, active}
 #define OKIN_DOP_STRIDE 8
 // Derived-Jacobian column task: int32[8] = {D, B, comp, dblk_off, chain_begin, chain_end, 0, 0}
 #define OKIN_ADJ_STRIDE 8
