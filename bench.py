@@ -248,7 +248,7 @@ def run_cuda(args) -> None:
         _lib.check(lib.okin_solve_batch_device(
             topo.handle, ctypes.byref(cfg), local, ctypes.c_void_p(stream), n_inst, S,
             hp.data_ptr(), tv.data_ptr(), pos.data_ptr(), status.data_ptr(), failed.data_ptr(),
-            iters.data_ptr(), maxres.data_ptr(), None), "okin_solve_batch_device")
+            iters.data_ptr(), maxres.data_ptr(), None, None), "okin_solve_batch_device")
 
     def barrier():
         if world > 1:
@@ -294,7 +294,7 @@ def run_cuda(args) -> None:
         _lib.check(lib.okin_solve_batch(
             topo.handle, ctypes.byref(cfg), e2e_inst, S, h_hp.data_ptr(), h_tv.data_ptr(), devs.ctypes.data, 1,
             h_pos.data_ptr(), h_status.data_ptr(), h_failed.data_ptr(), h_iters.data_ptr(), h_maxres.data_ptr(),
-            None), "okin_solve_batch")
+            None, None), "okin_solve_batch")
 
     for _ in range(2):
         e2e_call()

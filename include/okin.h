@@ -9,7 +9,9 @@
  *                             manager.py:95-105): everything computed once per topology.
  *   okin_solve_batch       <- solve_suspension_sweep (solver.py:654-776), once per instance,
  *                             plus compute_state_tangents (sensitivity.py:57-143) when
- *                             tangents_out is given.
+ *                             tangents_out is given and Suspension.compute_state_metrics
+ *                             (suspensions/base.py:198-204 -> metrics/main.py:63, :145) when
+ *                             metrics_out is given.
  *   okin_solve_batch_device   same, on buffers already resident in device memory.
  *
  * Conventions: plain pointers and sizes, caller owns every buffer, every function returns 0 on
@@ -28,6 +30,9 @@
  *   iters_out       [n_instances][n_steps]           residual evaluations (SolverInfo.nfev)
  *   max_residual_out[n_instances][n_steps]           max |r| at the solution (SolverInfo.max_residual)
  *   tangents_out    [n_instances][n_steps][n_targets][n_unknowns]  dq/dt_j, reference column order
+ *   metrics_out     [n_instances][n_steps][n_metrics]  state / mechanism / derivative metric columns in
+ *                                                    the reference's flat export order; NaN where the
+ *                                                    reference yields None
  *   status_out      [n_instances]                    OKIN_STATUS_*
  *   failed_step_out [n_instances]                    -1 or the first failed step
  * Any *_out pointer except status_out / failed_step_out may be NULL.
@@ -79,7 +84,7 @@ typedef struct okin_solver_cfg {
 
 typedef struct okin_topology_info {
   int32_t n_points, n_in_points, n_out_points, n_unknowns, n_targets, n_rows;
-  int32_t smem_bytes_per_instance, n_levels;
+  int32_t smem_bytes_per_instance, n_levels, n_metrics;
 } okin_topology_info;
 
 int okin_device_count(int* out);
@@ -92,7 +97,7 @@ int okin_topology_get_info(const okin_topology* topo, okin_topology_info* out);
 int okin_solve_batch(okin_topology* topo, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
                      const double* hardpoints, const double* target_values, const int32_t* device_ids,
                      int32_t n_devices, double* positions_out, int32_t* status_out, int32_t* failed_step_out,
-                     int32_t* iters_out, double* max_residual_out, double* tangents_out);
+                     int32_t* iters_out, double* max_residual_out, double* tangents_out, double* metrics_out);
 
 /* Device buffers on `device`; enqueues on `stream` (a cudaStream_t, may be NULL) and returns
  * without synchronising. */
@@ -100,7 +105,7 @@ int okin_solve_batch_device(okin_topology* topo, const okin_solver_cfg* cfg, int
                             int64_t n_instances, int32_t n_steps, const double* d_hardpoints,
                             const double* d_target_values, double* d_positions_out, int32_t* d_status_out,
                             int32_t* d_failed_step_out, int32_t* d_iters_out, double* d_max_residual_out,
-                            double* d_tangents_out);
+                            double* d_tangents_out, double* d_metrics_out);
 
 /* Launch geometry the library would use for n_instances on `device` (for reporting). */
 int okin_launch_geometry(okin_topology* topo, int32_t device, int64_t n_instances, int32_t* grid, int32_t* block,

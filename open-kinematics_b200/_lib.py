@@ -39,7 +39,7 @@ class SolverCfg(ctypes.Structure):
 class TopologyInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "n_points", "n_in_points", "n_out_points", "n_unknowns", "n_targets", "n_rows",
-        "smem_bytes_per_instance", "n_levels")]
+        "smem_bytes_per_instance", "n_levels", "n_metrics")]
 
 
 # name -> (restype, argtypes); also the list the "exports every declared symbol" test checks.
@@ -52,11 +52,12 @@ SIGNATURES = {
     "okin_solve_batch": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int64, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
-        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p]),
     "okin_solve_batch_device": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-        ctypes.c_void_p, ctypes.c_void_p]),
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "okin_launch_geometry": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_i32p]),
     "okin_fp64_peak": (ctypes.c_int, [ctypes.c_int32, c_f64p]),
@@ -174,7 +175,7 @@ class DeviceTopology:
 
     # -- host buffers ------------------------------------------------------------------
     def solve_batch(self, hardpoints: np.ndarray, target_values: np.ndarray, cfg: SolverCfg | None = None,
-                    devices=None, want_positions=True, want_tangents=False) -> dict:
+                    devices=None, want_positions=True, want_tangents=False, want_metrics=False) -> dict:
         """hardpoints [n_inst, n_in*3]; target_values [n_targets, n_steps]."""
         require_device()
         prog = self.program
@@ -194,7 +195,10 @@ class DeviceTopology:
             "iters": np.empty((n_inst, n_steps), np.int32),
             "max_residual": np.empty((n_inst, n_steps)),
             "tangents": np.empty((n_inst, n_steps, nt, prog.n_unknowns)) if want_tangents else None,
+            "metrics": np.empty((n_inst, n_steps, len(prog.metric_names))) if want_metrics else None,
         }
+        if want_metrics and not prog.metric_names:
+            raise ValueError("This topology was compiled without a metric program")
         dev = np.ascontiguousarray(devices if devices is not None else [0], dtype=np.int32)
 
         def p(a):
@@ -203,5 +207,5 @@ class DeviceTopology:
         check(load().okin_solve_batch(
             self.handle, ctypes.byref(cfg), n_inst, n_steps, p(hp), p(tv), p(dev), dev.size,
             p(out["positions"]), p(out["status"]), p(out["failed_step"]), p(out["iters"]),
-            p(out["max_residual"]), p(out["tangents"])), "okin_solve_batch")
+            p(out["max_residual"]), p(out["tangents"]), p(out["metrics"])), "okin_solve_batch")
         return out

@@ -35,6 +35,8 @@ class BatchSweepResult:
     nfev         [n_instances, n_steps]
     max_residual [n_instances, n_steps]
     tangents     [n_instances, n_steps, n_targets, n_unknowns] or None
+    metrics      [n_instances, n_steps, n_metrics] or None; columns = ``metric_names`` (the
+                 reference's flat export order), NaN where the reference yields None
     """
 
     program: TopologyProgram
@@ -44,10 +46,15 @@ class BatchSweepResult:
     nfev: np.ndarray
     max_residual: np.ndarray
     tangents: np.ndarray | None
+    metrics: np.ndarray | None = None
 
     @property
     def point_keys(self) -> list:
         return self.program.out_keys
+
+    @property
+    def metric_names(self) -> list:
+        return self.program.metric_names
 
 
 class BatchSolver:
@@ -61,9 +68,12 @@ class BatchSolver:
         validate_sweep_controls(sweep_config, suspension.actuator_dofs())
         self.suspension = suspension
         self.heads, self.values = sweep_target_values(sweep_config)
+        from .metrics_program import build_metric_program
         self.program = compile_topology(
             suspension.initial_state(), suspension.constraints(), suspension.derived_spec(), self.heads,
             output_points=output_points, design_rules=True,
+            metrics=(lambda pidx: build_metric_program(suspension, self.heads, pidx))
+            if suspension.config is not None else None,
         )
         self.topology = _lib.DeviceTopology(self.program)
 
@@ -84,14 +94,16 @@ class BatchSolver:
         return dict(sus.hardpoints)
 
     def solve(self, hardpoints: np.ndarray, solver_config: SolverConfig = SolverConfig(), devices=None,
-              want_positions: bool = True, want_tangents: bool = False) -> BatchSweepResult:
+              want_positions: bool = True, want_tangents: bool = False,
+              want_metrics: bool = False) -> BatchSweepResult:
         cfg = _lib.default_cfg(residual_tol=float(solver_config.residual_tolerance))
         hp = np.asarray(hardpoints, dtype=np.float64)
         hp = hp.reshape(hp.shape[0], -1)
         out = self.topology.solve_batch(hp, self.values, cfg, devices=devices,
-                                        want_positions=want_positions, want_tangents=want_tangents)
+                                        want_positions=want_positions, want_tangents=want_tangents,
+                                        want_metrics=want_metrics)
         return BatchSweepResult(self.program, out["positions"], out["status"], out["failed_step"],
-                                out["iters"], out["max_residual"], out["tangents"])
+                                out["iters"], out["max_residual"], out["tangents"], out["metrics"])
 
     def close(self) -> None:
         self.topology.close()
@@ -104,3 +116,11 @@ def solve_sweep_batch(suspension, sweep_config: SweepConfig, hardpoints: np.ndar
         return solver.solve(hardpoints, **kwargs)
     finally:
         solver.close()
+
+
+def compute_sweep_metrics_batch(suspension, sweep_config: SweepConfig, hardpoints: np.ndarray, **kwargs):
+    """Batched counterpart of reference ``compute_sweep_metrics`` (core/sweep.py:144-173): solves
+    the sweeps and returns ``(metric_names, metrics[n_instances, n_steps, n_metrics], result)``
+    with tangents and derivative metrics evaluated on the device."""
+    result = solve_sweep_batch(suspension, sweep_config, hardpoints, want_metrics=True, **kwargs)
+    return result.metric_names, result.metrics, result

@@ -114,6 +114,7 @@ class TopologyProgram:
     row_source: list          # LS rows then report rows
     target_points: list
     stats: dict
+    metric_names: list = field(default_factory=list)
 
     @property
     def n_unknowns(self) -> int:
@@ -272,6 +273,7 @@ def compile_topology(
     targets: list,
     output_points=None,
     design_rules: bool = True,
+    metrics=None,
 ) -> TopologyProgram:
     """Compile one topology.
 
@@ -604,6 +606,23 @@ def compile_topology(
         row_tab.append(rec + [0] * (D["OKIN_ROW_STRIDE"] - len(rec)))
     cst_init = [v for row in rows for v in row.consts]
 
+    point_elim = [-1] * P
+    for j in range(NF):
+        point_elim[elim_point[j]] = j
+    point_dop = [-1] * P
+    for key, d in dop_of.items():
+        point_dop[pidx[key]] = d
+    mprog = metrics(pidx) if metrics is not None else None
+    mcorners = mprog.corners if mprog else []
+    mops = mprog.mops if mprog else []
+    maxle = [mprog.axle] if (mprog and mprog.axle) else []
+    design_pts = mprog.design_pts if mprog else []
+    mconst = mprog.fconst if mprog else []
+    metric_names = list(mprog.names) if mprog else []
+    ndsn = len(design_pts)
+    layout["OKIN_H_OFF_DSN"] = take(max(3 * ndsn, 1))
+    layout["OKIN_H_OFF_MCTX"] = take(4 * max(len(mcorners), 2))
+
     isecs = {
         "OKIN_S_POINT_KIND": kind, "OKIN_S_IN_POINT": [pidx[k] for k in in_keys],
         "OKIN_S_DOP": dops, "OKIN_S_PAR_MODE": par_mode, "OKIN_S_ADJ": adj_tasks, "OKIN_S_ADJ_CHAIN": adj_chain,
@@ -617,7 +636,8 @@ def compile_topology(
         "OKIN_S_ELIM_POINT": elim_point, "OKIN_S_ELIM_COL": elim_col,
         "OKIN_S_TGT_SC_PTR": tgt_sc_ptr, "OKIN_S_TGT_SC": tgt_sc,
         "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_ROW_ORDER": row_order,
-        "OKIN_S_DOP_LEV": dop_lev,
+        "OKIN_S_DOP_LEV": dop_lev, "OKIN_S_POINT_ELIM": point_elim, "OKIN_S_POINT_DOP": point_dop,
+        "OKIN_S_DESIGN_PT": design_pts, "OKIN_S_MCORNER": mcorners, "OKIN_S_MOP": mops, "OKIN_S_MAXLE": maxle,
     }
     hdr = np.zeros(D["OKIN_HDR_SIZE"], np.int32)
     chunks, cursor = [], 0
@@ -631,7 +651,7 @@ def compile_topology(
         chunks.append(arr.astype(np.int32))
         cursor += arr.size
     iblob = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
-    fsecs = {"OKIN_F_PAR_VAL": par_val, "OKIN_F_CST_INIT": cst_init}
+    fsecs = {"OKIN_F_PAR_VAL": par_val, "OKIN_F_CST_INIT": cst_init, "OKIN_F_MCONST": mconst}
     fchunks, cursor = [], 0
     for name, data in fsecs.items():
         arr = np.asarray(data, dtype=np.float64).reshape(-1)
@@ -649,7 +669,9 @@ def compile_topology(
         "OKIN_H_NDOP": len(dops), "OKIN_H_NPAR": len(par_val), "OKIN_H_NROW": NROW, "OKIN_H_NREP": NREP,
         "OKIN_H_NT": NT, "OKIN_H_NCST": ncst, "OKIN_H_NRG": nrg, "OKIN_H_NAD": len(adj_tasks), "OKIN_H_NDB": ndb,
         "OKIN_H_NB": NB, "OKIN_H_NLEV": NLEV, "OKIN_H_NAT": NAT, "OKIN_H_NOUT": len(out_keys),
-        "OKIN_H_TROW0": trow0, "OKIN_H_SMEM_DOUBLES": off, **layout,
+        "OKIN_H_TROW0": trow0, "OKIN_H_SMEM_DOUBLES": off, "OKIN_H_NM": len(metric_names),
+        "OKIN_H_NMC": len(mcorners), "OKIN_H_NMOP": len(mops), "OKIN_H_NMAXLE": len(maxle), "OKIN_H_NDSN": ndsn,
+        **layout,
     }
     for name, value in counts.items():
         hdr[D[name]] = value
@@ -665,16 +687,18 @@ def compile_topology(
     return TopologyProgram(
         hdr=hdr, iblob=iblob, fblob=fblob, point_keys=point_keys, free_order=free_order, in_keys=in_keys,
         out_keys=out_keys, n_constraints=len(constraints), row_source=[r.source for r in rows],
-        target_points=[t.point_id for t in targets], stats=stats,
+        target_points=[t.point_id for t in targets], stats=stats, metric_names=metric_names,
     )
 
 
-def compile_suspension(suspension, sweep_config, output_points=None, design_rules: bool = True) -> TopologyProgram:
+def compile_suspension(suspension, sweep_config, output_points=None, design_rules: bool = True,
+                       with_metrics: bool = True) -> TopologyProgram:
     """Compile a built suspension + sweep (first-step targets define the target rows)."""
+    from .metrics_program import build_metric_program
+
     targets = [sweep[0] for sweep in sweep_config.target_sweeps]
-    if output_points is None:
-        output_points = None
+    metrics = (lambda pidx: build_metric_program(suspension, targets, pidx)) if with_metrics else None
     return compile_topology(
         suspension.initial_state(), suspension.constraints(), suspension.derived_spec(), targets,
-        output_points=output_points, design_rules=design_rules,
+        output_points=output_points, design_rules=design_rules, metrics=metrics,
     )

@@ -23,6 +23,7 @@
 
 #include "okin_defs.h"
 #include "okin_gen_constraints.cuh"
+#include "okin_metrics.cuh"
 
 // Phase functions are kept out of line on the device: inlining all of them into the sweep loop
 // (each is called from several places) costs registers (255/thread) and instruction cache.
@@ -219,6 +220,15 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
   OKIN_PHASE_END
 
   okin_derived_update(pr, sm, false);
+
+  {  // design positions kept for the metrics (travel references, rotation datums)
+    const int ndsn = hdr[OKIN_H_NDSN];
+    const int32_t* dpt = okin_sec(pr, OKIN_S_DESIGN_PT);
+    double* dsn = sm + hdr[OKIN_H_OFF_DSN];
+    OKIN_PHASE_BEGIN
+    for (int t = lane; t < 3 * ndsn; t += 32) dsn[t] = pos[3 * OKIN_LDG(dpt + t / 3) + t % 3];
+    OKIN_PHASE_END
+  }
 
   // Per-instance constants: each row's own quantity at the design pose (true norms, no
   // softnorm: vector_utils/geometric.py:17-28, :71-104, :197-214).
@@ -748,11 +758,314 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
   return nfev;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Metrics (csrc/okin_metrics.cuh holds the response kernels and record layouts).
+// ---------------------------------------------------------------------------------------
+// Velocity of point p along tangent j: free points read the tangent vector, fixed points are at
+// rest, derived points push their inputs' velocities through the op (sensitivity.py:118-141).
+// Derived inputs of derived points are supported one level deep (contact patch <- wheel centre).
+OKIN_HD void okin_point_vel_base(const OkinProgram& pr, const double* sm, int p, int j, double v[3]) {
+  v[0] = v[1] = v[2] = 0.0;
+  if (p < 0) return;
+  const int e = OKIN_LDG(okin_sec(pr, OKIN_S_POINT_ELIM) + p);
+  if (e < 0) return;
+  const double* V = sm + pr.hdr[OKIN_H_OFF_VEC] + (1 + j) * 3 * pr.hdr[OKIN_H_NF] + 3 * e;
+  v[0] = V[0]; v[1] = V[1]; v[2] = V[2];
+}
+OKIN_HD void okin_point_vel_op(const OkinProgram& pr, const double* sm, int d, const double* da, const double* db,
+                               const double* dc, double v[3]) {
+  const int32_t* rec = okin_sec(pr, OKIN_S_DOP) + d * OKIN_DOP_STRIDE;
+  const int ia = OKIN_LDG(rec + 2), ib = OKIN_LDG(rec + 3), ic = OKIN_LDG(rec + 4);
+  const double* pos = sm + pr.hdr[OKIN_H_OFF_POS];
+  const double* par = sm + pr.hdr[OKIN_H_OFF_PAR];
+  double out[3];
+  okin_dop_eval(OKIN_LDG(rec + 0), par[OKIN_LDG(rec + 5)], pos + 3 * ia, pos + 3 * (ib < 0 ? ia : ib),
+                pos + 3 * (ic < 0 ? ia : ic), da, db, dc, out, v);
+}
+OKIN_HD void okin_point_vel1(const OkinProgram& pr, const double* sm, int p, int j, double v[3]) {
+  const int d = p < 0 ? -1 : OKIN_LDG(okin_sec(pr, OKIN_S_POINT_DOP) + p);
+  if (d < 0) { okin_point_vel_base(pr, sm, p, j, v); return; }
+  const int32_t* rec = okin_sec(pr, OKIN_S_DOP) + d * OKIN_DOP_STRIDE;
+  double da[3], db[3], dc[3];
+  okin_point_vel_base(pr, sm, OKIN_LDG(rec + 2), j, da);
+  okin_point_vel_base(pr, sm, OKIN_LDG(rec + 3), j, db);
+  okin_point_vel_base(pr, sm, OKIN_LDG(rec + 4), j, dc);
+  okin_point_vel_op(pr, sm, d, da, db, dc, v);
+}
+OKIN_HD void okin_point_vel(const OkinProgram& pr, const double* sm, int p, int j, double v[3]) {
+  const int d = p < 0 ? -1 : OKIN_LDG(okin_sec(pr, OKIN_S_POINT_DOP) + p);
+  if (d < 0) { okin_point_vel_base(pr, sm, p, j, v); return; }
+  const int32_t* rec = okin_sec(pr, OKIN_S_DOP) + d * OKIN_DOP_STRIDE;
+  double da[3], db[3], dc[3];
+  okin_point_vel1(pr, sm, OKIN_LDG(rec + 2), j, da);
+  okin_point_vel1(pr, sm, OKIN_LDG(rec + 3), j, db);
+  okin_point_vel1(pr, sm, OKIN_LDG(rec + 4), j, dc);
+  okin_point_vel_op(pr, sm, d, da, db, dc, v);
+}
+
+// One generic response on T in {double, OkinDual}; vel == nullptr for plain values.
+template <typename T>
+OKIN_HD T okin_response(const OkinProgram& pr, const double* sm, const int32_t* rec, int j) {
+  const int32_t* hdr = pr.hdr;
+  const double* pos = sm + hdr[OKIN_H_OFF_POS];
+  const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
+  const double* fc = okin_fsec(pr, OKIN_F_MCONST) + OKIN_LDG(rec + 12);
+  const int rtype = OKIN_LDG(rec + 1);
+  OkinV3<T> P[4];
+  for (int k = 0; k < 4; ++k) {
+    const int p = OKIN_LDG(rec + 2 + k);
+    double v[3] = {0.0, 0.0, 0.0};
+    if (p >= 0 && j >= 0) okin_point_vel(pr, sm, p, j, v);
+    P[k] = okin_lift(pos + 3 * (p < 0 ? 0 : p), v, T());
+  }
+  const int d0 = OKIN_LDG(rec + 6), d1 = OKIN_LDG(rec + 7);
+  switch (rtype) {
+    case OKIN_R_COORD: return P[0].x * fc[0] + P[0].y * fc[1] + P[0].z * fc[2];
+    case OKIN_R_DIST: return okin_distance(P[0], P[1]);
+    case OKIN_R_CAMBER: return okin_camber_deg(P[0], P[1], fc[0]);
+    case OKIN_R_TOE: return okin_toe_deg(P[0], P[1], fc[0]);
+    case OKIN_R_CASTER: return okin_caster_deg(P[0], P[1]);
+    case OKIN_R_KPI: return okin_kpi_deg(P[0], P[1], fc[0]);
+    case OKIN_R_ROTATION: {
+      const double* a = pos + 3 * OKIN_LDG(rec + 3);
+      const double* b = pos + 3 * OKIN_LDG(rec + 4);
+      return okin_rotation_deg(P[0], dsn + 3 * d0, a, b) * fc[0];
+    }
+    case OKIN_R_ROTATION_DIFF: {
+      const double* a = pos + 3 * OKIN_LDG(rec + 3);
+      const double* b = pos + 3 * OKIN_LDG(rec + 4);
+      return okin_rotation_deg(P[0], dsn + 3 * d0, a, b) - okin_rotation_deg(P[3], dsn + 3 * d1, a, b);
+    }
+    case OKIN_R_MID_X: return P[0].x + (P[1].x - P[0].x) * 0.5;
+    case OKIN_R_TBAR_TWIST_DEG: return okin_tbar_twist_rad(P[0], P[1], P[2]) * OKIN_RAD2DEG;
+    case OKIN_R_TBAR_TWIST_DELTA: {
+      const double z[3] = {0.0, 0.0, 0.0};
+      const double design = okin_tbar_twist_rad(okin_lift(dsn + 3 * d0, z, 0.0), okin_lift(dsn + 3 * d1, z, 0.0),
+                                                okin_lift(pos + 3 * OKIN_LDG(rec + 4), z, 0.0));
+      return (okin_tbar_twist_rad(P[0], P[1], P[2]) - okin_const(design, T())) * OKIN_RAD2DEG;
+    }
+    case OKIN_R_TBAR_HEAVE: {
+      // signed angle of the crossbar centre about (pivot, +Y) from its design position
+      const T half = okin_const(0.5, T());
+      const OkinV3<T> center = P[0] + okin_scale(P[1] - P[0], half);
+      double dc[3];
+      for (int k = 0; k < 3; ++k) dc[k] = dsn[3 * d0 + k] + (dsn[3 * d1 + k] - dsn[3 * d0 + k]) * 0.5;
+      const double* pivot = pos + 3 * OKIN_LDG(rec + 4);
+      const double pivot_b[3] = {pivot[0], pivot[1] + 1.0, pivot[2]};
+      return okin_rotation_deg(center, dc, pivot, pivot_b);
+    }
+    default: return okin_const(NAN, T());
+  }
+}
+
+// 19 corner state metrics of catalog.py:86-159 for one corner; one lane.
+OKIN_HD void okin_corner_metrics(const OkinProgram& pr, double* sm, const int32_t* rec, double* out, double* ctx) {
+  const int32_t* hdr = pr.hdr;
+  const double* pos = sm + hdr[OKIN_H_OFF_POS];
+  const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
+  const double* fc = okin_fsec(pr, OKIN_F_MCONST) + OKIN_LDG(rec + 18);
+  const double side = fc[0], cg_z = fc[1], wheelbase = fc[2], bias = fc[3];
+  const int flags = OKIN_LDG(rec + 19);
+  const double* ai = pos + 3 * OKIN_LDG(rec + 0);
+  const double* ao = pos + 3 * OKIN_LDG(rec + 1);
+  const double* wc = pos + 3 * OKIN_LDG(rec + 2);
+  const double* cp = pos + 3 * OKIN_LDG(rec + 3);
+  const double* lo = pos + 3 * OKIN_LDG(rec + 4);
+  const double* up = pos + 3 * OKIN_LDG(rec + 5);
+  double* o = out + OKIN_LDG(rec + 17);
+  const double z3[3] = {0.0, 0.0, 0.0};
+  const OkinV3<double> AI = okin_lift(ai, z3, 0.0), AO = okin_lift(ao, z3, 0.0);
+  const OkinV3<double> LO = okin_lift(lo, z3, 0.0), UP = okin_lift(up, z3, 0.0);
+  o[0] = okin_camber_deg(AI, AO, side);
+  o[1] = okin_caster_deg(LO, UP);
+  o[2] = okin_kpi_deg(LO, UP, side);
+  o[5] = okin_toe_deg(AI, AO, side);
+  // steering axis / ground plane at the contact-patch height (context.py:118-141)
+  const double sd[3] = {up[0] - lo[0], up[1] - lo[1], up[2] - lo[2]};
+  double ax[3] = {ao[0] - ai[0], ao[1] - ai[1], ao[2] - ai[2]};
+  const double ial = 1.0 / sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+  ax[0] *= ial; ax[1] *= ial; ax[2] *= ial;
+  if (fabs(sd[2]) < OKIN_GEOM_EPS) {
+    o[3] = NAN; o[4] = NAN;
+  } else {
+    const double t = (cp[2] - lo[2]) / sd[2];
+    const double gp[3] = {lo[0] + t * sd[0], lo[1] + t * sd[1], lo[2] + t * sd[2]};
+    const double wl = 1.0 / sqrt(ax[0] * ax[0] + ax[1] * ax[1]);
+    o[3] = -((gp[0] - cp[0]) * ax[0] * wl + (gp[1] - cp[1]) * ax[1] * wl);  // scrub radius
+    o[4] = gp[0] - cp[0];                                                  // mechanical trail
+  }
+  // instant axis = intersection of two planes n.x + d = 0 (geometric.py:216-302)
+  double n1[3], n2[3], d1, d2;
+  bool ok = true;
+  {
+    const double* a = pos + 3 * OKIN_LDG(rec + 7);
+    const double* b = pos + 3 * OKIN_LDG(rec + 8);
+    const double* c = pos + 3 * OKIN_LDG(rec + 9);
+    const double u[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, w[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    n1[0] = u[1] * w[2] - u[2] * w[1]; n1[1] = u[2] * w[0] - u[0] * w[2]; n1[2] = u[0] * w[1] - u[1] * w[0];
+    const double m = sqrt(n1[0] * n1[0] + n1[1] * n1[1] + n1[2] * n1[2]);
+    ok = ok && m >= OKIN_GEOM_EPS;
+    n1[0] /= m; n1[1] /= m; n1[2] /= m;
+    d1 = -(n1[0] * a[0] + n1[1] * a[1] + n1[2] * a[2]);
+  }
+  if (OKIN_LDG(rec + 6) == OKIN_IC_DW) {
+    const double* a = pos + 3 * OKIN_LDG(rec + 10);
+    const double* b = pos + 3 * OKIN_LDG(rec + 11);
+    const double* c = pos + 3 * OKIN_LDG(rec + 12);
+    const double u[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, w[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    n2[0] = u[1] * w[2] - u[2] * w[1]; n2[1] = u[2] * w[0] - u[0] * w[2]; n2[2] = u[0] * w[1] - u[1] * w[0];
+    const double m = sqrt(n2[0] * n2[0] + n2[1] * n2[1] + n2[2] * n2[2]);
+    ok = ok && m >= OKIN_GEOM_EPS;
+    n2[0] /= m; n2[1] /= m; n2[2] /= m;
+    d2 = -(n2[0] * a[0] + n2[1] * a[1] + n2[2] * a[2]);
+  } else {  // MacPherson: plane through the strut top normal to the strut axis (macpherson.py:346-355)
+    const double* ball = pos + 3 * OKIN_LDG(rec + 9);
+    const double* top = pos + 3 * OKIN_LDG(rec + 10);
+    n2[0] = top[0] - ball[0]; n2[1] = top[1] - ball[1]; n2[2] = top[2] - ball[2];
+    const double m = sqrt(n2[0] * n2[0] + n2[1] * n2[1] + n2[2] * n2[2]);
+    n2[0] /= m; n2[1] /= m; n2[2] /= m;
+    d2 = -(n2[0] * top[0] + n2[1] * top[1] + n2[2] * top[2]);
+  }
+  double dir[3] = {n1[1] * n2[2] - n1[2] * n2[1], n1[2] * n2[0] - n1[0] * n2[2], n1[0] * n2[1] - n1[1] * n2[0]};
+  const double dm2 = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
+  ok = ok && dm2 >= OKIN_GEOM_EPS * OKIN_GEOM_EPS;
+  const double q[3] = {d2 * n1[0] - d1 * n2[0], d2 * n1[1] - d1 * n2[1], d2 * n1[2] - d1 * n2[2]};
+  const double pt[3] = {(q[1] * dir[2] - q[2] * dir[1]) / dm2, (q[2] * dir[0] - q[0] * dir[2]) / dm2,
+                        (q[0] * dir[1] - q[1] * dir[0]) / dm2};
+  const double idm = 1.0 / sqrt(dm2);
+  dir[0] *= idm; dir[1] *= idm; dir[2] *= idm;
+  const bool sv_ok = ok && fabs(dir[1]) >= OKIN_GEOM_EPS;  // y = wc.y plane (double_wishbone.py:352-376)
+  const bool fv_ok = ok && fabs(dir[0]) >= OKIN_GEOM_EPS;  // x = wc.x plane (:405-431)
+  double svic[3] = {NAN, NAN, NAN}, fvic[3] = {NAN, NAN, NAN};
+  if (sv_ok) {
+    const double t = (wc[1] - pt[1]) / dir[1];
+    for (int k = 0; k < 3; ++k) svic[k] = pt[k] + t * dir[k];
+  }
+  if (fv_ok) {
+    const double t = (wc[0] - pt[0]) / dir[0];
+    for (int k = 0; k < 3; ++k) fvic[k] = pt[k] + t * dir[k];
+  }
+  o[6] = svic[0]; o[7] = svic[2];
+  o[8] = sv_ok ? svic[0] - cp[0] : NAN;
+  o[9] = fvic[1]; o[10] = fvic[2];
+  if (fv_ok) {
+    const double dy = fvic[1] - cp[1], dz = fvic[2] - cp[2];
+    const double sgn = dy > 0.0 ? 1.0 : (dy < 0.0 ? -1.0 : 0.0);
+    o[11] = sqrt(dy * dy + dz * dz) * (-side * sgn);
+  } else {
+    o[11] = NAN;
+  }
+  o[12] = wc[2] - dsn[3 * OKIN_LDG(rec + 15) + 2];
+  o[13] = fabs(cp[1]);
+  const int dt = OKIN_LDG(rec + 13), db = OKIN_LDG(rec + 14);
+  if (dt >= 0) {
+    const double* a = pos + 3 * dt;
+    const double* b = pos + 3 * db;
+    o[14] = sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+  } else {
+    o[14] = NAN;
+  }
+  // anti geometry (anti_geometry.py:33-206)
+  const double run_cp = svic[0] - cp[0];
+  o[15] = (sv_ok && fabs(run_cp) >= OKIN_GEOM_EPS) ? atan((svic[2] - cp[2]) / run_cp) * OKIN_RAD2DEG : NAN;
+  const double height = cg_z - cp[2];
+  const bool h_ok = height > OKIN_GEOM_EPS;
+  o[16] = NAN; o[17] = NAN; o[18] = NAN;
+  if ((flags & OKIN_MF_FRONT) && (flags & OKIN_MF_HAS_BIAS) && sv_ok && fabs(run_cp) >= OKIN_GEOM_EPS && h_ok)
+    o[16] = 100.0 * bias * (wheelbase / height) * ((svic[2] - cp[2]) / (cp[0] - svic[0]));
+  if ((flags & OKIN_MF_REAR) && (flags & OKIN_MF_HAS_BIAS) && sv_ok && fabs(run_cp) >= OKIN_GEOM_EPS && h_ok)
+    o[17] = 100.0 * (1.0 - bias) * (wheelbase / height) * ((svic[2] - cp[2]) / run_cp);
+  if ((flags & OKIN_MF_DRIVEN_HERE) && sv_ok && h_ok) {
+    const double run = (flags & OKIN_MF_FRONT) ? wc[0] - svic[0] : svic[0] - wc[0];
+    if (fabs(run) >= OKIN_GEOM_EPS) o[18] = 100.0 * (wheelbase / height) * ((svic[2] - wc[2]) / run);
+  }
+  ctx[0] = fvic[1]; ctx[1] = fvic[2]; ctx[2] = fv_ok ? 1.0 : 0.0;
+}
+
+// All metric columns of one state into out[NM].
+template <typename Dummy = void>
+OKIN_FN void okin_metrics(const OkinProgram& pr, double* sm, double* out) {
+  const int32_t* hdr = pr.hdr;
+  const int nmc = hdr[OKIN_H_NMC], nmop = hdr[OKIN_H_NMOP];
+  const int32_t* corners = okin_sec(pr, OKIN_S_MCORNER);
+  const int32_t* mops = okin_sec(pr, OKIN_S_MOP);
+  double* ctx = sm + hdr[OKIN_H_OFF_MCTX];
+  const int nt = hdr[OKIN_H_NT];
+  OKIN_PHASE_BEGIN
+  if (lane < nmc) okin_corner_metrics(pr, sm, corners + lane * OKIN_MCORNER_STRIDE, out, ctx + 4 * lane);
+  for (int t = lane - nmc; t < nmop; t += 32 - nmc) {
+    if (t < 0) continue;
+    const int32_t* rec = mops + t * OKIN_MOP_STRIDE;
+    double value;
+    if (OKIN_LDG(rec + 0) == OKIN_MOP_VALUE) {
+      value = okin_response<double>(pr, sm, rec, -1);
+    } else {
+      // select the tangent with the strongest driver rate (derivatives.py:273-309)
+      const int dp = OKIN_LDG(rec + 8), da = OKIN_LDG(rec + 9), mask = OKIN_LDG(rec + 10);
+      int best = -1;
+      double strongest = 0.0, best_rate = 0.0;
+      bool tied = false;
+      for (int j = 0; j < nt; ++j) {
+        if (!((mask >> j) & 1)) continue;
+        double v[3];
+        okin_point_vel(pr, sm, dp, j, v);
+        const double rate = fabs(v[da]);
+        if (rate > strongest + OKIN_GEOM_EPS) { best = j; strongest = rate; best_rate = v[da]; tied = false; }
+        else if (rate >= OKIN_GEOM_EPS && fabs(rate - strongest) <= OKIN_GEOM_EPS) tied = true;
+      }
+      if (best < 0 || strongest < OKIN_GEOM_EPS || tied) {
+        value = NAN;
+      } else {
+        const OkinDual resp = okin_response<OkinDual>(pr, sm, rec, best);
+        value = resp.d / best_rate;
+      }
+    }
+    out[OKIN_LDG(rec + 11)] = value;
+  }
+  OKIN_PHASE_END
+  if (hdr[OKIN_H_NMAXLE]) {
+    // axle-level state metrics (axle_metrics.py:18-95)
+    const int32_t* rec = okin_sec(pr, OKIN_S_MAXLE);
+    const double* pos = sm + hdr[OKIN_H_OFF_POS];
+    const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
+    OKIN_PHASE_BEGIN
+    if (lane == 0) {
+      const double* wcL = pos + 3 * OKIN_LDG(rec + 0);
+      const double* wcR = pos + 3 * OKIN_LDG(rec + 1);
+      const double* cpL = pos + 3 * OKIN_LDG(rec + 2);
+      const double* cpR = pos + 3 * OKIN_LDG(rec + 3);
+      const double lz = wcL[2] - dsn[3 * OKIN_LDG(rec + 4) + 2], rz = wcR[2] - dsn[3 * OKIN_LDG(rec + 5) + 2];
+      const double clz = cpL[2] - dsn[3 * OKIN_LDG(rec + 6) + 2], crz = cpR[2] - dsn[3 * OKIN_LDG(rec + 7) + 2];
+      const double track = fabs(cpL[1] - cpR[1]);
+      double* o = out + OKIN_LDG(rec + 10);
+      o[0] = 0.5 * (lz + rz);
+      o[1] = atan2(lz - rz, track) * OKIN_RAD2DEG;
+      o[2] = -0.5 * (clz + crz);
+      o[3] = track;
+      o[4] = NAN; o[5] = NAN;
+      if (ctx[2] != 0.0 && ctx[6] != 0.0) {
+        const double l2 = ctx[0] - cpL[1], l3 = ctx[1] - cpL[2], r2 = ctx[4] - cpR[1], r3 = ctx[5] - cpR[2];
+        const double den = l2 * r3 - l3 * r2;
+        if (fabs(den) >= OKIN_GEOM_EPS) {
+          const double par = ((cpR[1] - cpL[1]) * r3 - (cpR[2] - cpL[2]) * r2) / den;
+          o[4] = cpL[1] + par * l2;
+          o[5] = cpL[2] + par * l3;
+        }
+      }
+      const int rack = OKIN_LDG(rec + 8);
+      o[6] = rack >= 0 ? pos[3 * rack + 1] - dsn[3 * OKIN_LDG(rec + 9) + 1] : NAN;
+    }
+    OKIN_PHASE_END
+  }
+}
+
 struct OkinOutputs {
   double* positions;      // [n_steps][NOUT*3] or null
   int32_t* iters;         // [n_steps] or null
   double* max_residual;   // [n_steps] or null
   double* tangents;       // [n_steps][NT][3*NF] (reference column order) or null
+  double* metrics;        // [n_steps][NM] or null (NaN == the reference's None)
   int32_t* status;        // [1]
   int32_t* failed_step;   // [1]
 };
@@ -813,7 +1126,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
       if (status == OKIN_STATUS_OK) {
-        if (out.tangents || !tangents_ready) {
+        if (out.tangents || out.metrics || !tangents_ready) {
           // Exported tangents are taken at the solution itself: relinearise there.  (For the
           // predictor alone the factor of the last Gauss-Newton point, <= coarse_tol away, is
           // enough and was solved together with the chord step.)
@@ -843,6 +1156,17 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       for (int t = lane; t < 3 * nout; t += 32)
         dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
       OKIN_PHASE_END
+    }
+    if (out.metrics) {
+      const int nm = hdr[OKIN_H_NM];
+      double* dst = out.metrics + (size_t)s * nm;
+      if (ok) {
+        okin_metrics(pr, sm, dst);
+      } else {
+        OKIN_PHASE_BEGIN
+        for (int t = lane; t < nm; t += 32) dst[t] = NAN;
+        OKIN_PHASE_END
+      }
     }
     if (out.tangents) {
       double* dst = out.tangents + (size_t)s * nt * n;

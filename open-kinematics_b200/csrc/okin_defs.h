@@ -93,9 +93,16 @@ enum okin_hdr_slot {
   OKIN_H_OFF_POS, OKIN_H_OFF_CST, OKIN_H_OFF_R, OKIN_H_OFF_RG, OKIN_H_OFF_DBLK, OKIN_H_OFF_LB,
   OKIN_H_OFF_DFAC, OKIN_H_OFF_VEC, OKIN_H_OFF_XSAVE, OKIN_H_OFF_RED, OKIN_H_OFF_PAR, OKIN_H_OFF_PPREV,
   OKIN_H_SMEM_DOUBLES, // shared-memory doubles per instance
-  OKIN_H_SEC0 = 32,
-  OKIN_H_FSEC0 = 32 + 2 * 40,
-  OKIN_HDR_SIZE = 32 + 2 * 40 + 2 * 4
+  // metric program (csrc/okin_metrics.cuh)
+  OKIN_H_NM,       // metric columns per state
+  OKIN_H_NMC,      // corner records
+  OKIN_H_NMOP,     // generic metric ops
+  OKIN_H_NMAXLE,   // 0 or 1 axle record
+  OKIN_H_NDSN,     // design-pose slots kept for the metrics
+  OKIN_H_OFF_DSN, OKIN_H_OFF_MCTX,
+  OKIN_H_SEC0 = 48,
+  OKIN_H_FSEC0 = 48 + 2 * 40,
+  OKIN_HDR_SIZE = 48 + 2 * 40 + 2 * 4
 };
 #define OKIN_MAGIC 0x4f4b494e  // "OKIN"
 
@@ -133,12 +140,18 @@ enum okin_isec {
   OKIN_S_OUT_POINT,      // [NOUT]
   OKIN_S_ROW_ORDER,      // [NROW+NREP] evaluation order (rows grouped by family)
   OKIN_S_DOP_LEV,        // [n_derived_levels+1] ranges of DOP evaluated in one parallel phase
+  OKIN_S_POINT_ELIM,     // [P] elimination position of a free point, else -1
+  OKIN_S_POINT_DOP,      // [P] derived-op index of a derived point, else -1
+  OKIN_S_DESIGN_PT,      // [NDSN] points whose design position is kept for the metrics
+  OKIN_S_MCORNER,        // [NMC][OKIN_MCORNER_STRIDE]
+  OKIN_S_MOP,            // [NMOP][OKIN_MOP_STRIDE]
+  OKIN_S_MAXLE,          // [NMAXLE][OKIN_MAXLE_STRIDE]
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000
 
 // double sections
-enum okin_fsec { OKIN_F_PAR_VAL = 0, OKIN_F_CST_INIT, OKIN_F_COUNT };
+enum okin_fsec { OKIN_F_PAR_VAL = 0, OKIN_F_CST_INIT, OKIN_F_MCONST, OKIN_F_COUNT };
 
 // Row record: int32[OKIN_ROW_STRIDE]
 enum okin_row_slot {

@@ -11,7 +11,7 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
                               int n_steps, const double* hardpoints, const double* tvals, double step_tol,
                               double coarse_tol, double residual_tol, double mu_init, int max_iter, int use_predictor,
                               double* positions, int32_t* iters, double* max_residual, double* tangents,
-                              int32_t* status, int32_t* failed_step) {
+                              double* metrics, int32_t* status, int32_t* failed_step) {
   if (hdr[OKIN_H_MAGIC] != OKIN_MAGIC) return -1;
   OkinProgram pr{hdr, ib, fb};
   OkinSolverCfg cfg{step_tol, coarse_tol, residual_tol, mu_init, max_iter, use_predictor};
@@ -24,6 +24,7 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
     out.iters = iters ? iters + (size_t)i * n_steps : nullptr;
     out.max_residual = max_residual ? max_residual + (size_t)i * n_steps : nullptr;
     out.tangents = tangents ? tangents + (size_t)i * n_steps * nt * n : nullptr;
+    out.metrics = metrics ? metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
     out.status = status + i;
     out.failed_step = failed_step + i;
     okin_sweep(pr, sm.data(), hardpoints + (size_t)i * 3 * nin, tvals, n_steps, cfg, out);

@@ -38,6 +38,7 @@ from kinematics.core.input import build_suspension, build_sweep  # noqa: E402
 from kinematics.core.points.derived.manager import DerivedPointsManager  # noqa: E402
 from kinematics.core.primitives.geometry import Direction3, Point3  # noqa: E402
 from kinematics.core.sensitivity import compute_state_tangents  # noqa: E402
+from kinematics.core.sweep import compute_sweep_metrics  # noqa: E402
 from kinematics.core.solver import (  # noqa: E402
     ResidualComputer, SolverConfig, convert_targets_to_absolute, solve_suspension_sweep,
 )
@@ -148,6 +149,14 @@ def run_case(name: str, geom: dict, sweep: dict, with_default=True) -> None:
     arrays["tangent_rank"] = np.array(rank)
     arrays["tangent_sigma_min"] = np.array(smin)
     arrays["tangent_cond"] = np.array(cond)
+    # metric rows (state + derivative metrics) evaluated by the reference on its tight states
+    result = compute_sweep_metrics(sus, cfg, states_t)
+    assert result.derivative_error is None, result.derivative_error
+    flat_rows = [row.flat_row() if hasattr(row, "flat_row") else row for row in result.rows]
+    names = list(flat_rows[0].keys())
+    assert all(list(r.keys()) == names for r in flat_rows)
+    arrays["metrics"] = np.array([[np.nan if r[k] is None else float(r[k]) for k in names] for r in flat_rows])
+    meta["metric_names"] = names
     arrays["design_positions"] = np.array([init.positions[k].data for k in keys])
     arrays["sweep_values"] = np.array([[t.value for t in sw] for sw in cfg.target_sweeps])
     meta.update(

@@ -135,7 +135,7 @@ def emu_lib():
             [ctypes.c_void_p] * 3 + [ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_int, ctypes.c_int]
-            + [ctypes.c_void_p] * 6)
+            + [ctypes.c_void_p] * 7)
         _EMU = lib
     return _EMU
 
@@ -149,13 +149,15 @@ def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, step_tol=1e-6
         "positions": np.zeros((n_inst, n_steps, program.n_out, 3)), "iters": np.zeros((n_inst, n_steps), np.int32),
         "max_residual": np.zeros((n_inst, n_steps)), "tangents": np.zeros((n_inst, n_steps, nt, n)),
         "status": np.zeros(n_inst, np.int32), "failed_step": np.zeros(n_inst, np.int32),
+        "metrics": np.zeros((n_inst, n_steps, max(len(program.metric_names), 1))),
     }
     hdr = np.ascontiguousarray(program.hdr)
     rc = emu_lib().okin_emu_sweep(
         hdr.ctypes.data, program.iblob.ctypes.data, program.fblob.ctypes.data, n_inst, n_steps,
         hp.ctypes.data, tv.ctypes.data, step_tol, coarse_tol, residual_tol, mu_init, max_iter, use_predictor,
         out["positions"].ctypes.data, out["iters"].ctypes.data, out["max_residual"].ctypes.data,
-        out["tangents"].ctypes.data, out["status"].ctypes.data, out["failed_step"].ctypes.data)
+        out["tangents"].ctypes.data, out["metrics"].ctypes.data if program.metric_names else None,
+        out["status"].ctypes.data, out["failed_step"].ctypes.data)
     assert rc == 0
     return out
 

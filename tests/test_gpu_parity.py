@@ -18,7 +18,8 @@ def gpu_solve(prog, hardpoints, values, **cfg):
     from open_kinematics_b200 import _lib
     topo = _lib.DeviceTopology(prog)
     try:
-        out = topo.solve_batch(hardpoints, values, _lib.default_cfg(**cfg), want_tangents=True)
+        out = topo.solve_batch(hardpoints, values, _lib.default_cfg(**cfg), want_tangents=True,
+                               want_metrics=bool(prog.metric_names))
     finally:
         topo.close()
     return out
@@ -37,6 +38,21 @@ def test_positions_match_reference_tight_run(case):
     scale = max(1.0, np.abs(arr["tangents"]).max())
     assert np.abs(out["tangents"][0] - arr["tangents"]).max() <= 1e-7 * scale
     assert out["max_residual"].max() < 1e-5
+
+
+@pytest.mark.parametrize("case", SWEEP_CASES)
+def test_metric_rows_match_reference(case):
+    """State, mechanism and derivative metrics evaluated on the device vs the reference's
+    compute_sweep_metrics rows (angles within 1e-9 rad)."""
+    from open_kinematics_b200.core.topology import compile_suspension
+    from test_emu_metrics import check_metrics
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    prog = compile_suspension(sus, sweep)
+    assert prog.metric_names == meta["metric_names"]
+    out = gpu_solve(prog, _nominal(sus, prog), arr["sweep_values"])
+    assert out["status"][0] == 0
+    check_metrics(prog.metric_names, out["metrics"][0], arr["metrics"])
 
 
 @pytest.mark.parametrize("batch,case", [("batch_c1", "c1_dw_corner_bump"), ("batch_c2", "c2_macpherson_bump_steer"),
