@@ -80,6 +80,26 @@ def algorithmic_flops_per_state(stats: dict, mean_iters: float, n_targets: int) 
     return lin_solves * per_iter + eval_flops + n_targets * 2.0 * stats["solve_fma"]
 
 
+def rank_seed(rank: int) -> int:
+    """Perturbation seed of a rank: config index (2) + rank, so ranks draw disjoint streams."""
+    return 2 + rank
+
+
+def reduce_max_ms(values, device, world: int) -> list:
+    """Max over ranks of per-rank timings (the job is as slow as its slowest rank)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.tolist()]
+
+
+def job_throughput(units_per_rank: float, world: int, ms: float) -> float:
+    """Whole-job units per second with per-rank work fixed (weak scaling)."""
+    return world * units_per_rank / (ms * 1e-3)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -228,7 +248,7 @@ def run_cuda(args) -> None:
     # ---- device-resident inputs (value) ---------------------------------------------------
     own, pairs = perturbation_mask(prog)
     gen = torch.Generator(device=dev)
-    gen.manual_seed(2 + rank)                                   # seed = config index (+ rank)
+    gen.manual_seed(rank_seed(rank))
     nominal = torch.tensor(solver.nominal_hardpoints(), device=dev, dtype=torch.float64).reshape(-1, 3)
     hp = nominal.unsqueeze(0).repeat(n_inst, 1, 1)
     own_t = torch.tensor(own, device=dev)
@@ -308,15 +328,12 @@ def run_cuda(args) -> None:
     e2e_ok = float((h_status == 0).double().mean().item())
 
     # ---- reduce over ranks (max time) ------------------------------------------------------
-    t = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max, e2e_s_max = float(t[0].item()), float(t[1].item())
+    total_ms_max, e2e_s_max = reduce_max_ms([total_ms, e2e_s], dev, world)
 
     if rank == 0:
         ms_per_step = total_ms_max / args.steps
-        value = world * states_per_launch / (ms_per_step * 1e-3)
-        e2e_value = world * e2e_inst * S / e2e_s_max
+        value = job_throughput(states_per_launch, world, ms_per_step)
+        e2e_value = job_throughput(e2e_inst * S, world, e2e_s_max * 1e3)
         peak = ctypes.c_double(0.0)
         _lib.check(lib.okin_fp64_peak(local, ctypes.byref(peak)), "okin_fp64_peak")
         flops_state = algorithmic_flops_per_state(prog.stats, mean_iters, nt)

@@ -107,6 +107,10 @@ int okin_solve_batch_device(okin_topology* topo, const okin_solver_cfg* cfg, int
                             int32_t* d_failed_step_out, int32_t* d_iters_out, double* d_max_residual_out,
                             double* d_tangents_out, double* d_metrics_out);
 
+/* Instance range [begin, begin+count) that shard k of n_shards owns: [k*N/G, (k+1)*N/G).  The
+ * same rule splits a host batch over device_ids and a torchrun job over ranks. */
+int okin_shard_range(int64_t n_instances, int32_t shard, int32_t n_shards, int64_t* begin, int64_t* count);
+
 /* Launch geometry the library would use for n_instances on `device` (for reporting). */
 int okin_launch_geometry(okin_topology* topo, int32_t device, int64_t n_instances, int32_t* grid, int32_t* block,
                          int32_t* smem_bytes, int32_t* ctas_per_sm);

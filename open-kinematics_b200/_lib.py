@@ -58,6 +58,8 @@ SIGNATURES = {
         ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "okin_shard_range": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "okin_launch_geometry": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_i32p]),
     "okin_fp64_peak": (ctypes.c_int, [ctypes.c_int32, c_f64p]),
@@ -125,6 +127,13 @@ def device_count() -> int:
 def require_device() -> None:
     if device_count() < 1:
         raise RuntimeError("No CUDA device visible: the solver has no CPU fallback (" + last_error() + ")")
+
+
+def shard_range(n_instances: int, shard: int, n_shards: int) -> tuple:
+    begin, count = ctypes.c_int64(), ctypes.c_int64()
+    check(load().okin_shard_range(n_instances, shard, n_shards, ctypes.byref(begin), ctypes.byref(count)),
+          "okin_shard_range")
+    return begin.value, count.value
 
 
 def default_cfg(**overrides) -> SolverCfg:

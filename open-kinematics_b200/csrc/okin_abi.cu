@@ -268,6 +268,14 @@ int okin_solve_batch_device(okin_topology* t, const okin_solver_cfg* cfg, int32_
                 d_metrics_out);
 }
 
+int okin_shard_range(int64_t n_instances, int32_t shard, int32_t n_shards, int64_t* begin, int64_t* count) {
+  if (!begin || !count || n_instances < 0 || n_shards < 1 || shard < 0 || shard >= n_shards)
+    return fail(OKIN_ERR_USAGE, "invalid shard arguments");
+  *begin = n_instances * shard / n_shards;
+  *count = n_instances * (shard + 1) / n_shards - *begin;
+  return OKIN_OK;
+}
+
 int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
                      const double* hardpoints, const double* target_values, const int32_t* device_ids,
                      int32_t n_devices, double* positions_out, int32_t* status_out, int32_t* failed_step_out,
@@ -297,8 +305,7 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
   for (int k = 0; k < n_devices; ++k) {
     Shard s{};
     s.device = device_ids[k];
-    s.begin = n_instances * k / n_devices;
-    s.count = n_instances * (k + 1) / n_devices - s.begin;
+    okin_shard_range(n_instances, k, n_devices, &s.begin, &s.count);
     if (s.count == 0) continue;
     rc = ensure_device(t, s.device, &s.d);
     if (rc) return rc;

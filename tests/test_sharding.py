@@ -1,0 +1,59 @@
+"""Multi-GPU plumbing that does not need a GPU: the instance-range rule of the C ABI and the
+rank protocol of bench.py (world_size 2 over gloo on the CPU)."""
+
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from open_kinematics_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n,g", [(0, 1), (1, 8), (7, 2), (1000003, 8), (1 << 20, 4), (5, 8)])
+def test_shard_ranges_partition_the_batch(n, g):
+    ranges = [_lib.shard_range(n, k, g) for k in range(g)]
+    assert ranges[0][0] == 0
+    assert sum(c for _, c in ranges) == n
+    for (b0, c0), (b1, _) in zip(ranges, ranges[1:]):
+        assert b0 + c0 == b1
+    counts = [c for _, c in ranges]
+    assert max(counts) - min(counts) <= 1
+
+
+def test_shard_range_rejects_bad_arguments():
+    with pytest.raises(RuntimeError):
+        _lib.shard_range(10, 3, 2)
+
+
+def _rank_main(rank: int, world: int, port: int, out_dir: str) -> None:
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import bench
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # each rank owns a contiguous instance range and its own perturbation seed
+    n_total = 1001
+    begin, count = _lib.shard_range(n_total, rank, world)
+    seed = bench.rank_seed(rank)
+    # per-rank timing -> job timing = max over ranks; job throughput = all units / that time
+    local_ms = 10.0 * (rank + 1)
+    ms_max = bench.reduce_max_ms([local_ms, 2.0 * local_ms], torch.device("cpu"), world)
+    value = bench.job_throughput(units_per_rank=count * 21, world=world, ms=ms_max[0])
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array([begin, count, seed, ms_max[0], ms_max[1], value]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_rank_protocol_world_size_2_gloo(tmp_path):
+    world, port = 2, 29000 + os.getpid() % 2000
+    mp.spawn(_rank_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    rows = [np.load(tmp_path / f"rank{r}.npy") for r in range(world)]
+    assert rows[0][0] == 0 and rows[0][0] + rows[0][1] == rows[1][0] and rows[1][0] + rows[1][1] == 1001
+    assert rows[0][2] != rows[1][2]                      # different perturbation streams
+    for r in rows:                                       # every rank sees the max over ranks
+        assert r[3] == 20.0 and r[4] == 40.0
