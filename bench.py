@@ -347,6 +347,13 @@ def run_cuda(args) -> None:
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes_state = nout3 * 8 + 12 + (nin3 * 8 + 8) / S
         hbm_achieved = alg_bytes_state * states_per_launch / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+            traffic = tj["dram_bytes_per_state"] * states_per_launch
+            traffic_src = tj["source"]
+        except (OSError, KeyError):
+            pass
         geo = topo.launch_geometry(n_inst, local)
         base = cpu_baseline(sample_instances=args.cpu_sample, processes=1)
         line = {
@@ -366,7 +373,8 @@ def run_cuda(args) -> None:
             "clocks": clocks,
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tflops, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved_tflops / peak.value if peak.value else None, "traffic": None,
+                "frac": achieved_tflops / peak.value if peak.value else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": "okin_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic_flops_per_state": flops_state, "kernel_ms": k_ms,
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
