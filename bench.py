@@ -267,8 +267,8 @@ def run_cuda(args) -> None:
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.okin_solve_batch_device(
             topo.handle, ctypes.byref(cfg), local, ctypes.c_void_p(stream), n_inst, S,
-            hp.data_ptr(), tv.data_ptr(), pos.data_ptr(), status.data_ptr(), failed.data_ptr(),
-            iters.data_ptr(), maxres.data_ptr(), None, None), "okin_solve_batch_device")
+            hp.data_ptr(), None, tv.data_ptr(), pos.data_ptr(), status.data_ptr(), failed.data_ptr(),
+            iters.data_ptr(), maxres.data_ptr(), None, None, None), "okin_solve_batch_device")
 
     def barrier():
         if world > 1:
@@ -312,9 +312,9 @@ def run_cuda(args) -> None:
 
     def e2e_call():
         _lib.check(lib.okin_solve_batch(
-            topo.handle, ctypes.byref(cfg), e2e_inst, S, h_hp.data_ptr(), h_tv.data_ptr(), devs.ctypes.data, 1,
+            topo.handle, ctypes.byref(cfg), e2e_inst, S, h_hp.data_ptr(), None, h_tv.data_ptr(), devs.ctypes.data, 1,
             h_pos.data_ptr(), h_status.data_ptr(), h_failed.data_ptr(), h_iters.data_ptr(), h_maxres.data_ptr(),
-            None, None), "okin_solve_batch")
+            None, None, None), "okin_solve_batch")
 
     for _ in range(2):
         e2e_call()

@@ -7,7 +7,9 @@
  *   okin_topology_create   <- ResidualComputer.__init__ / build_jac_plan (solver.py:187-214,
  *                             :281-500) + DerivedPointsManager.__init__ (points/derived/
  *                             manager.py:95-105): everything computed once per topology.
- *   okin_solve_batch       <- solve_suspension_sweep (solver.py:654-776), once per instance,
+ *   okin_solve_batch       <- Suspension.initial_state() incl. the camber-shim pre-solve
+ *                             (corner/double_wishbone.py:233-257, :501-571, config/shims.py:284-501),
+ *                             solve_suspension_sweep (solver.py:654-776), once per instance,
  *                             plus compute_state_tangents (sensitivity.py:57-143) when
  *                             tangents_out is given and Suspension.compute_state_metrics
  *                             (suspensions/base.py:198-204 -> metrics/main.py:63, :145) when
@@ -23,6 +25,9 @@
  * instance reads and writes coalesced rows and an instance range is one contiguous slab):
  *   hardpoints      [n_instances][n_in_points*3]     authored positions, slot order = the
  *                                                    compiled topology's input points
+ *   params          [n_instances][n_params]          per-instance scalar parameters (camber-shim face
+ *                                                    datums, normal and thicknesses per shimmed
+ *                                                    corner); NULL = the topology's defaults
  *   target_values   [n_targets][n_steps]             sweep values shared by all instances
  *                                                    (relative displacement or absolute coordinate,
  *                                                    as declared per target)
@@ -33,6 +38,8 @@
  *   metrics_out     [n_instances][n_steps][n_metrics]  state / mechanism / derivative metric columns in
  *                                                    the reference's flat export order; NaN where the
  *                                                    reference yields None
+ *   design_out      [n_instances][n_out_points*3]    design (setup) pose after the camber-shim
+ *                                                    pre-solve and derived points
  *   status_out      [n_instances]                    OKIN_STATUS_*
  *   failed_step_out [n_instances]                    -1 or the first failed step
  * Any *_out pointer except status_out / failed_step_out may be NULL.
@@ -84,7 +91,7 @@ typedef struct okin_solver_cfg {
 
 typedef struct okin_topology_info {
   int32_t n_points, n_in_points, n_out_points, n_unknowns, n_targets, n_rows;
-  int32_t smem_bytes_per_instance, n_levels, n_metrics;
+  int32_t smem_bytes_per_instance, n_levels, n_metrics, n_params;
 } okin_topology_info;
 
 int okin_device_count(int* out);
@@ -95,17 +102,19 @@ int okin_topology_get_info(const okin_topology* topo, okin_topology_info* out);
 
 /* Host buffers; instance range sharded evenly over device_ids (NULL / 0 => device 0). */
 int okin_solve_batch(okin_topology* topo, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
-                     const double* hardpoints, const double* target_values, const int32_t* device_ids,
-                     int32_t n_devices, double* positions_out, int32_t* status_out, int32_t* failed_step_out,
-                     int32_t* iters_out, double* max_residual_out, double* tangents_out, double* metrics_out);
+                     const double* hardpoints, const double* params, const double* target_values,
+                     const int32_t* device_ids, int32_t n_devices, double* positions_out, int32_t* status_out,
+                     int32_t* failed_step_out, int32_t* iters_out, double* max_residual_out, double* tangents_out,
+                     double* metrics_out, double* design_out);
 
 /* Device buffers on `device`; enqueues on `stream` (a cudaStream_t, may be NULL) and returns
  * without synchronising. */
 int okin_solve_batch_device(okin_topology* topo, const okin_solver_cfg* cfg, int32_t device, void* stream,
                             int64_t n_instances, int32_t n_steps, const double* d_hardpoints,
-                            const double* d_target_values, double* d_positions_out, int32_t* d_status_out,
-                            int32_t* d_failed_step_out, int32_t* d_iters_out, double* d_max_residual_out,
-                            double* d_tangents_out, double* d_metrics_out);
+                            const double* d_params, const double* d_target_values, double* d_positions_out,
+                            int32_t* d_status_out, int32_t* d_failed_step_out, int32_t* d_iters_out,
+                            double* d_max_residual_out, double* d_tangents_out, double* d_metrics_out,
+                            double* d_design_out);
 
 /* Instance range [begin, begin+count) that shard k of n_shards owns: [k*N/G, (k+1)*N/G).  The
  * same rule splits a host batch over device_ids and a torchrun job over ranks. */

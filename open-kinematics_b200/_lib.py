@@ -39,7 +39,7 @@ class SolverCfg(ctypes.Structure):
 class TopologyInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "n_points", "n_in_points", "n_out_points", "n_unknowns", "n_targets", "n_rows",
-        "smem_bytes_per_instance", "n_levels", "n_metrics")]
+        "smem_bytes_per_instance", "n_levels", "n_metrics", "n_params")]
 
 
 # name -> (restype, argtypes); also the list the "exports every declared symbol" test checks.
@@ -51,13 +51,13 @@ SIGNATURES = {
     "okin_topology_get_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(TopologyInfo)]),
     "okin_solve_batch": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int64, ctypes.c_int32,
-        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-        ctypes.c_void_p]),
+        ctypes.c_void_p, ctypes.c_void_p]),
     "okin_solve_batch_device": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "okin_shard_range": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "okin_launch_geometry": (ctypes.c_int, [
@@ -184,7 +184,8 @@ class DeviceTopology:
 
     # -- host buffers ------------------------------------------------------------------
     def solve_batch(self, hardpoints: np.ndarray, target_values: np.ndarray, cfg: SolverCfg | None = None,
-                    devices=None, want_positions=True, want_tangents=False, want_metrics=False) -> dict:
+                    devices=None, want_positions=True, want_tangents=False, want_metrics=False,
+                    want_design=False, params: np.ndarray | None = None) -> dict:
         """hardpoints [n_inst, n_in*3]; target_values [n_targets, n_steps]."""
         require_device()
         prog = self.program
@@ -196,6 +197,13 @@ class DeviceTopology:
         if tv.ndim != 2 or tv.shape[0] != nt:
             raise ValueError(f"target_values must have shape ({nt}, n_steps), got {tv.shape}")
         n_inst, n_steps = hp.shape[0], tv.shape[1]
+        par = None
+        if params is not None:
+            par = np.ascontiguousarray(params, dtype=np.float64)
+            if par.shape != (n_inst, len(prog.param_names)):
+                raise ValueError(f"params must have shape ({n_inst}, {len(prog.param_names)}), got {par.shape}")
+            if par.shape[1] == 0:
+                par = None
         cfg = cfg or default_cfg()
         out = {
             "positions": np.empty((n_inst, n_steps, prog.n_out, 3)) if want_positions else None,
@@ -205,6 +213,7 @@ class DeviceTopology:
             "max_residual": np.empty((n_inst, n_steps)),
             "tangents": np.empty((n_inst, n_steps, nt, prog.n_unknowns)) if want_tangents else None,
             "metrics": np.empty((n_inst, n_steps, len(prog.metric_names))) if want_metrics else None,
+            "design": np.empty((n_inst, prog.n_out, 3)) if want_design else None,
         }
         if want_metrics and not prog.metric_names:
             raise ValueError("This topology was compiled without a metric program")
@@ -214,7 +223,7 @@ class DeviceTopology:
             return None if a is None else a.ctypes.data
 
         check(load().okin_solve_batch(
-            self.handle, ctypes.byref(cfg), n_inst, n_steps, p(hp), p(tv), p(dev), dev.size,
+            self.handle, ctypes.byref(cfg), n_inst, n_steps, p(hp), p(par), p(tv), p(dev), dev.size,
             p(out["positions"]), p(out["status"]), p(out["failed_step"]), p(out["iters"]),
-            p(out["max_residual"]), p(out["tangents"]), p(out["metrics"])), "okin_solve_batch")
+            p(out["max_residual"]), p(out["tangents"]), p(out["metrics"]), p(out["design"])), "okin_solve_batch")
         return out

@@ -78,7 +78,7 @@ def build_sweep(data: dict, suspension=None) -> SweepConfig:
         direction = _direction(spec["direction"])
         if suspension is not None:
             key = suspension.resolve_target_key(point, side)
-            state = suspension.initial_state()
+            state = suspension.structure()[0]      # point set only; never needs the setup pose
             if key not in state.positions:
                 raise ValueError(f"Sweep target point '{key.name}' is not present in suspension type "
                                  f"'{suspension.reported_type_key()}'.")

@@ -94,7 +94,7 @@ class ArbUBar:
         for side in _SIDES:
             arm = self.droplink_points[side]
             arm_key = PointRef(side, P.DROPLINK_U_BAR)
-            rocker = axle.corners[side].initial_state().positions[P.DROPLINK_ROCKER]
+            rocker = axle.corner_design(side).positions[P.DROPLINK_ROCKER]
             rows += [
                 DistanceConstraint(arm_key, a_key, _dist(arm, axis_a)),
                 DistanceConstraint(arm_key, b_key, _dist(arm, axis_b)),
@@ -150,7 +150,7 @@ class ArbTBar:
             state.free_points.add(key)
 
     def constraints(self, axle) -> list:
-        design = axle.initial_state()
+        design = axle.design_state()
         g = design.get
         rows = [
             DistanceConstraint(T_BAR_LEFT_KEY, T_BAR_RIGHT_KEY, _dist(g(T_BAR_LEFT_KEY), g(T_BAR_RIGHT_KEY))),
@@ -178,8 +178,9 @@ class HeaveLink:
         for side, corner in axle.corners.items():
             if P.HEAVE_LINK_ROCKER not in corner.free_points():
                 raise ValueError(f"{side.name} corner does not expose HEAVE_LINK_ROCKER as a moving pickup")
-        left = axle.corners[Side.LEFT].initial_state().get(P.HEAVE_LINK_ROCKER)
-        right = axle.corners[Side.RIGHT].initial_state().get(P.HEAVE_LINK_ROCKER)
+        # authored pose: the separation check does not need the (device-computed) setup pose
+        left = axle.corners[Side.LEFT].authored_state().get(P.HEAVE_LINK_ROCKER)
+        right = axle.corners[Side.RIGHT].authored_state().get(P.HEAVE_LINK_ROCKER)
         if _dist(left, right) <= EPS_GEOMETRIC:
             raise ValueError("Rocker-to-rocker heave-link pickups must be separated in the design state")
 
@@ -196,6 +197,7 @@ class AxleSuspension(Suspension):
     side: Side = Side.CENTER
     hardpoints: dict = field(default_factory=dict)
     _initial_state: SuspensionState | None = field(default=None, init=False, repr=False)
+    _authored_mode: bool = field(default=False, init=False, repr=False)
 
     def __post_init__(self) -> None:
         self.validate_hardpoints()
@@ -203,6 +205,33 @@ class AxleSuspension(Suspension):
     @property
     def is_axle(self) -> bool:
         return True
+
+    # -- design pose access; in "authored mode" (structure()) no setup shim is applied --------
+    def corner_design(self, side: Side) -> SuspensionState:
+        corner = self.corners[side]
+        return corner.authored_state() if self._authored_mode else corner.initial_state()
+
+    def design_state(self) -> SuspensionState:
+        return self._merged_state() if self._authored_mode else self.initial_state()
+
+    def structure(self) -> tuple:
+        self._authored_mode = True
+        try:
+            return self._merged_state(), self.constraints()
+        finally:
+            self._authored_mode = False
+
+    def _merged_state(self) -> SuspensionState:
+        positions: dict = {}
+        free: set = set()
+        for side in self.corners:
+            cs = self.corner_design(side)
+            positions.update({PointRef(side, k): p.copy() for k, p in cs.positions.items()})
+            free.update(PointRef(side, k) for k in cs.free_points)
+        state = SuspensionState(positions, free)
+        self.anti_roll.add_to_state(state)
+        state.free_points_order = sorted(state.free_points)
+        return state
 
     def reported_type_key(self) -> SuspensionType:
         return self.type_key
@@ -237,16 +266,7 @@ class AxleSuspension(Suspension):
 
     def initial_state(self) -> SuspensionState:
         if self._initial_state is None:
-            positions: dict = {}
-            free: set = set()
-            for side, corner in self.corners.items():
-                cs = corner.initial_state()
-                positions.update({PointRef(side, k): p.copy() for k, p in cs.positions.items()})
-                free.update(PointRef(side, k) for k in cs.free_points)
-            state = SuspensionState(positions, free)
-            self.anti_roll.add_to_state(state)
-            state.free_points_order = sorted(state.free_points)
-            self._initial_state = state
+            self._initial_state = self._merged_state()
         return self._initial_state
 
     def free_points(self) -> tuple:
@@ -261,12 +281,12 @@ class AxleSuspension(Suspension):
         rows = [
             c.remap(lambda k, side=side: side_qualified(side, k))
             for side, corner in self.corners.items()
-            for c in corner.constraints()
+            for c in corner.constraints_at(self.corner_design(side).positions)
         ]
         rack = self.rack_attachment_points()
         if rack is not None:
-            left = self.corners[Side.LEFT].initial_state().positions[rack[0]]
-            right = self.corners[Side.RIGHT].initial_state().positions[rack[1]]
+            left = self.corner_design(Side.LEFT).positions[rack[0]]
+            right = self.corner_design(Side.RIGHT).positions[rack[1]]
             # The rigid rack keeps its two ends a fixed distance apart (suspension.py:196-209).
             rows.append(DistanceConstraint(PointRef(Side.LEFT, rack[0]), PointRef(Side.RIGHT, rack[1]),
                                            _dist(left, right)))

@@ -60,6 +60,12 @@ class Suspension:
             )
         return point
 
+    def structure(self) -> tuple:
+        """``(state, constraints)`` describing the topology without touching the device: the
+        authored pose stands in for the design pose (a setup shim would need the device), which
+        is all the topology compiler needs when design constants are recomputed per instance."""
+        return self.initial_state(), self.constraints()
+
     def all_point_keys(self) -> set:
         """Every point present in a solved state (authored + derived)."""
         return set(self.initial_state().positions)

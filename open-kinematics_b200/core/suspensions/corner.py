@@ -259,6 +259,10 @@ class CornerSpring:
     def damper_points(self):
         return (P.STRUT_TOP, P.STRUT_BOTTOM) if self.kind == "coilover" else None
 
+    @property
+    def rocker_mounted_points(self) -> tuple:
+        return (P.STRUT_BOTTOM,) if self.kind == "coilover" else ()
+
     def validate(self, actuation) -> None:
         if self.kind == "torsion_bar" and actuation.torsion_axis is None:
             raise ValueError("Corner torsion bar is not supported by direct actuation yet")
@@ -370,22 +374,47 @@ class DoubleWishboneSuspension(_Corner):
     def derived_spec(self) -> DerivedPointsSpec:
         return build_wheel_derived_spec(self.config.wheel)
 
+    def shim_rocker_coupled(self) -> bool:
+        """An upright-mounted pushrod couples the rocker group into the shim assembly
+        (double_wishbone.py:518-533)."""
+        return (isinstance(self.actuation, ActuationPushrodRocker)
+                and self.actuation.moving_pickup_body == self.UPRIGHT_BODY)
+
+    def upright_attachment_points(self) -> tuple:
+        """Points carried by the upright during camber-shim setup (double_wishbone.py:573-581)."""
+        base = (P.AXLE_INBOARD, P.AXLE_OUTBOARD, self.wheel_heading_link.outboard_point)
+        if self.actuation.moving_pickup_body == self.UPRIGHT_BODY:
+            return (*base, self.actuation.moving_pickup_point)
+        return base
+
+    def authored_state(self) -> SuspensionState:
+        """Hardpoints + derived points before any setup shim is applied."""
+        positions = self.get_hardpoints_copy()
+        DerivedPointsManager(self.derived_spec()).update_in_place(positions)
+        return SuspensionState(positions=positions, free_points=set(self.free_points()))
+
     def initial_state(self) -> SuspensionState:
         if self._initial_state is None:
-            positions = self.get_hardpoints_copy()
             shim = self.config.camber_shim
             if shim is not None and abs(shim.setup_thickness - shim.design_thickness) >= EPS_GEOMETRIC:
-                # Pre-solve of the split-body shim assembly (reference config/shims.py:284-501)
-                # is a §8 row not built yet; a no-op shim (setup == design) is exact.
-                raise NotImplementedError(
-                    "camber-shim setup thickness different from design thickness is not supported yet"
-                )
-            DerivedPointsManager(self.derived_spec()).update_in_place(positions)
-            self._initial_state = SuspensionState(positions=positions, free_points=set(self.free_points()))
+                # The split-body shim assembly pre-solve (reference config/shims.py:284-501) runs on
+                # the device like every other piece of arithmetic: ask it for the setup pose.
+                from ..shim_setup import device_setup_pose
+                positions = device_setup_pose(self)
+                self._initial_state = SuspensionState(positions=positions, free_points=set(self.free_points()))
+            else:
+                self._initial_state = self.authored_state()
         return self._initial_state
 
     def constraints(self) -> list:
-        pos = self.initial_state().positions
+        return self.constraints_at(self.initial_state().positions)
+
+    def structure(self) -> tuple:
+        state = self.authored_state()
+        return state, self.constraints_at(state.positions)
+
+    def constraints_at(self, pos: dict) -> list:
+        """Constraint declarations with constants measured at the given pose."""
         rows: list[Constraint] = [
             distance_constraint(pos, a, b)
             for a, b in (
@@ -497,8 +526,13 @@ class MacPhersonSuspension(_Corner):
             self._initial_state = SuspensionState(positions=positions, free_points=set(self.free_points()))
         return self._initial_state
 
+    def authored_state(self) -> SuspensionState:
+        return self.initial_state()
+
     def constraints(self) -> list:
-        pos = self.initial_state().positions
+        return self.constraints_at(self.initial_state().positions)
+
+    def constraints_at(self, pos: dict) -> list:
         rows: list[Constraint] = [
             distance_constraint(pos, a, b)
             for a, b in (

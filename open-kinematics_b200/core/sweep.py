@@ -69,11 +69,14 @@ class BatchSolver:
         self.suspension = suspension
         self.heads, self.values = sweep_target_values(sweep_config)
         from .metrics_program import build_metric_program
+        from .shim_program import shim_records
+        state, constraints = suspension.structure()
         self.program = compile_topology(
-            suspension.initial_state(), suspension.constraints(), suspension.derived_spec(), self.heads,
+            state, constraints, suspension.derived_spec(), self.heads,
             output_points=output_points, design_rules=True,
             metrics=(lambda pidx: build_metric_program(suspension, self.heads, pidx))
             if suspension.config is not None else None,
+            shims=shim_records(suspension),
         )
         self.topology = _lib.DeviceTopology(self.program)
 
@@ -85,23 +88,29 @@ class BatchSolver:
     def authored_positions(self) -> dict:
         sus = self.suspension
         if getattr(sus, "is_axle", False):
-            from .primitives.point_ref import PointRef
+            from .enums import PointID
+            from .primitives.point_ref import PointRef, Side
             out = {PointRef(side, k): p for side, corner in sus.corners.items() for k, p in corner.hardpoints.items()}
-            state = sus.initial_state()
-            for k in state.positions:
-                out.setdefault(k, state.positions[k])
+            for point, p in getattr(sus.anti_roll, "center_points", {}).items():
+                out[PointRef(Side.CENTER, point)] = p
+            for side, p in getattr(sus.anti_roll, "droplink_points", {}).items():
+                arm = PointID.DROPLINK_U_BAR if PointRef(side, PointID.DROPLINK_U_BAR) in self.program.in_keys \
+                    else PointID.DROPLINK_T_BAR
+                out[PointRef(side, arm)] = p
             return out
         return dict(sus.hardpoints)
 
     def solve(self, hardpoints: np.ndarray, solver_config: SolverConfig = SolverConfig(), devices=None,
               want_positions: bool = True, want_tangents: bool = False,
-              want_metrics: bool = False) -> BatchSweepResult:
+              want_metrics: bool = False, params: np.ndarray | None = None) -> BatchSweepResult:
+        """``params``: optional ``[n_instances, n_params]`` per-instance scalars in the order of
+        ``program.param_names`` (camber-shim datums and thicknesses); default = the model's."""
         cfg = _lib.default_cfg(residual_tol=float(solver_config.residual_tolerance))
         hp = np.asarray(hardpoints, dtype=np.float64)
         hp = hp.reshape(hp.shape[0], -1)
         out = self.topology.solve_batch(hp, self.values, cfg, devices=devices,
                                         want_positions=want_positions, want_tangents=want_tangents,
-                                        want_metrics=want_metrics)
+                                        want_metrics=want_metrics, params=params)
         return BatchSweepResult(self.program, out["positions"], out["status"], out["failed_step"],
                                 out["iters"], out["max_residual"], out["tangents"], out["metrics"])
 

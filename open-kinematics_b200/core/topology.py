@@ -115,6 +115,8 @@ class TopologyProgram:
     target_points: list
     stats: dict
     metric_names: list = field(default_factory=list)
+    param_names: list = field(default_factory=list)
+    param_default: np.ndarray = field(default_factory=lambda: np.zeros(0))
 
     @property
     def n_unknowns(self) -> int:
@@ -274,6 +276,7 @@ def compile_topology(
     output_points=None,
     design_rules: bool = True,
     metrics=None,
+    shims=None,
 ) -> TopologyProgram:
     """Compile one topology.
 
@@ -612,6 +615,25 @@ def compile_topology(
     point_dop = [-1] * P
     for key, d in dop_of.items():
         point_dop[pidx[key]] = d
+    shim_recs, shim_pts, param_default, param_names = [], [], [], []
+    for sh in (shims or []):
+        ix = lambda k: -1 if k is None else pidx[k]   # noqa: E731
+        up_begin = len(shim_pts)
+        shim_pts += [pidx[k] for k in sh["upright_points"]]
+        rk_begin = len(shim_pts)
+        shim_pts += [pidx[k] for k in sh["rocker_points"]]
+        rocker = sh.get("rocker")
+        rec = [ix(sh["ubj"]), ix(sh["lbj"]), ix(sh["uw_front"]), ix(sh["uw_rear"]), ix(sh["heading_in"]),
+               ix(sh["heading_out"]), 1 if rocker else 0,
+               *([ix(k) for k in rocker] if rocker else [-1, -1, -1, -1]),
+               len(param_default), up_begin, rk_begin, rk_begin, len(shim_pts)]
+        shim_recs.append(rec + [0] * (D["OKIN_SHIM_STRIDE"] - len(rec)))
+        param_default += [float(v) for v in sh["params"]]
+        param_names += [f"{sh['label']}.{n}" for n in (
+            "face_a.x", "face_a.y", "face_a.z", "face_b.x", "face_b.y", "face_b.z", "normal.x", "normal.y",
+            "normal.z", "design_thickness", "setup_thickness")]
+    if len(shim_recs) > 32:
+        raise ValueError("At most 32 shimmed corners per topology")
     mprog = metrics(pidx) if metrics is not None else None
     mcorners = mprog.corners if mprog else []
     mops = mprog.mops if mprog else []
@@ -638,6 +660,7 @@ def compile_topology(
         "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_ROW_ORDER": row_order,
         "OKIN_S_DOP_LEV": dop_lev, "OKIN_S_POINT_ELIM": point_elim, "OKIN_S_POINT_DOP": point_dop,
         "OKIN_S_DESIGN_PT": design_pts, "OKIN_S_MCORNER": mcorners, "OKIN_S_MOP": mops, "OKIN_S_MAXLE": maxle,
+        "OKIN_S_SHIM": shim_recs, "OKIN_S_SHIM_PTS": shim_pts,
     }
     hdr = np.zeros(D["OKIN_HDR_SIZE"], np.int32)
     chunks, cursor = [], 0
@@ -651,7 +674,8 @@ def compile_topology(
         chunks.append(arr.astype(np.int32))
         cursor += arr.size
     iblob = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
-    fsecs = {"OKIN_F_PAR_VAL": par_val, "OKIN_F_CST_INIT": cst_init, "OKIN_F_MCONST": mconst}
+    fsecs = {"OKIN_F_PAR_VAL": par_val, "OKIN_F_CST_INIT": cst_init, "OKIN_F_MCONST": mconst,
+             "OKIN_F_PARAM_DEFAULT": param_default}
     fchunks, cursor = [], 0
     for name, data in fsecs.items():
         arr = np.asarray(data, dtype=np.float64).reshape(-1)
@@ -671,6 +695,7 @@ def compile_topology(
         "OKIN_H_NB": NB, "OKIN_H_NLEV": NLEV, "OKIN_H_NAT": NAT, "OKIN_H_NOUT": len(out_keys),
         "OKIN_H_TROW0": trow0, "OKIN_H_SMEM_DOUBLES": off, "OKIN_H_NM": len(metric_names),
         "OKIN_H_NMC": len(mcorners), "OKIN_H_NMOP": len(mops), "OKIN_H_NMAXLE": len(maxle), "OKIN_H_NDSN": ndsn,
+        "OKIN_H_NSHIM": len(shim_recs), "OKIN_H_NPARAM": len(param_default),
         **layout,
     }
     for name, value in counts.items():
@@ -688,6 +713,7 @@ def compile_topology(
         hdr=hdr, iblob=iblob, fblob=fblob, point_keys=point_keys, free_order=free_order, in_keys=in_keys,
         out_keys=out_keys, n_constraints=len(constraints), row_source=[r.source for r in rows],
         target_points=[t.point_id for t in targets], stats=stats, metric_names=metric_names,
+        param_names=param_names, param_default=np.asarray(param_default, dtype=np.float64),
     )
 
 
@@ -695,10 +721,14 @@ def compile_suspension(suspension, sweep_config, output_points=None, design_rule
                        with_metrics: bool = True) -> TopologyProgram:
     """Compile a built suspension + sweep (first-step targets define the target rows)."""
     from .metrics_program import build_metric_program
+    from .shim_program import shim_records
 
     targets = [sweep[0] for sweep in sweep_config.target_sweeps]
     metrics = (lambda pidx: build_metric_program(suspension, targets, pidx)) if with_metrics else None
+    state, constraints = suspension.structure() if design_rules else (suspension.initial_state(),
+                                                                       suspension.constraints())
     return compile_topology(
-        suspension.initial_state(), suspension.constraints(), suspension.derived_spec(), targets,
+        state, constraints, suspension.derived_spec(), targets,
         output_points=output_points, design_rules=design_rules, metrics=metrics,
+        shims=shim_records(suspension) if design_rules else None,
     )

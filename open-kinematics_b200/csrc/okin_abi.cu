@@ -62,8 +62,9 @@ struct okin_topology {
 __global__ void __launch_bounds__(OKIN_WARPS_PER_CTA * 32)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, const double* __restrict__ hardpoints,
-                  const double* __restrict__ tvals, OkinSolverCfg cfg, double* positions, int32_t* iters,
-                  double* max_residual, double* tangents, double* metrics, int32_t* status, int32_t* failed_step) {
+                  const double* __restrict__ params, const double* __restrict__ tvals, OkinSolverCfg cfg,
+                  double* positions, int32_t* iters, double* max_residual, double* tangents, double* metrics,
+                  double* design, int32_t* status, int32_t* failed_step) {
   extern __shared__ double okin_smem[];
   OkinProgram pr{hdr, ib, fb};
   const int warp = threadIdx.x >> 5;
@@ -77,9 +78,11 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
     out.max_residual = max_residual ? max_residual + (size_t)i * n_steps : nullptr;
     out.tangents = tangents ? tangents + (size_t)i * n_steps * nt * n : nullptr;
     out.metrics = metrics ? metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
+    out.design = design ? design + (size_t)i * 3 * nout : nullptr;
     out.status = status + i;
     out.failed_step = failed_step + i;
-    okin_sweep(pr, sm, hardpoints + (size_t)i * 3 * nin, tvals, n_steps, cfg, out);
+    okin_sweep(pr, sm, hardpoints + (size_t)i * 3 * nin,
+               params ? params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, tvals, n_steps, cfg, out);
     __syncwarp();
   }
 }
@@ -127,8 +130,8 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
 }
 
 int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStream_t stream, int64_t n_instances,
-           int32_t n_steps, const double* hp, const double* tv, double* pos, int32_t* status, int32_t* failed,
-           int32_t* iters, double* maxres, double* tangents, double* metrics) {
+           int32_t n_steps, const double* hp, const double* par, const double* tv, double* pos, int32_t* status,
+           int32_t* failed, int32_t* iters, double* maxres, double* tangents, double* metrics, double* design) {
   if (n_instances == 0) return OKIN_OK;
   OkinSolverCfg c{cfg->step_tol, cfg->coarse_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter, cfg->use_predictor};
   const int smem = OKIN_WARPS_PER_CTA * t->hdr[OKIN_H_SMEM_DOUBLES] * (int)sizeof(double);
@@ -136,8 +139,8 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
   const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
   const int grid = (int)std::min<int64_t>(needed, resident);
   okin_sweep_kernel<<<grid, OKIN_WARPS_PER_CTA * 32, smem, stream>>>(
-      d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, hp, tv, c, pos, iters, maxres, tangents, metrics, status,
-      failed);
+      d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, hp, par, tv, c, pos, iters, maxres, tangents, metrics,
+      design, status, failed);
   OKIN_CUDA(cudaGetLastError());
   return OKIN_OK;
 }
@@ -235,6 +238,7 @@ int okin_topology_get_info(const okin_topology* t, okin_topology_info* out) {
   out->smem_bytes_per_instance = h[OKIN_H_SMEM_DOUBLES] * (int32_t)sizeof(double);
   out->n_levels = h[OKIN_H_NLEV];
   out->n_metrics = h[OKIN_H_NM];
+  out->n_params = h[OKIN_H_NPARAM];
   return OKIN_OK;
 }
 
@@ -254,18 +258,19 @@ int okin_launch_geometry(okin_topology* t, int32_t device, int64_t n_instances, 
 
 int okin_solve_batch_device(okin_topology* t, const okin_solver_cfg* cfg, int32_t device, void* stream,
                             int64_t n_instances, int32_t n_steps, const double* d_hardpoints,
-                            const double* d_target_values, double* d_positions_out, int32_t* d_status_out,
-                            int32_t* d_failed_step_out, int32_t* d_iters_out, double* d_max_residual_out,
-                            double* d_tangents_out, double* d_metrics_out) {
+                            const double* d_params, const double* d_target_values, double* d_positions_out,
+                            int32_t* d_status_out, int32_t* d_failed_step_out, int32_t* d_iters_out,
+                            double* d_max_residual_out, double* d_tangents_out, double* d_metrics_out,
+                            double* d_design_out) {
   int rc = check_common(t, cfg, n_instances, n_steps, d_hardpoints, d_target_values, d_status_out, d_failed_step_out);
   if (rc) return rc;
   DeviceCopy* d = nullptr;
   rc = ensure_device(t, device, &d);
   if (rc) return rc;
   OKIN_CUDA(cudaSetDevice(device));
-  return launch(t, d, cfg, (cudaStream_t)stream, n_instances, n_steps, d_hardpoints, d_target_values,
+  return launch(t, d, cfg, (cudaStream_t)stream, n_instances, n_steps, d_hardpoints, d_params, d_target_values,
                 d_positions_out, d_status_out, d_failed_step_out, d_iters_out, d_max_residual_out, d_tangents_out,
-                d_metrics_out);
+                d_metrics_out, d_design_out);
 }
 
 int okin_shard_range(int64_t n_instances, int32_t shard, int32_t n_shards, int64_t* begin, int64_t* count) {
@@ -277,9 +282,10 @@ int okin_shard_range(int64_t n_instances, int32_t shard, int32_t n_shards, int64
 }
 
 int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
-                     const double* hardpoints, const double* target_values, const int32_t* device_ids,
-                     int32_t n_devices, double* positions_out, int32_t* status_out, int32_t* failed_step_out,
-                     int32_t* iters_out, double* max_residual_out, double* tangents_out, double* metrics_out) {
+                     const double* hardpoints, const double* params, const double* target_values,
+                     const int32_t* device_ids, int32_t n_devices, double* positions_out, int32_t* status_out,
+                     int32_t* failed_step_out, int32_t* iters_out, double* max_residual_out, double* tangents_out,
+                     double* metrics_out, double* design_out) {
   int rc = check_common(t, cfg, n_instances, n_steps, hardpoints, target_values, status_out, failed_step_out);
   if (rc) return rc;
   const int32_t default_dev = 0;
@@ -297,7 +303,7 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
     DeviceCopy* d;
     int device;
     int64_t begin, count;
-    double *hp, *tv, *pos, *maxres, *tan, *met;
+    double *hp, *par, *tv, *pos, *maxres, *tan, *met, *dsn;
     int32_t *status, *failed, *iters;
   };
   std::vector<Shard> shards;
@@ -322,9 +328,12 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
     const size_t b_tan = tangents_out ? align(c * S * nt * n * 8) : 0;
     const size_t nm = (size_t)h[OKIN_H_NM];
     const size_t b_met = (metrics_out && nm) ? align(c * S * nm * 8) : 0;
+    const size_t npar = (size_t)h[OKIN_H_NPARAM];
+    const size_t b_par = (params && npar) ? align(c * npar * 8) : 0;
+    const size_t b_dsn = design_out ? align(c * nout3 * 8) : 0;
     const size_t b_it = iters_out ? align(c * S * 4) : 0;
     const size_t b_st = align(c * 4);
-    const size_t total = b_hp + b_tv + b_pos + b_mr + b_tan + b_met + b_it + 2 * b_st;
+    const size_t total = b_hp + b_tv + b_pos + b_mr + b_tan + b_met + b_par + b_dsn + b_it + 2 * b_st;
     if (total > s.d->ws_bytes) {
       if (s.d->ws) OKIN_CUDA(cudaFree(s.d->ws));
       s.d->ws = nullptr;
@@ -339,13 +348,18 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
     s.maxres = max_residual_out ? (double*)p : nullptr; p += b_mr;
     s.tan = tangents_out ? (double*)p : nullptr; p += b_tan;
     s.met = b_met ? (double*)p : nullptr; p += b_met;
+    s.par = b_par ? (double*)p : nullptr; p += b_par;
+    s.dsn = b_dsn ? (double*)p : nullptr; p += b_dsn;
     s.iters = iters_out ? (int32_t*)p : nullptr; p += b_it;
     s.status = (int32_t*)p; p += b_st;
     s.failed = (int32_t*)p;
     cudaStream_t st = s.d->stream;
     OKIN_CUDA(cudaMemcpyAsync(s.hp, hardpoints + (size_t)s.begin * nin3, c * nin3 * 8, cudaMemcpyHostToDevice, st));
+    if (s.par)
+      OKIN_CUDA(cudaMemcpyAsync(s.par, params + (size_t)s.begin * npar, c * npar * 8, cudaMemcpyHostToDevice, st));
     if (nt * S) OKIN_CUDA(cudaMemcpyAsync(s.tv, target_values, nt * S * 8, cudaMemcpyHostToDevice, st));
-    rc = launch(t, s.d, cfg, st, s.count, n_steps, s.hp, s.tv, s.pos, s.status, s.failed, s.iters, s.maxres, s.tan, s.met);
+    rc = launch(t, s.d, cfg, st, s.count, n_steps, s.hp, s.par, s.tv, s.pos, s.status, s.failed, s.iters, s.maxres,
+                s.tan, s.met, s.dsn);
     if (rc) return rc;
     const size_t b0 = (size_t)s.begin;
     if (positions_out)
@@ -354,6 +368,7 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
       OKIN_CUDA(cudaMemcpyAsync(max_residual_out + b0 * S, s.maxres, c * S * 8, cudaMemcpyDeviceToHost, st));
     if (tangents_out)
       OKIN_CUDA(cudaMemcpyAsync(tangents_out + b0 * S * nt * n, s.tan, c * S * nt * n * 8, cudaMemcpyDeviceToHost, st));
+    if (s.dsn) OKIN_CUDA(cudaMemcpyAsync(design_out + b0 * nout3, s.dsn, c * nout3 * 8, cudaMemcpyDeviceToHost, st));
     if (s.met)
       OKIN_CUDA(cudaMemcpyAsync(metrics_out + b0 * S * nm, s.met, c * S * nm * 8, cudaMemcpyDeviceToHost, st));
     if (iters_out) OKIN_CUDA(cudaMemcpyAsync(iters_out + b0 * S, s.iters, c * S * 4, cudaMemcpyDeviceToHost, st));

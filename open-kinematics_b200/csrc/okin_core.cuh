@@ -182,10 +182,155 @@ OKIN_FN void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Camber-shim assembly pre-solve: moves the design pose to the setup pose before anything else is
+// derived from it (double_wishbone.py:501-571, config/shims.py:284-501).  One lane per shimmed
+// corner: Gauss-Newton on 7(+1) unknowns / 10(+1) residuals from x = 0 with a forward-mode
+// Jacobian (the reference uses SciPy's finite differences; both converge to the same root of the
+// consistent system, 1e-13 apart in the reference's own default-vs-tight runs).
+// ---------------------------------------------------------------------------------------
+template <typename Dummy = void>
+OKIN_FN void okin_shim_presolve(const OkinProgram& pr, double* sm, const double* params, int* invalid) {
+  const int32_t* hdr = pr.hdr;
+  const int nshim = hdr[OKIN_H_NSHIM];
+  if (nshim == 0) return;
+  const int32_t* recs = okin_sec(pr, OKIN_S_SHIM);
+  const int32_t* lists = okin_sec(pr, OKIN_S_SHIM_PTS);
+  double* pos = sm + hdr[OKIN_H_OFF_POS];
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  red[lane] = 0.0;
+  if (lane < nshim) {
+    const int32_t* rec = recs + lane * OKIN_SHIM_STRIDE;
+    const double* q = params + OKIN_LDG(rec + 11);
+    const double t_design = q[9], t_setup = q[10];
+    if (fabs(t_setup - t_design) >= OKIN_GEOM_EPS) {
+      double* ubj = pos + 3 * OKIN_LDG(rec + 0);
+      const double* lbj = pos + 3 * OKIN_LDG(rec + 1);
+      const double* uwf = pos + 3 * OKIN_LDG(rec + 2);
+      const double* uwr = pos + 3 * OKIN_LDG(rec + 3);
+      const double* hli = pos + 3 * OKIN_LDG(rec + 4);
+      const double* hlo = pos + 3 * OKIN_LDG(rec + 5);
+      OkinShimCtx c;
+      c.t_setup = t_setup;
+      const double half = 0.5 * t_design;
+      double wl = 0.0, hl = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        c.n[k] = q[6 + k];
+        c.wb_axis[k] = uwr[k] - uwf[k]; wl += c.wb_axis[k] * c.wb_axis[k];
+        c.hl_in[k] = hli[k]; c.lbj[k] = lbj[k]; c.uwf[k] = uwf[k];
+        c.uwf_to_ubj[k] = ubj[k] - uwf[k];
+        c.ubj_to_a[k] = q[k] - half * q[6 + k] - ubj[k];
+        c.ubj_to_b[k] = q[3 + k] - half * q[6 + k] - ubj[k];
+        c.lbj_to_a[k] = q[k] + half * q[6 + k] - lbj[k];
+        c.lbj_to_b[k] = q[3 + k] + half * q[6 + k] - lbj[k];
+        c.lbj_to_hl_out[k] = hlo[k] - lbj[k];
+        hl += (hlo[k] - hli[k]) * (hlo[k] - hli[k]);
+      }
+      wl = 1.0 / sqrt(wl);
+      for (int k = 0; k < 3; ++k) c.wb_axis[k] *= wl;
+      c.hl_len = sqrt(hl);
+      c.has_rocker = OKIN_LDG(rec + 6);
+      const double* ra = pos;
+      if (c.has_rocker) {
+        ra = pos + 3 * OKIN_LDG(rec + 7);
+        const double* rb = pos + 3 * OKIN_LDG(rec + 8);
+        const double* pi = pos + 3 * OKIN_LDG(rec + 9);
+        const double* po = pos + 3 * OKIN_LDG(rec + 10);
+        double al = 0.0, pl = 0.0;
+        for (int k = 0; k < 3; ++k) {
+          c.rk_axis_pt[k] = ra[k];
+          c.rk_axis[k] = rb[k] - ra[k]; al += c.rk_axis[k] * c.rk_axis[k];
+          c.rk_to_pr_in[k] = pi[k] - ra[k];
+          c.lbj_to_pr_out[k] = po[k] - lbj[k];
+          pl += (po[k] - pi[k]) * (po[k] - pi[k]);
+        }
+        al = 1.0 / sqrt(al);
+        for (int k = 0; k < 3; ++k) c.rk_axis[k] *= al;
+        c.pr_len = sqrt(pl);
+      }
+      const int n = 7 + c.has_rocker, m = 10 + c.has_rocker;
+      double x[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      bool ok = false;
+      for (int it = 0; it < 40 && !ok; ++it) {
+        double J[11][8], r[11];
+        for (int col = 0; col < n; ++col) {
+          OkinDual xd[8], rd[11];
+          for (int k = 0; k < 8; ++k) xd[k] = OkinDual{x[k], k == col ? 1.0 : 0.0};
+          okin_shim_residuals<OkinDual>(c, xd, rd);
+          for (int i = 0; i < m; ++i) { J[i][col] = rd[i].d; r[i] = rd[i].v; }
+        }
+        // normal equations + dense Cholesky (8x8)
+        double A[8][8], g[8];
+        for (int a = 0; a < n; ++a) {
+          g[a] = 0.0;
+          for (int i = 0; i < m; ++i) g[a] -= J[i][a] * r[i];
+          for (int b = 0; b <= a; ++b) {
+            double acc = 0.0;
+            for (int i = 0; i < m; ++i) acc += J[i][a] * J[i][b];
+            A[a][b] = acc;
+          }
+        }
+        bool pd = true;
+        for (int a = 0; a < n; ++a) {
+          for (int b = 0; b <= a; ++b) {
+            double acc = A[a][b];
+            for (int k = 0; k < b; ++k) acc -= A[a][k] * A[b][k];
+            if (a == b) { pd = pd && acc > 0.0; A[a][a] = sqrt(acc); }
+            else A[a][b] = acc / A[b][b];
+          }
+        }
+        if (!pd) break;
+        for (int a = 0; a < n; ++a) {
+          double acc = g[a];
+          for (int k = 0; k < a; ++k) acc -= A[a][k] * g[k];
+          g[a] = acc / A[a][a];
+        }
+        double hmax = 0.0;
+        for (int a = n - 1; a >= 0; --a) {
+          double acc = g[a];
+          for (int k = a + 1; k < n; ++k) acc -= A[k][a] * g[k];
+          g[a] = acc / A[a][a];
+          x[a] += g[a];
+          hmax = fabs(g[a]) > hmax ? fabs(g[a]) : hmax;
+        }
+        ok = hmax <= 1e-13;
+      }
+      double rfin[11];
+      okin_shim_residuals<double>(c, x, rfin);
+      double rmax = 0.0;
+      for (int i = 0; i < m; ++i) rmax = fabs(rfin[i]) > rmax ? fabs(rfin[i]) : rmax;
+      if (!ok || !(rmax <= 1e-3)) {
+        red[lane] = 1.0;  // shims.py:451-462 raises: flag the instance invalid
+      } else {
+        // apply (double_wishbone.py:546-571)
+        const double z3[3] = {0.0, 0.0, 0.0};
+        const OkinV3<double> wb = {c.wb_axis[0] * x[0], c.wb_axis[1] * x[0], c.wb_axis[2] * x[0]};
+        const OkinV3<double> nu = okin_rodrigues(okin_lift(c.uwf_to_ubj, z3, 0.0), wb);
+        ubj[0] = c.uwf[0] + nu.x; ubj[1] = c.uwf[1] + nu.y; ubj[2] = c.uwf[2] + nu.z;
+        const double ang = sqrt(x[4] * x[4] + x[5] * x[5] + x[6] * x[6]);
+        if (ang > OKIN_GEOM_EPS) {
+          const double axis[3] = {x[4] / ang, x[5] / ang, x[6] / ang};
+          for (int k = OKIN_LDG(rec + 12); k < OKIN_LDG(rec + 13); ++k)
+            okin_rotate_about_axis(pos + 3 * OKIN_LDG(lists + k), c.lbj, axis, ang);
+        }
+        if (c.has_rocker)
+          for (int k = OKIN_LDG(rec + 14); k < OKIN_LDG(rec + 15); ++k)
+            okin_rotate_about_axis(pos + 3 * OKIN_LDG(lists + k), c.rk_axis_pt, c.rk_axis, x[7]);
+      }
+    }
+  }
+  OKIN_PHASE_END
+  double bad = 0.0;
+  for (int k = 0; k < 32; ++k) bad += red[k];
+  if (bad != 0.0) *invalid = 1;
+}
+
+// ---------------------------------------------------------------------------------------
 // Setup: inputs -> pos, derived parameters, design pose, per-instance constants.
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
-OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints) {
+OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints,
+                        const double* __restrict__ params, int* invalid) {
   const int32_t* hdr = pr.hdr;
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* cst = sm + hdr[OKIN_H_OFF_CST];
@@ -195,6 +340,7 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
   OKIN_PHASE_BEGIN
   for (int t = lane; t < 3 * nin; t += 32) pos[3 * OKIN_LDG(in_point + t / 3) + t % 3] = hardpoints[t];
   OKIN_PHASE_END
+  okin_shim_presolve(pr, sm, params ? params : okin_fsec(pr, OKIN_F_PARAM_DEFAULT), invalid);
 
   // Derived-op parameters.  A design projection reads the *authored* position of the derived
   // point (macpherson.py:199-204), which is what pos[] still holds at this moment.
@@ -1066,6 +1212,7 @@ struct OkinOutputs {
   double* max_residual;   // [n_steps] or null
   double* tangents;       // [n_steps][NT][3*NF] (reference column order) or null
   double* metrics;        // [n_steps][NM] or null (NaN == the reference's None)
+  double* design;         // [NOUT*3] design (setup) pose or null
   int32_t* status;        // [1]
   int32_t* failed_step;   // [1]
 };
@@ -1074,8 +1221,8 @@ struct OkinOutputs {
 // sweep values shared by all instances of the launch.
 template <typename Dummy = void>
 OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints,
-                        const double* __restrict__ tvals, int n_steps, const OkinSolverCfg& cfg,
-                        const OkinOutputs& out) {
+                        const double* __restrict__ params, const double* __restrict__ tvals, int n_steps,
+                        const OkinSolverCfg& cfg, const OkinOutputs& out) {
   const int32_t* hdr = pr.hdr;
   const int nt = hdr[OKIN_H_NT];
   const int n = 3 * hdr[OKIN_H_NF];
@@ -1084,11 +1231,17 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   const int32_t* ecol = okin_sec(pr, OKIN_S_ELIM_COL);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
-  okin_setup(pr, sm, hardpoints);
+  int invalid = 0;
+  okin_setup(pr, sm, hardpoints, params, &invalid);
+  if (out.design) {  // design (setup) pose of every output point
+    OKIN_PHASE_BEGIN
+    for (int t = lane; t < 3 * nout; t += 32) out.design[t] = pos[3 * OKIN_LDG(out_point + t / 3) + t % 3];
+    OKIN_PHASE_END
+  }
 
   OkinState st;
   st.f2 = 0.0; st.rmax = 0.0; st.mu = 0.0; st.notpd = 0;
-  int status = OKIN_STATUS_OK, failed = -1;
+  int status = invalid ? OKIN_STATUS_INVALID_GEOMETRY : OKIN_STATUS_OK, failed = invalid ? 0 : -1;
   double tcur[OKIN_MAX_TARGETS], tprev[OKIN_MAX_TARGETS];
   for (int j = 0; j < OKIN_MAX_TARGETS; ++j) { tcur[j] = 0.0; tprev[j] = 0.0; }
   bool have_tangent = false, have_pprev = false;

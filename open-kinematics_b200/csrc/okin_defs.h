@@ -100,6 +100,8 @@ enum okin_hdr_slot {
   OKIN_H_NMAXLE,   // 0 or 1 axle record
   OKIN_H_NDSN,     // design-pose slots kept for the metrics
   OKIN_H_OFF_DSN, OKIN_H_OFF_MCTX,
+  OKIN_H_NSHIM,    // camber-shim pre-solve records (one per shimmed corner)
+  OKIN_H_NPARAM,   // per-instance scalar parameters (doubles)
   OKIN_H_SEC0 = 48,
   OKIN_H_FSEC0 = 48 + 2 * 40,
   OKIN_HDR_SIZE = 48 + 2 * 40 + 2 * 4
@@ -146,12 +148,14 @@ enum okin_isec {
   OKIN_S_MCORNER,        // [NMC][OKIN_MCORNER_STRIDE]
   OKIN_S_MOP,            // [NMOP][OKIN_MOP_STRIDE]
   OKIN_S_MAXLE,          // [NMAXLE][OKIN_MAXLE_STRIDE]
+  OKIN_S_SHIM,           // [NSHIM][OKIN_SHIM_STRIDE]
+  OKIN_S_SHIM_PTS,       // point lists referenced by SHIM (upright attachments, rocker group)
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000
 
 // double sections
-enum okin_fsec { OKIN_F_PAR_VAL = 0, OKIN_F_CST_INIT, OKIN_F_MCONST, OKIN_F_COUNT };
+enum okin_fsec { OKIN_F_PAR_VAL = 0, OKIN_F_CST_INIT, OKIN_F_MCONST, OKIN_F_PARAM_DEFAULT, OKIN_F_COUNT };
 
 // Row record: int32[OKIN_ROW_STRIDE]
 enum okin_row_slot {
@@ -175,3 +179,11 @@ enum okin_row_slot {
 #define OKIN_ADJ_STRIDE 8
 #define OKIN_MAX_CHAIN 4
 #define OKIN_MAX_TARGETS 4
+
+// Camber-shim record: int32[OKIN_SHIM_STRIDE] =
+//   {ubj, lbj, upper_wishbone_inboard_front, upper_wishbone_inboard_rear, heading_in, heading_out,
+//    has_rocker, rocker_axis_a, rocker_axis_b, pushrod_in, pushrod_out, param_off,
+//    upright_list_begin, upright_list_end, rocker_list_begin, rocker_list_end}
+// params[param_off ..] = {face_a(3), face_b(3), face_normal(3), design_thickness, setup_thickness}
+#define OKIN_SHIM_STRIDE 16
+#define OKIN_SHIM_NPARAM 11

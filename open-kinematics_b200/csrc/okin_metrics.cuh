@@ -175,3 +175,76 @@ OKIN_HD T okin_distance(OkinV3<T> a, OkinV3<T> b) {
 #define OKIN_MF_DRIVEN_HERE 8
 // Axle record: int32[16] = {wcL, wcR, cpL, cpR, d_wcL, d_wcR, d_cpL, d_cpR, rackL, d_rackL, out_base, 0...}
 #define OKIN_MAXLE_STRIDE 16
+
+// ---- camber-shim assembly pre-solve (suspensions/config/shims.py:126-501) -------------------------
+OKIN_HD OkinDual okin_sin(OkinDual a) { return {sin(a.v), cos(a.v) * a.d}; }
+OKIN_HD OkinDual okin_cos(OkinDual a) { return {cos(a.v), -sin(a.v) * a.d}; }
+OKIN_HD double okin_sin(double a) { return sin(a); }
+OKIN_HD double okin_cos(double a) { return cos(a); }
+
+// Rodrigues rotation of v by the rotation vector w (geometric.py:351-374).  For |w| -> 0 the
+// series forms of sin(a)/a and (1-cos a)/a^2 keep the value and its derivative exact.
+template <typename T>
+OKIN_HD OkinV3<T> okin_rodrigues(OkinV3<T> v, OkinV3<T> w) {
+  const T a2 = okin_dot(w, w);
+  T s, c;  // s = sin(a)/a, c = (1 - cos a)/a^2
+  if (okin_val(a2) < 1e-12) {
+    s = okin_const(1.0, T()) - a2 * (1.0 / 6.0);
+    c = okin_const(0.5, T()) - a2 * (1.0 / 24.0);
+  } else {
+    const T a = okin_sqrt(a2);
+    s = okin_sin(a) / a;
+    c = (okin_const(1.0, T()) - okin_cos(a)) / a2;
+  }
+  const OkinV3<T> wxv = okin_cross(w, v);
+  const OkinV3<T> wxwxv = okin_cross(w, wxv);
+  return v + okin_scale(wxv, s) + okin_scale(wxwxv, c);
+}
+
+struct OkinShimCtx {
+  double t_setup, n[3], wb_axis[3], hl_in[3], hl_len, lbj[3], uwf[3], uwf_to_ubj[3];
+  double ubj_to_a[3], ubj_to_b[3], lbj_to_a[3], lbj_to_b[3], lbj_to_hl_out[3];
+  int has_rocker;
+  double rk_axis_pt[3], rk_axis[3], rk_to_pr_in[3], lbj_to_pr_out[3], pr_len;
+};
+
+template <typename T>
+OKIN_HD OkinV3<T> okin_c3(const double* p) { return {okin_const(p[0], T()), okin_const(p[1], T()), okin_const(p[2], T())}; }
+
+// Residuals (shims.py:126-268): datum A closure (3), datum B closure (3), normal alignment (3),
+// heading-link length (1), optional pushrod length (1).
+template <typename T>
+OKIN_HD void okin_shim_residuals(const OkinShimCtx& c, const T* x, T* r) {
+  const OkinV3<T> wb = okin_scale(okin_c3<T>(c.wb_axis), x[0]);
+  const OkinV3<T> cb = {x[1], x[2], x[3]}, ub = {x[4], x[5], x[6]};
+  const OkinV3<T> ubj = okin_c3<T>(c.uwf) + okin_rodrigues(okin_c3<T>(c.uwf_to_ubj), wb);
+  const OkinV3<T> lbj = okin_c3<T>(c.lbj);
+  const OkinV3<T> ncb = okin_rodrigues(okin_c3<T>(c.n), cb);
+  const OkinV3<T> nub = okin_rodrigues(okin_c3<T>(c.n), ub);
+  const OkinV3<T> cbA = ubj + okin_rodrigues(okin_c3<T>(c.ubj_to_a), cb);
+  const OkinV3<T> cbB = ubj + okin_rodrigues(okin_c3<T>(c.ubj_to_b), cb);
+  const OkinV3<T> ubA = lbj + okin_rodrigues(okin_c3<T>(c.lbj_to_a), ub);
+  const OkinV3<T> ubB = lbj + okin_rodrigues(okin_c3<T>(c.lbj_to_b), ub);
+  const T t = okin_const(c.t_setup, T());
+  const OkinV3<T> ra = ubA - cbA - okin_scale(ncb, t);
+  const OkinV3<T> rb = ubB - cbB - okin_scale(ncb, t);
+  const OkinV3<T> rn = nub - ncb;
+  r[0] = ra.x; r[1] = ra.y; r[2] = ra.z; r[3] = rb.x; r[4] = rb.y; r[5] = rb.z;
+  r[6] = rn.x; r[7] = rn.y; r[8] = rn.z;
+  const OkinV3<T> hl_out = lbj + okin_rodrigues(okin_c3<T>(c.lbj_to_hl_out), ub);
+  r[9] = okin_distance(hl_out, okin_c3<T>(c.hl_in)) - okin_const(c.hl_len, T());
+  if (c.has_rocker) {
+    const OkinV3<T> pr_in = okin_c3<T>(c.rk_axis_pt) + okin_rodrigues(okin_c3<T>(c.rk_to_pr_in), okin_scale(okin_c3<T>(c.rk_axis), x[7]));
+    const OkinV3<T> pr_out = lbj + okin_rodrigues(okin_c3<T>(c.lbj_to_pr_out), ub);
+    r[10] = okin_distance(pr_out, pr_in) - okin_const(c.pr_len, T());
+  }
+}
+
+OKIN_HD void okin_rotate_about_axis(double* p, const double* pivot, const double* axis, double angle) {
+  // Rodrigues about a unit axis through pivot (geometric.py:377-400)
+  const double v[3] = {p[0] - pivot[0], p[1] - pivot[1], p[2] - pivot[2]};
+  const double ca = cos(angle), sa = sin(angle);
+  const double kv = axis[0] * v[0] + axis[1] * v[1] + axis[2] * v[2];
+  const double cr[3] = {axis[1] * v[2] - axis[2] * v[1], axis[2] * v[0] - axis[0] * v[2], axis[0] * v[1] - axis[1] * v[0]};
+  for (int k = 0; k < 3; ++k) p[k] = pivot[k] + v[k] * ca + cr[k] * sa + axis[k] * (kv * (1.0 - ca));
+}

@@ -8,10 +8,11 @@
 #include "okin_core.cuh"
 
 extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const double* fb, long n_instances,
-                              int n_steps, const double* hardpoints, const double* tvals, double step_tol,
+                              int n_steps, const double* hardpoints, const double* params, const double* tvals,
+                              double step_tol,
                               double coarse_tol, double residual_tol, double mu_init, int max_iter, int use_predictor,
                               double* positions, int32_t* iters, double* max_residual, double* tangents,
-                              double* metrics, int32_t* status, int32_t* failed_step) {
+                              double* metrics, double* design, int32_t* status, int32_t* failed_step) {
   if (hdr[OKIN_H_MAGIC] != OKIN_MAGIC) return -1;
   OkinProgram pr{hdr, ib, fb};
   OkinSolverCfg cfg{step_tol, coarse_tol, residual_tol, mu_init, max_iter, use_predictor};
@@ -25,9 +26,11 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
     out.max_residual = max_residual ? max_residual + (size_t)i * n_steps : nullptr;
     out.tangents = tangents ? tangents + (size_t)i * n_steps * nt * n : nullptr;
     out.metrics = metrics ? metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
+    out.design = design ? design + (size_t)i * 3 * nout : nullptr;
     out.status = status + i;
     out.failed_step = failed_step + i;
-    okin_sweep(pr, sm.data(), hardpoints + (size_t)i * 3 * nin, tvals, n_steps, cfg, out);
+    okin_sweep(pr, sm.data(), hardpoints + (size_t)i * 3 * nin,
+               params ? params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, tvals, n_steps, cfg, out);
   }
   return 0;
 }

@@ -78,6 +78,26 @@ def bump_sweep(steps: int, lo: float, hi: float) -> dict:
         {"point": "wheel_center", "direction": {"axis": "z"}, "mode": "relative", "start": lo, "stop": hi}]}
 
 
+def with_shim(geom: dict, setup: float) -> dict:
+    g = copy.deepcopy(geom)
+    g["config"]["camber_shim"]["setup_thickness"] = setup
+    return g
+
+
+def c4_full(geom: dict, setup: float) -> dict:
+    """BASELINE config 4: T-bar + torsion bars + rocker-to-rocker heave link + camber shim
+    (SURVEY.md section 8d)."""
+    g = copy.deepcopy(geom)
+    g["axle_config"]["heave_link"] = {"type": "rocker_to_rocker"}
+    g["hardpoints"]["left"]["heave_link_rocker"] = {"x": 0, "y": 300, "z": 400}
+    g["axle_config"]["left_setup"] = {"camber_shim": {
+        "shim_face_point_a": {"x": -25.0, "y": 750.0, "z": 510.0},
+        "shim_face_point_b": {"x": -25.0, "y": 750.0, "z": 490.0},
+        "shim_face_normal": {"x": 0.0, "y": 1.0, "z": 0.0},
+        "design_thickness": 30.0, "setup_thickness": setup}}
+    return g
+
+
 CASES = {
     # BASELINE.json configs[0]
     "c1_dw_corner_bump": (load("tests/data/geometry.yaml"), load("scripts/bump_sweep.yaml")),
@@ -95,6 +115,13 @@ CASES = {
     "macpherson_axle": (load("tests/data/macpherson_axle_geometry.yaml"), load("tests/data/axle_sweep.yaml")),
     "dw_corner_coilover_direct": (load("tests/data/corner_strut_geometry.yaml"), load("scripts/bump_sweep.yaml")),
     "dw_corner_rocker": (load("tests/data/corner_rocker_geometry.yaml"), bump_sweep(21, -40.0, 40.0)),
+    # camber-shim pre-solve (config/shims.py): 2 mm thicker shim on the shipped corner, upright-mounted
+    # pushrod corner (rocker coupling), and BASELINE configs[3] in full
+    "c1_shim_plus2mm": (with_shim(load("tests/data/geometry.yaml"), 32.0), load("scripts/bump_sweep.yaml")),
+    "c4_tbar_heave_shim_roll": (c4_full(load("tests/data/axle_geometry_t_bar.yaml"), 31.0),
+                                load("tests/data/axle_t_bar_roll_sweep.yaml")),
+    "c4_tbar_heave_shim_bump": (c4_full(load("tests/data/axle_geometry_t_bar.yaml"), 29.25),
+                                load("tests/data/axle_t_bar_bump_sweep.yaml")),
 }
 
 

@@ -27,6 +27,9 @@ SWEEP_CASES = [
     "c3_rocker_ubar_coilover_roll", "c4_tbar_roll", "c4_tbar_bump", "dw_axle_direct", "macpherson_axle",
     "dw_corner_coilover_direct", "dw_corner_rocker",
 ]
+# Configurations with a camber shim whose setup thickness differs from design: the pre-solve runs
+# on the device, so the host model's initial_state() needs a GPU; CPU tests use structure().
+SHIM_CASES = ["c1_shim_plus2mm", "c4_tbar_heave_shim_roll", "c4_tbar_heave_shim_bump"]
 
 
 def load_golden(name: str):
@@ -48,17 +51,18 @@ def key_from_name(name: str):
 
 
 def authored_positions(suspension) -> dict:
-    """Authored (un-derived) position of every non-derived point, keyed like a solved state."""
+    """Authored (un-derived, un-shimmed) position of every input point, keyed like a solved state."""
     if getattr(suspension, "is_axle", False):
         out = {PointRef(side, k): p.data.copy() for side, c in suspension.corners.items()
                for k, p in c.hardpoints.items()}
-        for k, p in suspension.initial_state().positions.items():
-            out.setdefault(k, p.data.copy())
+        arb = suspension.anti_roll
+        for point, p in getattr(arb, "center_points", {}).items():
+            out[PointRef(Side.CENTER, point)] = p.data.copy()
+        arm = PointID.DROPLINK_U_BAR if type(arb).__name__ == "ArbUBar" else PointID.DROPLINK_T_BAR
+        for side, p in getattr(arb, "droplink_points", {}).items():
+            out[PointRef(side, arm)] = p.data.copy()
         return out
-    out = {k: p.data.copy() for k, p in suspension.hardpoints.items()}
-    for k, p in suspension.initial_state().positions.items():
-        out.setdefault(k, p.data.copy())
-    return out
+    return {k: p.data.copy() for k, p in suspension.hardpoints.items()}
 
 
 _FAMILY = {
@@ -132,16 +136,16 @@ def emu_lib():
         lib = ctypes.CDLL(out)
         lib.okin_emu_sweep.restype = ctypes.c_int
         lib.okin_emu_sweep.argtypes = (
-            [ctypes.c_void_p] * 3 + [ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+            [ctypes.c_void_p] * 3 + [ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                      ctypes.c_int, ctypes.c_int]
-            + [ctypes.c_void_p] * 7)
+            + [ctypes.c_void_p] * 8)
         _EMU = lib
     return _EMU
 
 
 def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, step_tol=1e-6, coarse_tol=1e-3,
-              residual_tol=1e-3, mu_init=1e-3, max_iter=50, use_predictor=2) -> dict:
+              residual_tol=1e-3, mu_init=1e-3, max_iter=50, use_predictor=2, params=None) -> dict:
     hp = np.ascontiguousarray(hardpoints, dtype=np.float64).reshape(-1, 3 * program.n_in)
     tv = np.ascontiguousarray(values, dtype=np.float64)
     n_inst, n_steps, nt, n = hp.shape[0], tv.shape[1], tv.shape[0], program.n_unknowns
@@ -150,14 +154,17 @@ def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, step_tol=1e-6
         "max_residual": np.zeros((n_inst, n_steps)), "tangents": np.zeros((n_inst, n_steps, nt, n)),
         "status": np.zeros(n_inst, np.int32), "failed_step": np.zeros(n_inst, np.int32),
         "metrics": np.zeros((n_inst, n_steps, max(len(program.metric_names), 1))),
+        "design": np.zeros((n_inst, program.n_out, 3)),
     }
+    par = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
     hdr = np.ascontiguousarray(program.hdr)
     rc = emu_lib().okin_emu_sweep(
         hdr.ctypes.data, program.iblob.ctypes.data, program.fblob.ctypes.data, n_inst, n_steps,
-        hp.ctypes.data, tv.ctypes.data, step_tol, coarse_tol, residual_tol, mu_init, max_iter, use_predictor,
+        hp.ctypes.data, None if par is None else par.ctypes.data, tv.ctypes.data, step_tol, coarse_tol,
+        residual_tol, mu_init, max_iter, use_predictor,
         out["positions"].ctypes.data, out["iters"].ctypes.data, out["max_residual"].ctypes.data,
         out["tangents"].ctypes.data, out["metrics"].ctypes.data if program.metric_names else None,
-        out["status"].ctypes.data, out["failed_step"].ctypes.data)
+        out["design"].ctypes.data, out["status"].ctypes.data, out["failed_step"].ctypes.data)
     assert rc == 0
     return out
 

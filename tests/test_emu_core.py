@@ -19,9 +19,11 @@ POS_TOL_MM = 1e-6
 
 
 def _program(sus, sweep, design_rules=True):
+    from open_kinematics_b200.core.shim_program import shim_records
     heads, values = sweep_target_values(sweep)
-    prog = compile_topology(sus.initial_state(), sus.constraints(), sus.derived_spec(), heads,
-                            design_rules=design_rules)
+    state, constraints = sus.structure() if design_rules else (sus.initial_state(), sus.constraints())
+    prog = compile_topology(state, constraints, sus.derived_spec(), heads, design_rules=design_rules,
+                            shims=shim_records(sus) if design_rules else None)
     return prog, values
 
 
@@ -148,3 +150,36 @@ def test_oracle_and_core_agree_on_random_instance():
         assert out["status"][0] == 0 and ref["status"] == 0
         order = [prog.out_keys.index(k) for k in ref["keys"]]
         assert np.abs(out["positions"][0][:, order] - ref["positions"]).max() <= POS_TOL_MM
+
+
+from helpers import SHIM_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", SHIM_CASES)
+def test_camber_shim_presolve_matches_reference(case):
+    """Setup pose (config/shims.py assembly solve + double_wishbone.py:546-571 application) and the
+    sweep solved from it, positions and metric rows vs the reference."""
+    from open_kinematics_b200.core.topology import compile_suspension
+    from test_emu_metrics import check_metrics
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    prog = compile_suspension(sus, sweep)
+    assert prog.param_names and prog.metric_names == meta["metric_names"]
+    out = emu_solve(prog, _nominal(sus, prog), arr["sweep_values"])
+    assert out["status"][0] == 0
+    order = [prog.out_keys.index(key_from_name(n)) for n in meta["point_keys"]]
+    assert np.abs(out["design"][0][order] - arr["design_positions"]).max() <= POS_TOL_MM
+    assert np.abs(out["positions"][0][:, order] - arr["positions_tight"]).max() <= POS_TOL_MM
+    check_metrics(prog.metric_names, out["metrics"][0], arr["metrics"])
+    # the same answer when the shim parameters arrive per instance instead of as defaults
+    out2 = emu_solve(prog, _nominal(sus, prog), arr["sweep_values"], params=prog.param_default[None, :])
+    assert np.array_equal(out2["positions"], out["positions"])
+    # a no-op shim (setup == design) leaves the authored pose untouched
+    par = prog.param_default.copy()
+    for i, name in enumerate(prog.param_names):
+        if name.endswith("setup_thickness"):
+            par[i] = par[i - 1]
+    out3 = emu_solve(prog, _nominal(sus, prog), arr["sweep_values"][:, :1], params=par[None, :])
+    auth = authored_positions(sus)
+    for k, v in auth.items():
+        assert np.array_equal(out3["design"][0][prog.out_keys.index(k)], v)

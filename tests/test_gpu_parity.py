@@ -160,3 +160,61 @@ def test_invalid_geometry_is_flagged_not_propagated():
     good = [0, 1, 2, 4, 6, 7]
     assert (out["status"][good] == 0).all()
     assert np.abs(out["positions"][good] - out["positions"][0]).max() == 0.0
+
+
+from helpers import SHIM_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", SHIM_CASES)
+def test_camber_shim_presolve_matches_reference(case):
+    """Setup pose from the on-device shim assembly pre-solve, the sweep solved from it and its
+    metric rows vs the reference; also the host model's initial_state(), which asks the device
+    for the setup pose (no host-side shim arithmetic)."""
+    from open_kinematics_b200.core.topology import compile_suspension
+    from test_emu_metrics import check_metrics
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    prog = compile_suspension(sus, sweep)
+    out = gpu_solve(prog, _nominal(sus, prog), arr["sweep_values"])
+    assert out["status"][0] == 0
+    order = [prog.out_keys.index(key_from_name(n)) for n in meta["point_keys"]]
+    assert np.abs(out["positions"][0][:, order] - arr["positions_tight"]).max() <= POS_TOL_MM
+    check_metrics(prog.metric_names, out["metrics"][0], arr["metrics"])
+    state = sus.initial_state()
+    got = np.array([state.positions[key_from_name(n)].data for n in meta["point_keys"]])
+    assert np.abs(got - arr["design_positions"]).max() <= POS_TOL_MM
+    # single-instance boundary on the shimmed model
+    from open_kinematics_b200.core.sweep import solve_sweep
+    states, _ = solve_sweep(sus, sweep)
+    got = np.array([[st.positions[key_from_name(n)].data for n in meta["point_keys"]] for st in states])
+    assert np.abs(got - arr["positions_tight"]).max() <= POS_TOL_MM
+
+
+def test_per_instance_shim_thickness_batch():
+    """Monte-Carlo over shim thickness (BASELINE configs[3]): each instance's setup pose is
+    solved on the device; thickness == design reproduces the un-shimmed sweep."""
+    from open_kinematics_b200.core.sweep import BatchSolver
+    meta, arr = load_golden("c4_tbar_heave_shim_roll")
+    sus, sweep = build_case(meta)
+    solver = BatchSolver(sus, sweep)
+    prog = solver.program
+    n = 64
+    hp = np.repeat(solver.nominal_hardpoints()[None, :], n, axis=0)
+    params = np.repeat(prog.param_default[None, :], n, axis=0)
+    setup_cols = [i for i, name in enumerate(prog.param_names) if name.endswith("setup_thickness")]
+    rng = np.random.default_rng(4)
+    params[:, setup_cols] = rng.uniform(29.5, 30.5, size=(n, len(setup_cols)))
+    params[0, setup_cols] = 31.0      # the golden instance (left shim; the mirrored right follows)
+    params[1, setup_cols] = 30.0      # no-op shim
+    res = solver.solve(hp, params=params)
+    assert (res.status == 0).all()
+    order = [prog.out_keys.index(key_from_name(k)) for k in meta["point_keys"]]
+    assert np.abs(res.positions[0][:, order] - arr["positions_tight"]).max() <= POS_TOL_MM
+    meta0, arr0 = load_golden("c4_tbar_roll")      # same T-bar axle without heave link / shim
+    cam = prog.metric_names.index("camber_left")
+    met = solver.solve(hp, params=params, want_metrics=True).metrics
+    # thicker shim -> more negative camber at the design step, monotonically
+    mid = arr["sweep_values"].shape[1] // 2
+    order_t = np.argsort(params[:, setup_cols[0]])
+    assert np.all(np.diff(met[order_t, mid, cam]) < 0)
+    solver.close()
