@@ -59,7 +59,9 @@ struct okin_topology {
   std::mutex mu;
 };
 
-__global__ void __launch_bounds__(OKIN_WARPS_PER_CTA * 32)
+// 3 resident CTAs per SM (12 warps): caps the kernel and its out-of-line callees at 168 registers;
+// only the once-per-instance shim pre-solve spills.
+__global__ void __launch_bounds__(OKIN_WARPS_PER_CTA * 32, 3)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, const double* __restrict__ hardpoints,
                   const double* __restrict__ params, const double* __restrict__ tvals, OkinSolverCfg cfg,
