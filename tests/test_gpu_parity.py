@@ -215,7 +215,11 @@ def test_per_instance_shim_thickness_batch():
     met = solver.solve(hp, params=params, want_metrics=True).metrics
     # camber at the design step is a monotone function of the shim thickness
     mid = arr["sweep_values"].shape[1] // 2
+    # (instances within 0.01 mm of the design thickness are left out: below a 1e-6 rad upright
+    # rotation the reference skips the attachment rotation, double_wishbone.py:554)
+    far = np.abs(params[:, setup_cols[0]] - 30.0) > 0.01
     order_t = np.argsort(params[:, setup_cols[0]])
+    order_t = order_t[far[order_t]]
     steps = np.diff(met[order_t, mid, cam])
     assert np.all(steps > 0) or np.all(steps < 0)
     assert abs(met[order_t[-1], mid, cam] - met[order_t[0], mid, cam]) > 0.1
