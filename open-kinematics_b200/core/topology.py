@@ -62,6 +62,7 @@ def _parse_defs() -> dict:
 
 
 D = _parse_defs()
+assert D["OKIN_S_COUNT"] <= 64 and D["OKIN_F_COUNT"] <= 8 and D["OKIN_H_NGROW"] < D["OKIN_H_SEC0"]
 
 FAMILY_CODE = {
     "distance": D["OKIN_FAM_DISTANCE"], "spherical": D["OKIN_FAM_SPHERICAL"], "angle": D["OKIN_FAM_ANGLE"],
@@ -99,6 +100,14 @@ class _Row:
     slotmap: list = field(default_factory=list)
     cst_off: int = 0
     rg_off: int = 0
+    fast: bool = False      # plain distance row evaluated by the dedicated fast path (stores u only)
+
+    def grad_ref(self, e: int) -> tuple:
+        """(rg offset, negate) of the gradient w.r.t. effective block ``e``.  A fast distance row
+        stores the unit vector u = dR/dp2 once; dR/dp1 = -u."""
+        if self.fast:
+            return self.rg_off, self.eff_sign[e] < 0
+        return self.rg_off + 3 * e, False
 
 
 @dataclass
@@ -444,10 +453,18 @@ def compile_topology(
         row.cst_off = ncst
         ncst += len(row.consts)
         row.rg_off = nrg
-        if is_ls:
+        row.fast = (is_ls and row.fam == FAMILY_CODE["distance"]
+                    and all(what != "derived" for what, _ in per_slot) and len(eff) >= 1)
+        if row.fast:
+            # sign of dR/d(block e) relative to the stored u = (p2 - p1)/|p2 - p1|
+            row.eff_sign = [(-1 if col_of.get(point_keys[row.points[0]]) == c else +1) for c in eff]
+            nrg += 3
+        elif is_ls:
             nrg += 3 * len(eff)
-    if nrg >= 65536:
-        raise ValueError("Row-gradient storage exceeds the 16-bit index range")
+    rg_zero = nrg           # a 3-vector that stays zero (padding target for fixed-length gathers)
+    nrg += 3
+    if nrg >= 32768:
+        raise ValueError("Row-gradient storage exceeds the 15-bit index range")
 
     # ---- elimination order and symbolic block Cholesky ----------------------
     adjacency = [set() for _ in range(NF)]
@@ -482,7 +499,9 @@ def compile_topology(
                 pa, pb = pos_of[ca], pos_of[cb]
                 if pa < pb or (pa == pb and ea != eb):
                     continue
-                contrib.setdefault((pa, pb), []).append(((row.rg_off + 3 * ea) << 16) | (row.rg_off + 3 * eb))
+                (oa, na), (ob, nb) = row.grad_ref(ea), row.grad_ref(eb)
+                word = (oa << 16) | ob | (D["OKIN_CON_NEG"] if na != nb else 0)
+                contrib.setdefault((pa, pb), []).append(word)
     tasks = sorted(block_id.items(), key=lambda kv: (-len(contrib.get(kv[0], [])), kv[1]))
     asm_ptr, asm_task, asm_con = [0], [], []
     for (i, j), b in tasks:       # heaviest first: lanes take tasks round-robin
@@ -496,7 +515,9 @@ def compile_topology(
     per_block: dict = {}
     for row in ls_rows:
         for e, cblk in enumerate(row.eff):
-            per_block.setdefault(pos_of[cblk], []).append(((row.rg_off + 3 * e) << 16) | row_index[id(row)])
+            off_e, neg = row.grad_ref(e)
+            per_block.setdefault(pos_of[cblk], []).append(
+                (off_e << 16) | row_index[id(row)] | (D["OKIN_CON_NEG"] if neg else 0))
     for j in range(NF):
         g_con.extend(per_block.get(j, []))
         g_ptr.append(len(g_con))
@@ -567,9 +588,13 @@ def compile_topology(
         if k not in pidx:
             raise ValueError(f"Output point {k!r} is not part of the model")
 
+    # ---- fast distance rows: {p0 | p1 << 16, cst_off | rg_off << 16, row index}
+    drows = [[row.points[0] | (row.points[1] << 16), row.cst_off | (row.rg_off << 16), i, 0]
+             for i, row in enumerate(rows) if row.fast]
+
     # ---- evaluation order: rows of one family are adjacent so that a 32-row round of the
     # evaluation phase runs (mostly) one code path
-    row_order = sorted(range(len(rows)), key=lambda i: (rows[i].fam, i))
+    row_order = sorted((i for i in range(len(rows)) if not rows[i].fast), key=lambda i: (rows[i].fam, i))
 
     # ---- shared-memory layout (doubles) -----------------------------------------------
     NT = len(targets)
@@ -657,7 +682,7 @@ def compile_topology(
         "OKIN_S_FW_PTR": fw_ptr, "OKIN_S_FW_CON": fw_con, "OKIN_S_BW_PTR": bw_ptr, "OKIN_S_BW_CON": bw_con,
         "OKIN_S_ELIM_POINT": elim_point, "OKIN_S_ELIM_COL": elim_col,
         "OKIN_S_TGT_SC_PTR": tgt_sc_ptr, "OKIN_S_TGT_SC": tgt_sc,
-        "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_ROW_ORDER": row_order,
+        "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_ROW_ORDER": row_order, "OKIN_S_DROW": drows,
         "OKIN_S_DOP_LEV": dop_lev, "OKIN_S_POINT_ELIM": point_elim, "OKIN_S_POINT_DOP": point_dop,
         "OKIN_S_DESIGN_PT": design_pts, "OKIN_S_MCORNER": mcorners, "OKIN_S_MOP": mops, "OKIN_S_MAXLE": maxle,
         "OKIN_S_SHIM": shim_recs, "OKIN_S_SHIM_PTS": shim_pts,
@@ -666,12 +691,12 @@ def compile_topology(
     chunks, cursor = [], 0
     for name, data in isecs.items():
         arr = np.asarray(data, dtype=np.int64).reshape(-1)
-        if arr.size and (arr.max() > 2**31 - 1 or arr.min() < -(2**31)):
-            raise ValueError(f"section {name} overflows int32")
+        if arr.size and (arr.max() > 2**32 - 1 or arr.min() < -(2**31)):
+            raise ValueError(f"section {name} overflows 32 bits")
         s = D[name]
         hdr[D["OKIN_H_SEC0"] + 2 * s] = cursor
         hdr[D["OKIN_H_SEC0"] + 2 * s + 1] = arr.size
-        chunks.append(arr.astype(np.int32))
+        chunks.append((arr & 0xFFFFFFFF).astype(np.uint32).view(np.int32))   # flag bit 31 wraps to sign
         cursor += arr.size
     iblob = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
     fsecs = {"OKIN_F_PAR_VAL": par_val, "OKIN_F_CST_INIT": cst_init, "OKIN_F_MCONST": mconst,
@@ -696,6 +721,7 @@ def compile_topology(
         "OKIN_H_TROW0": trow0, "OKIN_H_SMEM_DOUBLES": off, "OKIN_H_NM": len(metric_names),
         "OKIN_H_NMC": len(mcorners), "OKIN_H_NMOP": len(mops), "OKIN_H_NMAXLE": len(maxle), "OKIN_H_NDSN": ndsn,
         "OKIN_H_NSHIM": len(shim_recs), "OKIN_H_NPARAM": len(param_default),
+        "OKIN_H_NDROW": len(drows), "OKIN_H_NGROW": len(row_order),
         **layout,
     }
     for name, value in counts.items():

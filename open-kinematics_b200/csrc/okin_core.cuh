@@ -43,6 +43,35 @@
 #define OKIN_LDG(p) (*(p))
 #endif
 
+// Warp reductions over the per-lane partials a phase left in red[0..32): shuffles on the device
+// (every lane ends with the result), a plain loop in the lane emulation.  NaN propagates in max.
+#if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
+OKIN_HD double okin_red_sum(const double* red) {
+  double v = red[threadIdx.x & 31u];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+OKIN_HD double okin_red_max(const double* red) {
+  double v = red[threadIdx.x & 31u];
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (w > v || w != w) ? w : v;
+  }
+  return v;
+}
+#else
+OKIN_HD double okin_red_sum(const double* red) {
+  double v = 0.0;
+  for (int k = 0; k < 32; ++k) v += red[k];
+  return v;
+}
+OKIN_HD double okin_red_max(const double* red) {
+  double v = red[0];
+  for (int k = 1; k < 32; ++k) v = (red[k] > v || red[k] != red[k]) ? red[k] : v;
+  return v;
+}
+#endif
+
 struct OkinProgram {
   const int32_t* hdr;  // [OKIN_HDR_SIZE]
   const int32_t* ib;   // int32 blob
@@ -320,9 +349,7 @@ OKIN_FN void okin_shim_presolve(const OkinProgram& pr, double* sm, const double*
     }
   }
   OKIN_PHASE_END
-  double bad = 0.0;
-  for (int k = 0; k < 32; ++k) bad += red[k];
-  if (bad != 0.0) *invalid = 1;
+  if (okin_red_sum(red) != 0.0) *invalid = 1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -448,9 +475,31 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   double* rg = sm + hdr[OKIN_H_OFF_RG];
   double* red = sm + hdr[OKIN_H_OFF_RED];
   const int32_t* order = okin_sec(pr, OKIN_S_ROW_ORDER);
+  const int32_t* drow = okin_sec(pr, OKIN_S_DROW);
+  const int ndrow = hdr[OKIN_H_NDROW], ngrow = hdr[OKIN_H_NGROW];
   OKIN_PHASE_BEGIN
   double sq = 0.0, mx = 0.0;
-  for (int slot = lane; slot < nrows; slot += 32) {
+  // Fast path: plain distance rows (most of every shipped topology).  r = sqrt(s + eps^2) - eps - L,
+  // u = (p2 - p1)/sqrt(s + eps^2) is the whole gradient (dR/dp2 = u, dR/dp1 = -u).
+  for (int slot = lane; slot < ndrow; slot += 32) {
+    const int32_t* rec = drow + 4 * slot;
+    const uint32_t pp = (uint32_t)OKIN_LDG(rec + 0), oo = (uint32_t)OKIN_LDG(rec + 1);
+    const double* a = pos + 3 * (pp & 0xffffu);
+    const double* b = pos + 3 * (pp >> 16);
+    const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+    const double s2 = dx * dx + dy * dy + dz * dz + OKIN_EPS_SQ;
+    const double inv = OKIN_RSQRT(s2);
+    const double res = s2 * inv - OKIN_EPS - cst[oo & 0xffffu];
+    r[OKIN_LDG(rec + 2)] = res;
+    const double ar = fabs(res);
+    mx = (ar > mx || ar != ar) ? ar : mx;
+    sq += res * res;
+    if (with_grad) {
+      double* u = rg + (oo >> 16);
+      u[0] = dx * inv; u[1] = dy * inv; u[2] = dz * inv;
+    }
+  }
+  for (int slot = lane; slot < ngrow; slot += 32) {
     const int t = OKIN_LDG(order + slot);
     const int32_t* rec = rows + t * OKIN_ROW_STRIDE;
     const int fam = OKIN_LDG(rec + OKIN_R_FAM);
@@ -475,7 +524,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
     }
     r[t] = res;
     const double ar = fabs(res);
-    mx = ar > mx ? ar : mx;
+    mx = (ar > mx || ar != ar) ? ar : mx;
     if (t < nls) sq += res * res;
     if (grad) {
       double* out = rg + OKIN_LDG(rec + OKIN_R_RG);
@@ -504,11 +553,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   red[lane] = sq;
   red[32 + lane] = mx;
   OKIN_PHASE_END
-  double f2 = 0.0, rmax = 0.0;
-  for (int k = 0; k < 32; ++k) {
-    f2 += red[k];
-    rmax = red[32 + k] > rmax ? red[32 + k] : rmax;
-  }
+  const double f2 = okin_red_sum(red), rmax = okin_red_max(red + 32);
   st.f2 = f2;
   st.rmax = rmax;
 }
@@ -539,9 +584,10 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
       double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(acon + q);
-        const double* ga = rg + (w >> 16);
+        const double* ga = rg + ((w >> 16) & 0x7fffu);
         const double* gb = rg + (w & 0xffffu);
-        const double x0 = ga[0], x1 = ga[1], x2 = ga[2], y0 = gb[0], y1 = gb[1], y2 = gb[2];
+        const double sg = (w & OKIN_CON_NEG) ? -1.0 : 1.0;
+        const double x0 = sg * ga[0], x1 = sg * ga[1], x2 = sg * ga[2], y0 = gb[0], y1 = gb[1], y2 = gb[2];
         a00 = fma(x0, y0, a00); a01 = fma(x0, y1, a01); a02 = fma(x0, y2, a02);
         a10 = fma(x1, y0, a10); a11 = fma(x1, y1, a11); a12 = fma(x1, y2, a12);
         a20 = fma(x2, y0, a20); a21 = fma(x2, y1, a21); a22 = fma(x2, y2, a22);
@@ -557,8 +603,8 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
       double g0 = 0, g1 = 0, g2 = 0;
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(gcon + q);
-        const double* ga = rg + (w >> 16);
-        const double res = r[w & 0xffffu];
+        const double* ga = rg + ((w >> 16) & 0x7fffu);
+        const double res = (w & OKIN_CON_NEG) ? -r[w & 0xffffu] : r[w & 0xffffu];
         g0 = fma(ga[0], res, g0); g1 = fma(ga[1], res, g1); g2 = fma(ga[2], res, g2);
       }
       vec[3 * j] = -g0; vec[3 * j + 1] = -g1; vec[3 * j + 2] = -g2;  // right-hand side of A h = -g
@@ -645,9 +691,7 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
     }
     OKIN_PHASE_END
   }
-  double bad = 0.0;
-  for (int k = 0; k < 32; ++k) bad += red[k];
-  st.notpd = bad != 0.0;
+  st.notpd = okin_red_sum(red) != 0.0;
 }
 
 // Solve A X = B for nrhs right-hand sides stored at vec[first .. first+nrhs) (elimination order),
@@ -734,13 +778,11 @@ OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, dou
     const double h = v[u];
     pos[idx] = x + scale * h;
     const double ah = fabs(h);
-    mx = ah > mx ? ah : mx;
+    mx = (ah > mx || ah != ah) ? ah : mx;
   }
   red[lane] = mx;
   OKIN_PHASE_END
-  double hmax = 0.0;
-  for (int k = 0; k < 32; ++k) hmax = red[k] > hmax ? red[k] : hmax;
-  return hmax;
+  return okin_red_max(red);
 }
 
 template <typename Dummy = void>
@@ -769,9 +811,7 @@ OKIN_FN double okin_vec_max(const OkinProgram& pr, double* sm, int which) {
   }
   red[lane] = mx;
   OKIN_PHASE_END
-  double out = 0.0;
-  for (int k = 0; k < 32; ++k) out = (red[k] > out || red[k] != red[k]) ? red[k] : out;
-  return out;
+  return okin_red_max(red);
 }
 
 // Continuation predictor: x += p + (second ? (p - p_prev)/2 : 0), p = sum_j V_j dt_j, where V_j
@@ -862,13 +902,13 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       okin_assemble(pr, sm, 0.0, true);
       okin_tangent_rhs(pr, sm);
       okin_solve(pr, sm, 0, 1 + pr.hdr[OKIN_H_NT], false);
-      const double h2 = okin_vec_max(pr, sm, 0);
+      const double h2 = okin_apply_step(pr, sm, 0, 1.0, true);
       if (h2 <= cfg.step_tol) {
-        okin_apply_step(pr, sm, 0, 1.0, false);
         *converged = true;
         *tangents_ready = true;
         break;
       }
+      okin_restore(pr, sm);
       // Not contracting fast enough: relinearise at the current point.
       okin_eval_rows(pr, sm, tval, true, st);
       ++nfev;

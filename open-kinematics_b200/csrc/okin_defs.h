@@ -102,9 +102,11 @@ enum okin_hdr_slot {
   OKIN_H_OFF_DSN, OKIN_H_OFF_MCTX,
   OKIN_H_NSHIM,    // camber-shim pre-solve records (one per shimmed corner)
   OKIN_H_NPARAM,   // per-instance scalar parameters (doubles)
-  OKIN_H_SEC0 = 48,
-  OKIN_H_FSEC0 = 48 + 2 * 40,
-  OKIN_HDR_SIZE = 48 + 2 * 40 + 2 * 4
+  OKIN_H_NDROW,    // distance rows on the fast evaluation path
+  OKIN_H_NGROW,    // rows on the generic evaluation path (ROW_ORDER entries)
+  OKIN_H_SEC0 = 64,                      // room for 64 scalar slots,
+  OKIN_H_FSEC0 = 64 + 2 * 64,            // 64 int32 sections
+  OKIN_HDR_SIZE = 64 + 2 * 64 + 2 * 8    // and 8 double sections
 };
 #define OKIN_MAGIC 0x4f4b494e  // "OKIN"
 
@@ -150,9 +152,13 @@ enum okin_isec {
   OKIN_S_MAXLE,          // [NMAXLE][OKIN_MAXLE_STRIDE]
   OKIN_S_SHIM,           // [NSHIM][OKIN_SHIM_STRIDE]
   OKIN_S_SHIM_PTS,       // point lists referenced by SHIM (upright attachments, rocker group)
+  OKIN_S_DROW,           // [NDROW][4] = {p0 | p1 << 16, cst_off | rg_off << 16, row, 0}: plain distance rows
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000
+// Contribution words carry a negate flag: the product enters with a minus sign (a fast distance
+// row stores u = dR/dp2 once, dR/dp1 = -u).
+#define OKIN_CON_NEG 0x80000000
 
 // double sections
 enum okin_fsec { OKIN_F_PAR_VAL = 0, OKIN_F_CST_INIT, OKIN_F_MCONST, OKIN_F_PARAM_DEFAULT, OKIN_F_COUNT };
