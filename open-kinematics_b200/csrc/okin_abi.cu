@@ -18,7 +18,8 @@
 #include "../../include/okin.h"
 #include "okin_core.cuh"
 
-#define OKIN_WARPS_PER_CTA 4
+#define OKIN_MAX_THREADS 384   // 12 warps: the most one CTA may hold (register cap 170 per thread)
+#define OKIN_REGS_PER_THREAD 168
 #define OKIN_MAX_DEVICES 16
 
 namespace {
@@ -44,6 +45,9 @@ struct DeviceCopy {
   double* fb = nullptr;
   int num_sms = 0;
   int ctas_per_sm = 0;
+  int warps_per_cta = 0;
+  int smem_bytes = 0;
+  int table_doubles = 0;
   // grow-only workspace for the host-buffer entry point
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -59,21 +63,30 @@ struct okin_topology {
   std::mutex mu;
 };
 
-// 3 resident CTAs per SM (12 warps): caps the kernel and its out-of-line callees at 168 registers;
-// only the once-per-instance shim pre-solve spills.
-__global__ void __launch_bounds__(OKIN_WARPS_PER_CTA * 32, 3)
+// Shared memory of a CTA = [topology tables (int32 blob)] [one state slice per warp].  The tables are
+// copied once per (persistent) CTA so that every index lookup of the interpreter is a shared-memory
+// load instead of a global one (ncu round 1: long-scoreboard stalls on __ldg were the top stall).
+// Register cap 170 = 65536 / 384: up to 12 resident warps per SM in any CTA shape the host picks.
+__global__ void __launch_bounds__(OKIN_MAX_THREADS, 1)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, const double* __restrict__ hardpoints,
                   const double* __restrict__ params, const double* __restrict__ tvals, OkinSolverCfg cfg,
                   double* positions, int32_t* iters, double* max_residual, double* tangents, double* metrics,
-                  double* design, int32_t* status, int32_t* failed_step) {
+                  double* design, int32_t* status, int32_t* failed_step, int n_iblob, int table_doubles) {
   extern __shared__ double okin_smem[];
-  OkinProgram pr{hdr, ib, fb};
+  int32_t* shdr = reinterpret_cast<int32_t*>(okin_smem);
+  int32_t* tab = shdr + OKIN_HDR_SIZE;
+  for (int i = threadIdx.x; i < OKIN_HDR_SIZE; i += blockDim.x) shdr[i] = hdr[i];
+  for (int i = threadIdx.x; i < n_iblob; i += blockDim.x) tab[i] = ib[i];
+  __syncthreads();
+  hdr = shdr;
+  OkinProgram pr{shdr, tab, fb};
   const int warp = threadIdx.x >> 5;
-  double* sm = okin_smem + (size_t)warp * hdr[OKIN_H_SMEM_DOUBLES];
+  const int warps_per_cta = blockDim.x >> 5;
+  double* sm = okin_smem + table_doubles + (size_t)warp * hdr[OKIN_H_SMEM_DOUBLES];
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
-  const long long stride = (long long)gridDim.x * OKIN_WARPS_PER_CTA;
-  for (long long i = (long long)blockIdx.x * OKIN_WARPS_PER_CTA + warp; i < n_instances; i += stride) {
+  const long long stride = (long long)gridDim.x * warps_per_cta;
+  for (long long i = (long long)blockIdx.x * warps_per_cta + warp; i < n_instances; i += stride) {
     OkinOutputs out;
     out.positions = positions ? positions + (size_t)i * n_steps * 3 * nout : nullptr;
     out.iters = iters ? iters + (size_t)i * n_steps : nullptr;
@@ -117,12 +130,31 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
     cudaDeviceProp prop;
     OKIN_CUDA(cudaGetDeviceProperties(&prop, device));
     d.num_sms = prop.multiProcessorCount;
-    const int smem = OKIN_WARPS_PER_CTA * t->hdr[OKIN_H_SMEM_DOUBLES] * (int)sizeof(double);
-    if ((size_t)smem > prop.sharedMemPerBlockOptin)
+    // CTA shape: W warps sharing one copy of the tables; pick the W that keeps the most warps resident
+    // (shared memory, the 64K-register file at OKIN_REGS_PER_THREAD, 1 KB per-CTA reservation).
+    d.table_doubles = (int)(((t->ib.size() + OKIN_HDR_SIZE) * sizeof(int32_t) + 7) / 8);
+    const size_t table_bytes = (size_t)d.table_doubles * 8;
+    const size_t slice_bytes = (size_t)t->hdr[OKIN_H_SMEM_DOUBLES] * sizeof(double);
+    const size_t sm_budget = prop.sharedMemPerMultiprocessor;
+    int best_w = 0, best_ctas = 0;
+    for (int w = 1; w <= OKIN_MAX_THREADS / 32; ++w) {
+      const size_t cta_bytes = table_bytes + w * slice_bytes;
+      if (cta_bytes > prop.sharedMemPerBlockOptin) break;
+      int ctas = (int)(sm_budget / (cta_bytes + 1024));
+      ctas = std::min(ctas, (int)(prop.regsPerMultiprocessor / (OKIN_REGS_PER_THREAD * 32 * w)));
+      ctas = std::min(ctas, 32);
+      if (ctas * w > best_w * best_ctas || (ctas * w == best_w * best_ctas && w < best_w && ctas * w > 0)) {
+        best_w = w;
+        best_ctas = ctas;
+      }
+    }
+    if (best_w == 0 || best_ctas == 0)
       return fail(OKIN_ERR_USAGE, "topology needs more shared memory per CTA than the device offers");
-    OKIN_CUDA(cudaFuncSetAttribute(okin_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.ctas_per_sm, okin_sweep_kernel,
-                                                            OKIN_WARPS_PER_CTA * 32, smem));
+    d.warps_per_cta = best_w;
+    d.smem_bytes = (int)(table_bytes + best_w * slice_bytes);
+    OKIN_CUDA(cudaFuncSetAttribute(okin_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_bytes));
+    OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.ctas_per_sm, okin_sweep_kernel, best_w * 32,
+                                                            d.smem_bytes));
     if (d.ctas_per_sm < 1) return fail(OKIN_ERR_CUDA, "kernel does not fit on an SM");
     OKIN_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     d.ready = true;
@@ -136,13 +168,13 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
            int32_t* failed, int32_t* iters, double* maxres, double* tangents, double* metrics, double* design) {
   if (n_instances == 0) return OKIN_OK;
   OkinSolverCfg c{cfg->step_tol, cfg->coarse_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter, cfg->use_predictor};
-  const int smem = OKIN_WARPS_PER_CTA * t->hdr[OKIN_H_SMEM_DOUBLES] * (int)sizeof(double);
-  const int64_t needed = (n_instances + OKIN_WARPS_PER_CTA - 1) / OKIN_WARPS_PER_CTA;
+  const int w = d->warps_per_cta;
+  const int64_t needed = (n_instances + w - 1) / w;
   const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
   const int grid = (int)std::min<int64_t>(needed, resident);
-  okin_sweep_kernel<<<grid, OKIN_WARPS_PER_CTA * 32, smem, stream>>>(
+  okin_sweep_kernel<<<grid, w * 32, d->smem_bytes, stream>>>(
       d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, hp, par, tv, c, pos, iters, maxres, tangents, metrics,
-      design, status, failed);
+      design, status, failed, (int)t->ib.size(), d->table_doubles);
   OKIN_CUDA(cudaGetLastError());
   return OKIN_OK;
 }
@@ -250,10 +282,10 @@ int okin_launch_geometry(okin_topology* t, int32_t device, int64_t n_instances, 
   DeviceCopy* d = nullptr;
   int rc = ensure_device(t, device, &d);
   if (rc) return rc;
-  const int64_t needed = (n_instances + OKIN_WARPS_PER_CTA - 1) / OKIN_WARPS_PER_CTA;
+  const int64_t needed = (n_instances + d->warps_per_cta - 1) / d->warps_per_cta;
   if (grid) *grid = (int32_t)std::min<int64_t>(needed, (int64_t)d->num_sms * d->ctas_per_sm);
-  if (block) *block = OKIN_WARPS_PER_CTA * 32;
-  if (smem_bytes) *smem_bytes = OKIN_WARPS_PER_CTA * t->hdr[OKIN_H_SMEM_DOUBLES] * (int32_t)sizeof(double);
+  if (block) *block = d->warps_per_cta * 32;
+  if (smem_bytes) *smem_bytes = d->smem_bytes;
   if (ctas_per_sm) *ctas_per_sm = d->ctas_per_sm;
   return OKIN_OK;
 }

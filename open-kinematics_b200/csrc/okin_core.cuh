@@ -36,7 +36,7 @@
 #if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
 #define OKIN_PHASE_BEGIN { const int lane = (int)(threadIdx.x & 31u);
 #define OKIN_PHASE_END } __syncwarp();
-#define OKIN_LDG(p) __ldg(p)
+#define OKIN_LDG(p) (*(p))   // int32 tables live in shared memory, double constants in global
 #else
 #define OKIN_PHASE_BEGIN for (int lane = 0; lane < 32; ++lane) {
 #define OKIN_PHASE_END }
