@@ -551,7 +551,6 @@ def compile_topology(
                 for k in cols_with[j]:
                     upd_con.append(((VEC, 3 * k), (LB, boff(j, k))))
                 upd_ptr.append(len(upd_con))
-            scl.append([j, (LB, boff(j, j)), -1, 0])
             for i in struct[j]:
                 for r in range(3):
                     scl.append([j, (LB, boff(j, j)), (LB, boff(i, j) + 3 * r), 0])
@@ -610,7 +609,7 @@ def compile_topology(
     layout = {
         "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
         "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)), "OKIN_H_OFF_LB": take(9 * NB),
-        "OKIN_H_OFF_DFAC": take(9 * NF), "OKIN_H_OFF_VEC": take((1 + NT) * N), "OKIN_H_OFF_XSAVE": take(N),
+        "OKIN_H_OFF_VEC": take((1 + NT) * N),
         "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)), "OKIN_H_OFF_PPREV": take(N),
     }
     if off >= 65536:
@@ -620,6 +619,7 @@ def compile_topology(
     def sm(ref) -> int:
         return base[ref[0]] + ref[1]
 
+    diag_off = [sm((LB, boff(j, j))) for j in range(NF)]
     upd_dst = [sm(d) for d in upd_dst]
     upd_con = [(sm(a) << 16) | sm(b) for a, b in upd_con]
     scl = [[j, sm(d), (-1 if r == -1 else sm(r)), z] for j, d, r, z in scl]
@@ -682,7 +682,7 @@ def compile_topology(
         "OKIN_S_FW_PTR": fw_ptr, "OKIN_S_FW_CON": fw_con, "OKIN_S_BW_PTR": bw_ptr, "OKIN_S_BW_CON": bw_con,
         "OKIN_S_ELIM_POINT": elim_point, "OKIN_S_ELIM_COL": elim_col,
         "OKIN_S_TGT_SC_PTR": tgt_sc_ptr, "OKIN_S_TGT_SC": tgt_sc,
-        "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_ROW_ORDER": row_order, "OKIN_S_DROW": drows,
+        "OKIN_S_OUT_POINT": [pidx[k] for k in out_keys], "OKIN_S_ROW_ORDER": row_order, "OKIN_S_DROW": drows, "OKIN_S_DIAG_OFF": diag_off,
         "OKIN_S_DOP_LEV": dop_lev, "OKIN_S_POINT_ELIM": point_elim, "OKIN_S_POINT_DOP": point_dop,
         "OKIN_S_DESIGN_PT": design_pts, "OKIN_S_MCORNER": mcorners, "OKIN_S_MOP": mops, "OKIN_S_MAXLE": maxle,
         "OKIN_S_SHIM": shim_recs, "OKIN_S_SHIM_PTS": shim_pts,

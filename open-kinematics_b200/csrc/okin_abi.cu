@@ -18,8 +18,8 @@
 #include "../../include/okin.h"
 #include "okin_core.cuh"
 
-#define OKIN_MAX_THREADS 384   // 12 warps: the most one CTA may hold (register cap 170 per thread)
-#define OKIN_REGS_PER_THREAD 168
+#define OKIN_MAX_THREADS 512   // 16 warps: the most one CTA may hold (register cap 128 per thread)
+#define OKIN_REGS_PER_THREAD 128
 #define OKIN_MAX_DEVICES 16
 
 namespace {
@@ -66,7 +66,8 @@ struct okin_topology {
 // Shared memory of a CTA = [topology tables (int32 blob)] [one state slice per warp].  The tables are
 // copied once per (persistent) CTA so that every index lookup of the interpreter is a shared-memory
 // load instead of a global one (ncu round 1: long-scoreboard stalls on __ldg were the top stall).
-// Register cap 170 = 65536 / 384: up to 12 resident warps per SM in any CTA shape the host picks.
+// Register cap 128 = 65536 / 512: up to 16 resident warps per SM in any CTA shape the host picks
+// (only the once-per-instance shim pre-solve spills at that cap).
 __global__ void __launch_bounds__(OKIN_MAX_THREADS, 1)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, const double* __restrict__ hardpoints,

@@ -633,6 +633,17 @@ OKIN_HD bool okin_chol3(const double* d, double f[9]) {
   return d00 > 0.0 && t11 > 0.0 && t22 > 0.0;
 }
 
+// After a column's rows are scaled its diagonal block is dead, so the diagonal factor
+// {l00,l10,l11,l20,l21,l22, 1/l00,1/l11,1/l22} is written over it -- one level later, inside the
+// next level's update phase (which never reads diagonal blocks of finished columns).
+OKIN_HD void okin_write_diag_factor(double* sm, int doff, double* red, int lane) {
+  double f[9];
+  const bool ok = okin_chol3(sm + doff, f);
+  double* o = sm + doff;
+  for (int k = 0; k < 9; ++k) o[k] = f[k];
+  if (!ok) red[lane] = 1.0;
+}
+
 template <typename Dummy = void>
 OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
   const int32_t* hdr = pr.hdr;
@@ -643,16 +654,19 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
   const int32_t* ucon = okin_sec(pr, OKIN_S_UPD_CON);
   const int32_t* lev_scl = okin_sec(pr, OKIN_S_LEV_SCL);
   const int32_t* scl = okin_sec(pr, OKIN_S_SCL);
-  double* Df = sm + hdr[OKIN_H_OFF_DFAC];
+  const int32_t* lcp = okin_sec(pr, OKIN_S_LEV_COL_PTR);
+  const int32_t* lcol = okin_sec(pr, OKIN_S_LEV_COL);
+  const int32_t* doffs = okin_sec(pr, OKIN_S_DIAG_OFF);
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   red[lane] = 0.0;
   OKIN_PHASE_END
-  for (int lv = 0; lv < nlev; ++lv) {
-    const int ub = OKIN_LDG(lev_upd + lv), ue = OKIN_LDG(lev_upd + lv + 1);
-    if (ue > ub) {
-      // left-looking update of one block row (or of the carried right-hand side)
+  for (int lv = 0; lv <= nlev; ++lv) {
+    const int ub = lv < nlev ? OKIN_LDG(lev_upd + lv) : 0, ue = lv < nlev ? OKIN_LDG(lev_upd + lv + 1) : 0;
+    const int wb = lv > 0 ? OKIN_LDG(lcp + lv - 1) : 0, we = lv > 0 ? OKIN_LDG(lcp + lv) : 0;
+    if (ue > ub || we > wb) {
       OKIN_PHASE_BEGIN
+      // left-looking update of one block row (or of the carried right-hand side)
       for (int t = ub + lane; t < ue; t += 32) {
         const int b = OKIN_LDG(uptr + t), e = OKIN_LDG(uptr + t + 1);
         double* dst = sm + OKIN_LDG(udst + t);
@@ -668,26 +682,24 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
         }
         dst[0] = c0; dst[1] = c1; dst[2] = c2;
       }
+      // diagonal factors of the previous level, taken by the highest lanes
+      for (int c = wb + (31 - lane); c < we; c += 32)
+        okin_write_diag_factor(sm, OKIN_LDG(doffs + OKIN_LDG(lcol + c)), red, lane);
       OKIN_PHASE_END
     }
+    if (lv == nlev) break;
     const int sb = OKIN_LDG(lev_scl + lv), se = OKIN_LDG(lev_scl + lv + 1);
     OKIN_PHASE_BEGIN
     for (int t = sb + lane; t < se; t += 32) {
       const int32_t* rec = scl + 4 * t;
-      const int j = OKIN_LDG(rec + 0), doff = OKIN_LDG(rec + 1), roff = OKIN_LDG(rec + 2);
+      const int doff = OKIN_LDG(rec + 1), roff = OKIN_LDG(rec + 2);
       double f[9];
-      const bool ok = okin_chol3(sm + doff, f);
-      if (roff < 0) {
-        double* o = Df + 9 * j;
-        for (int k = 0; k < 9; ++k) o[k] = f[k];
-        if (!ok) red[lane] = 1.0;
-      } else {
-        double* b = sm + roff;
-        const double x0 = b[0] * f[6];
-        const double x1 = (b[1] - x0 * f[1]) * f[7];
-        const double x2 = (b[2] - x0 * f[3] - x1 * f[4]) * f[8];
-        b[0] = x0; b[1] = x1; b[2] = x2;
-      }
+      okin_chol3(sm + doff, f);
+      double* b = sm + roff;
+      const double x0 = b[0] * f[6];
+      const double x1 = (b[1] - x0 * f[1]) * f[7];
+      const double x2 = (b[2] - x0 * f[3] - x1 * f[4]) * f[8];
+      b[0] = x0; b[1] = x1; b[2] = x2;
     }
     OKIN_PHASE_END
   }
@@ -709,7 +721,7 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
   const int32_t* bptr = okin_sec(pr, OKIN_S_BW_PTR);
   const int32_t* bcon = okin_sec(pr, OKIN_S_BW_CON);
   const double* Lb = sm;
-  const double* Df = sm + hdr[OKIN_H_OFF_DFAC];
+  const int32_t* doffs = okin_sec(pr, OKIN_S_DIAG_OFF);
   double* vec = sm + hdr[OKIN_H_OFF_VEC] + first * n;
   for (int lv = 0; lv < (skip_forward ? 0 : nlev); ++lv) {  // L y = b
     const int cb = OKIN_LDG(lcp + lv), ce = OKIN_LDG(lcp + lv + 1);
@@ -726,7 +738,7 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
         t1 -= B[3] * y[0] + B[4] * y[1] + B[5] * y[2];
         t2 -= B[6] * y[0] + B[7] * y[1] + B[8] * y[2];
       }
-      const double* f = Df + 9 * j;
+      const double* f = sm + OKIN_LDG(doffs + j);
       const double y0 = t0 * f[6];
       const double y1 = (t1 - f[1] * y0) * f[7];
       const double y2 = (t2 - f[3] * y0 - f[4] * y1) * f[8];
@@ -749,7 +761,7 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
         t1 -= B[1] * x[0] + B[4] * x[1] + B[7] * x[2];
         t2 -= B[2] * x[0] + B[5] * x[1] + B[8] * x[2];
       }
-      const double* f = Df + 9 * j;
+      const double* f = sm + OKIN_LDG(doffs + j);
       const double x2 = t2 * f[8];
       const double x1 = (t1 - f[4] * x2) * f[7];
       const double x0 = (t0 - f[1] * x1 - f[3] * x2) * f[6];
@@ -767,14 +779,12 @@ OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, dou
   const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* v = sm + hdr[OKIN_H_OFF_VEC] + which * n;
-  double* xs = sm + hdr[OKIN_H_OFF_XSAVE];
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   double mx = 0.0;
   for (int u = lane; u < n; u += 32) {
     const int idx = 3 * OKIN_LDG(ep + u / 3) + u % 3;
     const double x = pos[idx];
-    if (save) xs[u] = x;
     const double h = v[u];
     pos[idx] = x + scale * h;
     const double ah = fabs(h);
@@ -791,9 +801,9 @@ OKIN_FN void okin_restore(const OkinProgram& pr, double* sm) {
   const int n = 3 * hdr[OKIN_H_NF];
   const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
-  const double* xs = sm + hdr[OKIN_H_OFF_XSAVE];
+  const double* h = sm + hdr[OKIN_H_OFF_VEC];   // the step just applied (vec[0], scale 1)
   OKIN_PHASE_BEGIN
-  for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(ep + u / 3) + u % 3] = xs[u];
+  for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(ep + u / 3) + u % 3] -= h[u];
   OKIN_PHASE_END
 }
 

@@ -91,7 +91,9 @@ enum okin_hdr_slot {
   OKIN_H_TROW0,    // first target row
   // shared-memory layout (offsets in doubles from the instance's base)
   OKIN_H_OFF_POS, OKIN_H_OFF_CST, OKIN_H_OFF_R, OKIN_H_OFF_RG, OKIN_H_OFF_DBLK, OKIN_H_OFF_LB,
-  OKIN_H_OFF_DFAC, OKIN_H_OFF_VEC, OKIN_H_OFF_XSAVE, OKIN_H_OFF_RED, OKIN_H_OFF_PAR, OKIN_H_OFF_PPREV,
+  OKIN_H_OFF_DFAC /* unused: diagonal factors live in their diagonal blocks */, OKIN_H_OFF_VEC,
+  OKIN_H_OFF_XSAVE /* unused: a rejected step is undone by subtracting it */, OKIN_H_OFF_RED, OKIN_H_OFF_PAR,
+  OKIN_H_OFF_PPREV,
   OKIN_H_SMEM_DOUBLES, // shared-memory doubles per instance
   // metric program (csrc/okin_metrics.cuh)
   OKIN_H_NM,       // metric columns per state
@@ -130,7 +132,7 @@ enum okin_isec {
   OKIN_S_UPD_PTR,        // [n_upd+1]
   OKIN_S_UPD_CON,        // (offA << 16) | offB : acc[c] -= sum_t sm[offA+t]*sm[offB+3c+t]
   OKIN_S_LEV_SCL,        // [NLEV+1] ranges into SCL
-  OKIN_S_SCL,            // [..][4] = {elim col j, diag block offset, row offset or -1 (write Dfac), 0}
+  OKIN_S_SCL,            // [..][4] = {elim col j, diag block offset, row offset, 0}
   OKIN_S_LEV_COL_PTR,    // [NLEV+1]
   OKIN_S_LEV_COL,        // elimination columns of each level
   OKIN_S_FW_PTR,         // [NF+1]
@@ -153,6 +155,7 @@ enum okin_isec {
   OKIN_S_SHIM,           // [NSHIM][OKIN_SHIM_STRIDE]
   OKIN_S_SHIM_PTS,       // point lists referenced by SHIM (upright attachments, rocker group)
   OKIN_S_DROW,           // [NDROW][4] = {p0 | p1 << 16, cst_off | rg_off << 16, row, 0}: plain distance rows
+  OKIN_S_DIAG_OFF,       // [NF] shared-memory offset of the diagonal block of elimination column j
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000
