@@ -299,7 +299,7 @@ def run_cuda(args) -> None:
     import psutil
     avail = psutil.virtual_memory().available
     bytes_per_inst_out = S * nout3 * 8 + S * 12 + 8
-    e2e_inst = int(min(n_inst, max(4096, min(12e9, 0.2 * avail / max(world, 1)) // bytes_per_inst_out)))
+    e2e_inst = int(min(n_inst, max(4096, min(30e9, 0.25 * avail / max(world, 1)) // bytes_per_inst_out)))
     h_hp = torch.empty((e2e_inst, nin3), dtype=torch.float64, pin_memory=True)
     h_hp.copy_(hp[:e2e_inst].cpu())
     h_tv = torch.tensor(solver.values, dtype=torch.float64).contiguous()

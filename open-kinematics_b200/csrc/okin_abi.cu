@@ -21,6 +21,8 @@
 #define OKIN_MAX_THREADS 512   // 16 warps: the most one CTA may hold (register cap 128 per thread)
 #define OKIN_REGS_PER_THREAD 128
 #define OKIN_MAX_DEVICES 16
+#define OKIN_PIPE_SLOTS 3        // streams / workspace slots of the host-buffer pipeline
+#define OKIN_PIPE_CHUNK 32768   // instances per pipelined chunk
 
 namespace {
 
@@ -51,7 +53,7 @@ struct DeviceCopy {
   // grow-only workspace for the host-buffer entry point
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t streams[OKIN_PIPE_SLOTS] = {};
 };
 
 }  // namespace
@@ -157,7 +159,8 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
     OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.ctas_per_sm, okin_sweep_kernel, best_w * 32,
                                                             d.smem_bytes));
     if (d.ctas_per_sm < 1) return fail(OKIN_ERR_CUDA, "kernel does not fit on an SM");
-    OKIN_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    for (int k = 0; k < OKIN_PIPE_SLOTS; ++k)
+      OKIN_CUDA(cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking));
     d.ready = true;
   }
   *out = &d;
@@ -255,7 +258,8 @@ int okin_topology_destroy(okin_topology* t) {
     cudaFree(d.ib);
     cudaFree(d.fb);
     if (d.ws) cudaFree(d.ws);
-    if (d.stream) cudaStreamDestroy(d.stream);
+    for (int k = 0; k < OKIN_PIPE_SLOTS; ++k)
+      if (d.streams[k]) cudaStreamDestroy(d.streams[k]);
   }
   delete t;
   return OKIN_OK;
@@ -334,85 +338,81 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
   const size_t nt = h[OKIN_H_NT], n = 3 * (size_t)h[OKIN_H_NF];
   const size_t S = (size_t)n_steps;
 
-  struct Shard {
-    DeviceCopy* d;
-    int device;
-    int64_t begin, count;
-    double *hp, *par, *tv, *pos, *maxres, *tan, *met, *dsn;
-    int32_t *status, *failed, *iters;
-  };
-  std::vector<Shard> shards;
-  // Contiguous instance ranges [k*N/G, (k+1)*N/G): the host-side "gather" is the D2H copies.
+  // Contiguous instance ranges [k*N/G, (k+1)*N/G) per device: the host-side "gather" is the D2H
+  // copies.  Inside a device the range is cut into chunks that rotate over OKIN_PIPE_SLOTS streams,
+  // so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k.
+  const size_t nm = (size_t)h[OKIN_H_NM], npar = (size_t)h[OKIN_H_NPARAM];
+  auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t chunk = (size_t)std::min<int64_t>(std::max<int64_t>(n_instances, 1), OKIN_PIPE_CHUNK);
+  const size_t b_hp = align(chunk * nin3 * 8), b_tv = align(std::max<size_t>(nt * S, 1) * 8);
+  const size_t b_pos = positions_out ? align(chunk * S * nout3 * 8) : 0;
+  const size_t b_mr = max_residual_out ? align(chunk * S * 8) : 0;
+  const size_t b_tan = tangents_out ? align(chunk * S * nt * n * 8) : 0;
+  const size_t b_met = (metrics_out && nm) ? align(chunk * S * nm * 8) : 0;
+  const size_t b_par = (params && npar) ? align(chunk * npar * 8) : 0;
+  const size_t b_dsn = design_out ? align(chunk * nout3 * 8) : 0;
+  const size_t b_it = iters_out ? align(chunk * S * 4) : 0;
+  const size_t b_st = align(chunk * 4);
+  const size_t slot_bytes = b_hp + b_tv + b_pos + b_mr + b_tan + b_met + b_par + b_dsn + b_it + 2 * b_st;
+
+  std::vector<std::pair<int, DeviceCopy*>> used;
   for (int k = 0; k < n_devices; ++k) {
-    Shard s{};
-    s.device = device_ids[k];
-    okin_shard_range(n_instances, k, n_devices, &s.begin, &s.count);
-    if (s.count == 0) continue;
-    rc = ensure_device(t, s.device, &s.d);
+    int64_t begin = 0, count = 0;
+    okin_shard_range(n_instances, k, n_devices, &begin, &count);
+    if (count == 0) continue;
+    DeviceCopy* d = nullptr;
+    rc = ensure_device(t, device_ids[k], &d);
     if (rc) return rc;
-    shards.push_back(s);
-  }
-  // enqueue everything asynchronously on every device, then wait
-  for (Shard& s : shards) {
-    OKIN_CUDA(cudaSetDevice(s.device));
-    const size_t c = (size_t)s.count;
-    auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    const size_t b_hp = align(c * nin3 * 8), b_tv = align(std::max<size_t>(nt * S, 1) * 8);
-    const size_t b_pos = positions_out ? align(c * S * nout3 * 8) : 0;
-    const size_t b_mr = max_residual_out ? align(c * S * 8) : 0;
-    const size_t b_tan = tangents_out ? align(c * S * nt * n * 8) : 0;
-    const size_t nm = (size_t)h[OKIN_H_NM];
-    const size_t b_met = (metrics_out && nm) ? align(c * S * nm * 8) : 0;
-    const size_t npar = (size_t)h[OKIN_H_NPARAM];
-    const size_t b_par = (params && npar) ? align(c * npar * 8) : 0;
-    const size_t b_dsn = design_out ? align(c * nout3 * 8) : 0;
-    const size_t b_it = iters_out ? align(c * S * 4) : 0;
-    const size_t b_st = align(c * 4);
-    const size_t total = b_hp + b_tv + b_pos + b_mr + b_tan + b_met + b_par + b_dsn + b_it + 2 * b_st;
-    if (total > s.d->ws_bytes) {
-      if (s.d->ws) OKIN_CUDA(cudaFree(s.d->ws));
-      s.d->ws = nullptr;
-      s.d->ws_bytes = 0;
-      OKIN_CUDA(cudaMalloc(&s.d->ws, total));
-      s.d->ws_bytes = total;
+    OKIN_CUDA(cudaSetDevice(device_ids[k]));
+    used.push_back({device_ids[k], d});
+    const int slots = (int)std::min<int64_t>(OKIN_PIPE_SLOTS, (count + (int64_t)chunk - 1) / (int64_t)chunk);
+    if (slot_bytes * slots > d->ws_bytes) {
+      if (d->ws) OKIN_CUDA(cudaFree(d->ws));
+      d->ws = nullptr;
+      d->ws_bytes = 0;
+      OKIN_CUDA(cudaMalloc(&d->ws, slot_bytes * slots));
+      d->ws_bytes = slot_bytes * slots;
     }
-    char* p = (char*)s.d->ws;
-    s.hp = (double*)p; p += b_hp;
-    s.tv = (double*)p; p += b_tv;
-    s.pos = positions_out ? (double*)p : nullptr; p += b_pos;
-    s.maxres = max_residual_out ? (double*)p : nullptr; p += b_mr;
-    s.tan = tangents_out ? (double*)p : nullptr; p += b_tan;
-    s.met = b_met ? (double*)p : nullptr; p += b_met;
-    s.par = b_par ? (double*)p : nullptr; p += b_par;
-    s.dsn = b_dsn ? (double*)p : nullptr; p += b_dsn;
-    s.iters = iters_out ? (int32_t*)p : nullptr; p += b_it;
-    s.status = (int32_t*)p; p += b_st;
-    s.failed = (int32_t*)p;
-    cudaStream_t st = s.d->stream;
-    OKIN_CUDA(cudaMemcpyAsync(s.hp, hardpoints + (size_t)s.begin * nin3, c * nin3 * 8, cudaMemcpyHostToDevice, st));
-    if (s.par)
-      OKIN_CUDA(cudaMemcpyAsync(s.par, params + (size_t)s.begin * npar, c * npar * 8, cudaMemcpyHostToDevice, st));
-    if (nt * S) OKIN_CUDA(cudaMemcpyAsync(s.tv, target_values, nt * S * 8, cudaMemcpyHostToDevice, st));
-    rc = launch(t, s.d, cfg, st, s.count, n_steps, s.hp, s.par, s.tv, s.pos, s.status, s.failed, s.iters, s.maxres,
-                s.tan, s.met, s.dsn);
-    if (rc) return rc;
-    const size_t b0 = (size_t)s.begin;
-    if (positions_out)
-      OKIN_CUDA(cudaMemcpyAsync(positions_out + b0 * S * nout3, s.pos, c * S * nout3 * 8, cudaMemcpyDeviceToHost, st));
-    if (max_residual_out)
-      OKIN_CUDA(cudaMemcpyAsync(max_residual_out + b0 * S, s.maxres, c * S * 8, cudaMemcpyDeviceToHost, st));
-    if (tangents_out)
-      OKIN_CUDA(cudaMemcpyAsync(tangents_out + b0 * S * nt * n, s.tan, c * S * nt * n * 8, cudaMemcpyDeviceToHost, st));
-    if (s.dsn) OKIN_CUDA(cudaMemcpyAsync(design_out + b0 * nout3, s.dsn, c * nout3 * 8, cudaMemcpyDeviceToHost, st));
-    if (s.met)
-      OKIN_CUDA(cudaMemcpyAsync(metrics_out + b0 * S * nm, s.met, c * S * nm * 8, cudaMemcpyDeviceToHost, st));
-    if (iters_out) OKIN_CUDA(cudaMemcpyAsync(iters_out + b0 * S, s.iters, c * S * 4, cudaMemcpyDeviceToHost, st));
-    OKIN_CUDA(cudaMemcpyAsync(status_out + b0, s.status, c * 4, cudaMemcpyDeviceToHost, st));
-    OKIN_CUDA(cudaMemcpyAsync(failed_step_out + b0, s.failed, c * 4, cudaMemcpyDeviceToHost, st));
+    int64_t done = 0;
+    for (int ck = 0; done < count; ++ck, done += (int64_t)chunk) {
+      const int slot = ck % slots;
+      const size_t c = (size_t)std::min<int64_t>((int64_t)chunk, count - done);
+      const size_t b0 = (size_t)(begin + done);
+      cudaStream_t st = d->streams[slot];
+      char* p = (char*)d->ws + slot_bytes * slot;
+      double* w_hp = (double*)p; p += b_hp;
+      double* w_tv = (double*)p; p += b_tv;
+      double* w_pos = b_pos ? (double*)p : nullptr; p += b_pos;
+      double* w_mr = b_mr ? (double*)p : nullptr; p += b_mr;
+      double* w_tan = b_tan ? (double*)p : nullptr; p += b_tan;
+      double* w_met = b_met ? (double*)p : nullptr; p += b_met;
+      double* w_par = b_par ? (double*)p : nullptr; p += b_par;
+      double* w_dsn = b_dsn ? (double*)p : nullptr; p += b_dsn;
+      int32_t* w_it = b_it ? (int32_t*)p : nullptr; p += b_it;
+      int32_t* w_st = (int32_t*)p; p += b_st;
+      int32_t* w_fs = (int32_t*)p;
+      OKIN_CUDA(cudaMemcpyAsync(w_hp, hardpoints + b0 * nin3, c * nin3 * 8, cudaMemcpyHostToDevice, st));
+      if (w_par) OKIN_CUDA(cudaMemcpyAsync(w_par, params + b0 * npar, c * npar * 8, cudaMemcpyHostToDevice, st));
+      if (nt * S && ck < slots)
+        OKIN_CUDA(cudaMemcpyAsync(w_tv, target_values, nt * S * 8, cudaMemcpyHostToDevice, st));
+      rc = launch(t, d, cfg, st, (int64_t)c, n_steps, w_hp, w_par, w_tv, w_pos, w_st, w_fs, w_it, w_mr, w_tan, w_met,
+                  w_dsn);
+      if (rc) return rc;
+      if (w_pos)
+        OKIN_CUDA(cudaMemcpyAsync(positions_out + b0 * S * nout3, w_pos, c * S * nout3 * 8, cudaMemcpyDeviceToHost, st));
+      if (w_mr) OKIN_CUDA(cudaMemcpyAsync(max_residual_out + b0 * S, w_mr, c * S * 8, cudaMemcpyDeviceToHost, st));
+      if (w_tan)
+        OKIN_CUDA(cudaMemcpyAsync(tangents_out + b0 * S * nt * n, w_tan, c * S * nt * n * 8, cudaMemcpyDeviceToHost, st));
+      if (w_dsn) OKIN_CUDA(cudaMemcpyAsync(design_out + b0 * nout3, w_dsn, c * nout3 * 8, cudaMemcpyDeviceToHost, st));
+      if (w_met) OKIN_CUDA(cudaMemcpyAsync(metrics_out + b0 * S * nm, w_met, c * S * nm * 8, cudaMemcpyDeviceToHost, st));
+      if (w_it) OKIN_CUDA(cudaMemcpyAsync(iters_out + b0 * S, w_it, c * S * 4, cudaMemcpyDeviceToHost, st));
+      OKIN_CUDA(cudaMemcpyAsync(status_out + b0, w_st, c * 4, cudaMemcpyDeviceToHost, st));
+      OKIN_CUDA(cudaMemcpyAsync(failed_step_out + b0, w_fs, c * 4, cudaMemcpyDeviceToHost, st));
+    }
   }
-  for (Shard& s : shards) {
-    OKIN_CUDA(cudaSetDevice(s.device));
-    OKIN_CUDA(cudaStreamSynchronize(s.d->stream));
+  for (auto& u : used) {
+    OKIN_CUDA(cudaSetDevice(u.first));
+    for (int k = 0; k < OKIN_PIPE_SLOTS; ++k) OKIN_CUDA(cudaStreamSynchronize(u.second->streams[k]));
   }
   return OKIN_OK;
 }
