@@ -1,8 +1,9 @@
 // C ABI (include/okin.h) and the sm_100a kernels behind it.
 //
-// Kernel mapping: one warp per suspension instance, OKIN_WARPS_PER_CTA instances per CTA, each
-// warp working in its own slice of dynamic shared memory; the grid is persistent (a multiple of
-// the SM count times the resident CTAs per SM) and strides over the instance range.  The work
+// Kernel mapping: one warp per suspension instance, W instances per CTA (W chosen per topology by
+// ensure_device), each warp working in its own slice of dynamic shared memory next to one shared
+// copy of the topology tables; the grid is persistent (SM count x resident CTAs per SM) and
+// strides over the instance range.  The work
 // is fp64 FMA/issue bound, tens of unknowns per system, so tensor cores
 // and TMA have nothing to act on; the only global traffic is the coalesced instance-major
 // hardpoint read and state write.
@@ -89,7 +90,14 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
   double* sm = okin_smem + table_doubles + (size_t)warp * hdr[OKIN_H_SMEM_DOUBLES];
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
   const long long stride = (long long)gridDim.x * warps_per_cta;
-  for (long long i = (long long)blockIdx.x * warps_per_cta + warp; i < n_instances; i += stride) {
+  // The trip count is uniform over the CTA and every round starts with a CTA barrier: the warps
+  // of a CTA run the same code region at the same time, which keeps the (large) interpreter in
+  // the instruction cache.  Without it the warps of a long-lived persistent CTA drift apart and
+  // throughput drops ~10 % between a 2 k-instance and a 1 M-instance launch (measured).
+  for (long long base = (long long)blockIdx.x * warps_per_cta; base < n_instances; base += stride) {
+    __syncthreads();
+    const long long i = base + warp;
+    if (i >= n_instances) continue;
     OkinOutputs out;
     out.positions = positions ? positions + (size_t)i * n_steps * 3 * nout : nullptr;
     out.iters = iters ? iters + (size_t)i * n_steps : nullptr;

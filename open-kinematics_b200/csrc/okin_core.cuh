@@ -37,6 +37,7 @@
 #define OKIN_PHASE_BEGIN { const int lane = (int)(threadIdx.x & 31u);
 #define OKIN_PHASE_END } __syncwarp();
 #define OKIN_LDG(p) (*(p))   // int32 tables live in shared memory, double constants in global
+
 #else
 #define OKIN_PHASE_BEGIN for (int lane = 0; lane < 32; ++lane) {
 #define OKIN_PHASE_END }
