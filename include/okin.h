@@ -83,10 +83,12 @@ typedef struct okin_solver_cfg {
                             applied, has max|dx| <= step_tol; default 1e-6 (typical size 1e-9) */
   double coarse_tol;     /* mm; an undamped Gauss-Newton step this small triggers the chord step;
                             default 1e-3 */
+  double fine_tol;       /* mm; an undamped Gauss-Newton step this small ends the iteration without the
+                            chord step (error left ~ curvature x fine_tol^2); default 2e-5 */
   double residual_tol;   /* default 1e-3 */
   double mu_init;        /* first Marquardt damping after a rejected step; default 1e-3 */
   int32_t max_iter;      /* factorisations per step; default 50 */
-  int32_t use_predictor; /* 0 warm start only, 1 first-order tangent predictor, 2 second order (default) */
+  int32_t use_predictor; /* continuation predictor order 0..3 (Adams-Bashforth on the tangents); default 3 */
 } okin_solver_cfg;
 
 typedef struct okin_topology_info {

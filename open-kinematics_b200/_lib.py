@@ -31,7 +31,8 @@ class TopologyDesc(ctypes.Structure):
 
 
 class SolverCfg(ctypes.Structure):
-    _fields_ = [("step_tol", ctypes.c_double), ("coarse_tol", ctypes.c_double), ("residual_tol", ctypes.c_double),
+    _fields_ = [("step_tol", ctypes.c_double), ("coarse_tol", ctypes.c_double), ("fine_tol", ctypes.c_double),
+                ("residual_tol", ctypes.c_double),
                 ("mu_init", ctypes.c_double),
                 ("max_iter", ctypes.c_int32), ("use_predictor", ctypes.c_int32)]
 

@@ -526,7 +526,8 @@ def compile_topology(
     # One task per block *row* (3 entries): acc[c] -= a . B[c][:] for every earlier column K,
     # a = row r of L_iK, B = L_jK.  The right-hand side of the step equation is carried as one
     # extra block-row of the factor (a = y_K), which makes the forward substitution part of the
-    # factorisation.  Offsets are relative to the instance's shared-memory base.
+    # factorisation; the tangent right-hand sides ride along the same way.  Offsets are relative
+    # to the instance's shared-memory base.
     cols_with = [[] for _ in range(NF)]        # cols_with[j] = K < j with L_jK != 0
     for k in range(NF):
         for i in struct[k]:
@@ -547,14 +548,16 @@ def compile_topology(
                         upd_con.append(((LB, boff(i, k) + 3 * r), (LB, boff(j, k))))
                     upd_ptr.append(len(upd_con))
             if cols_with[j]:
-                upd_dst.append((VEC, 3 * j))
-                for k in cols_with[j]:
-                    upd_con.append(((VEC, 3 * k), (LB, boff(j, k))))
-                upd_ptr.append(len(upd_con))
+                for rhs in range(1 + len(targets)):     # carried right-hand sides: step + tangents
+                    upd_dst.append((VEC, rhs * 3 * NF + 3 * j))
+                    for k in cols_with[j]:
+                        upd_con.append(((VEC, rhs * 3 * NF + 3 * k), (LB, boff(j, k))))
+                    upd_ptr.append(len(upd_con))
             for i in struct[j]:
                 for r in range(3):
-                    scl.append([j, (LB, boff(j, j)), (LB, boff(i, j) + 3 * r), 0])
-            scl.append([j, (LB, boff(j, j)), (VEC, 3 * j), 0])
+                    scl.append(((LB, boff(j, j)), (LB, boff(i, j) + 3 * r)))
+            for rhs in range(1 + len(targets)):
+                scl.append(((LB, boff(j, j)), (VEC, rhs * 3 * NF + 3 * j)))
         lev_upd.append(len(upd_dst))
         lev_scl.append(len(scl))
 
@@ -588,8 +591,9 @@ def compile_topology(
             raise ValueError(f"Output point {k!r} is not part of the model")
 
     # ---- fast distance rows: {p0 | p1 << 16, cst_off | rg_off << 16, row index}
-    drows = [[row.points[0] | (row.points[1] << 16), row.cst_off | (row.rg_off << 16), i, 0]
-             for i, row in enumerate(rows) if row.fast]
+    fast_rows = [(i, row) for i, row in enumerate(rows) if row.fast]
+    drows = ([row.points[0] | (row.points[1] << 16) for _, row in fast_rows]
+             + [row.cst_off | (row.rg_off << 16) for _, row in fast_rows] + [i for i, _ in fast_rows])
 
     # ---- evaluation order: rows of one family are adjacent so that a 32-row round of the
     # evaluation phase runs (mostly) one code path
@@ -610,7 +614,7 @@ def compile_topology(
         "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
         "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)), "OKIN_H_OFF_LB": take(9 * NB),
         "OKIN_H_OFF_VEC": take((1 + NT) * N),
-        "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)), "OKIN_H_OFF_PPREV": take(N),
+        "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)), "OKIN_H_OFF_PPREV": take(N), "OKIN_H_OFF_PPREV2": take(N),
     }
     if off >= 65536:
         raise ValueError("Per-instance state exceeds the 16-bit shared-memory offset range")
@@ -622,7 +626,7 @@ def compile_topology(
     diag_off = [sm((LB, boff(j, j))) for j in range(NF)]
     upd_dst = [sm(d) for d in upd_dst]
     upd_con = [(sm(a) << 16) | sm(b) for a, b in upd_con]
-    scl = [[j, sm(d), (-1 if r == -1 else sm(r)), z] for j, d, r, z in scl]
+    scl = [sm(d) | (sm(r) << 16) for d, r in scl]
     fw_con = [(sm(b) << 16) | v for b, v in fw_con]
     bw_con = [(sm(b) << 16) | v for b, v in bw_con]
 
@@ -721,7 +725,7 @@ def compile_topology(
         "OKIN_H_TROW0": trow0, "OKIN_H_SMEM_DOUBLES": off, "OKIN_H_NM": len(metric_names),
         "OKIN_H_NMC": len(mcorners), "OKIN_H_NMOP": len(mops), "OKIN_H_NMAXLE": len(maxle), "OKIN_H_NDSN": ndsn,
         "OKIN_H_NSHIM": len(shim_recs), "OKIN_H_NPARAM": len(param_default),
-        "OKIN_H_NDROW": len(drows), "OKIN_H_NGROW": len(row_order),
+        "OKIN_H_NDROW": len(fast_rows), "OKIN_H_NGROW": len(row_order),
         **layout,
     }
     for name, value in counts.items():
@@ -732,7 +736,7 @@ def compile_topology(
         "n_points": P, "n_free": NF, "n_unknowns": N, "n_rows": NROW, "n_report_rows": NREP, "n_targets": NT,
         "n_blocks": NB, "n_levels": NLEV, "fill_blocks": NB - NF - sum(len(a) for a in adjacency) // 2,
         "asm_fma": 9 * len(asm_con), "g_fma": 3 * len(g_con), "update_fma": 9 * len(upd_con),
-        "scale_tasks": len(scl), "solve_fma": 9 * (len(fw_con) + len(bw_con)) + 12 * NF,
+        "scale_tasks": len(scl) + NF, "solve_fma": 9 * (len(fw_con) + len(bw_con)) + 12 * NF,
         "smem_doubles": off, "iblob_words": int(iblob.size), "dense_lu_flops": dense_flops,
     }
     return TopologyProgram(

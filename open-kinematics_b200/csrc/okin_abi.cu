@@ -179,7 +179,8 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
            int32_t n_steps, const double* hp, const double* par, const double* tv, double* pos, int32_t* status,
            int32_t* failed, int32_t* iters, double* maxres, double* tangents, double* metrics, double* design) {
   if (n_instances == 0) return OKIN_OK;
-  OkinSolverCfg c{cfg->step_tol, cfg->coarse_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter, cfg->use_predictor};
+  OkinSolverCfg c{cfg->step_tol, cfg->coarse_tol, cfg->fine_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter,
+                  cfg->use_predictor};
   const int w = d->warps_per_cta;
   const int64_t needed = (n_instances + w - 1) / w;
   const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
@@ -227,10 +228,11 @@ int okin_default_cfg(okin_solver_cfg* out) {
   if (!out) return fail(OKIN_ERR_USAGE, "null out");
   out->step_tol = 1e-6;
   out->coarse_tol = 1e-3;
+  out->fine_tol = 2e-5;
   out->residual_tol = 1e-3;
   out->mu_init = 1e-3;
   out->max_iter = 50;
-  out->use_predictor = 2;
+  out->use_predictor = 3;
   return OKIN_OK;
 }
 

@@ -82,10 +82,12 @@ struct OkinProgram {
 struct OkinSolverCfg {
   double step_tol;      // converged when the verification (chord) step has max|dx| <= step_tol (mm)
   double coarse_tol;    // a Gauss-Newton step with max|dx| <= coarse_tol is followed by the chord step
+  double fine_tol;      // a Gauss-Newton step with max|dx| <= fine_tol ends the iteration unverified
+                        // (the error left is second order in it)
   double residual_tol;  // accept a state when max|r| <= residual_tol   (reference constants.py:20)
   double mu_init;       // first Marquardt damping factor after a rejected Gauss-Newton step
   int32_t max_iter;     // factorisations per step before "not converged"
-  int32_t use_predictor;  // 0: warm start only; 1: first-order tangent predictor; 2: second order
+  int32_t use_predictor;  // continuation predictor order: 0 warm start only, 1..3 (Adams-Bashforth on the tangents)
 };
 
 OKIN_HD const int32_t* okin_sec(const OkinProgram& pr, int s) { return pr.ib + pr.hdr[OKIN_H_SEC0 + 2 * s]; }
@@ -483,15 +485,14 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   // Fast path: plain distance rows (most of every shipped topology).  r = sqrt(s + eps^2) - eps - L,
   // u = (p2 - p1)/sqrt(s + eps^2) is the whole gradient (dR/dp2 = u, dR/dp1 = -u).
   for (int slot = lane; slot < ndrow; slot += 32) {
-    const int32_t* rec = drow + 4 * slot;
-    const uint32_t pp = (uint32_t)OKIN_LDG(rec + 0), oo = (uint32_t)OKIN_LDG(rec + 1);
+    const uint32_t pp = (uint32_t)OKIN_LDG(drow + slot), oo = (uint32_t)OKIN_LDG(drow + ndrow + slot);
     const double* a = pos + 3 * (pp & 0xffffu);
     const double* b = pos + 3 * (pp >> 16);
     const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
     const double s2 = dx * dx + dy * dy + dz * dz + OKIN_EPS_SQ;
     const double inv = OKIN_RSQRT(s2);
     const double res = s2 * inv - OKIN_EPS - cst[oo & 0xffffu];
-    r[OKIN_LDG(rec + 2)] = res;
+    r[OKIN_LDG(drow + 2 * ndrow + slot)] = res;
     const double ar = fabs(res);
     mx = (ar > mx || ar != ar) ? ar : mx;
     sq += res * res;
@@ -692,8 +693,8 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
     const int sb = OKIN_LDG(lev_scl + lv), se = OKIN_LDG(lev_scl + lv + 1);
     OKIN_PHASE_BEGIN
     for (int t = sb + lane; t < se; t += 32) {
-      const int32_t* rec = scl + 4 * t;
-      const int doff = OKIN_LDG(rec + 1), roff = OKIN_LDG(rec + 2);
+      const uint32_t w = (uint32_t)OKIN_LDG(scl + t);
+      const int doff = (int)(w & 0xffffu), roff = (int)(w >> 16);
       double f[9];
       okin_chol3(sm + doff, f);
       double* b = sm + roff;
@@ -825,23 +826,30 @@ OKIN_FN double okin_vec_max(const OkinProgram& pr, double* sm, int which) {
   return okin_red_max(red);
 }
 
-// Continuation predictor: x += p + (second ? (p - p_prev)/2 : 0), p = sum_j V_j dt_j, where V_j
-// are the tangents of the previous state.  p is kept for the next step's curvature term.
+// Continuation predictor on the solution path x(t): p_k = sum_j V_j(t_k) dt_j is h x'(t_k) for
+// uniform target increments, and x(t_{k+1}) - x(t_k) is extrapolated Adams-Bashforth style:
+//   order 1: p_k     order 2: p_k + (p_k - p_{k-1})/2     order 3: (23 p_k - 16 p_{k-1} + 5 p_{k-2})/12
+// V_j are the tangents of the previous state; p_{k-1}, p_{k-2} are kept in shared memory.
 template <typename Dummy = void>
-OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, bool second) {
+OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, int order) {
   const int32_t* hdr = pr.hdr;
   const int n = 3 * hdr[OKIN_H_NF];
   const int nt = hdr[OKIN_H_NT];
   const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* V = sm + hdr[OKIN_H_OFF_VEC] + n;
-  double* pprev = sm + hdr[OKIN_H_OFF_PPREV];
+  double* p1 = sm + hdr[OKIN_H_OFF_PPREV];
+  double* p2 = sm + hdr[OKIN_H_OFF_PPREV2];
   OKIN_PHASE_BEGIN
   for (int u = lane; u < n; u += 32) {
     double p = 0.0;
     for (int j = 0; j < nt; ++j) p = fma(V[j * n + u], dt[j], p);
-    const double step = second ? p + 0.5 * (p - pprev[u]) : p;
-    pprev[u] = p;
+    const double a = p1[u], b = p2[u];
+    double step = p;
+    if (order == 2) step = p + 0.5 * (p - a);
+    if (order >= 3) step = (23.0 * p - 16.0 * a + 5.0 * b) * (1.0 / 12.0);
+    p2[u] = a;
+    p1[u] = p;
     pos[3 * OKIN_LDG(ep + u / 3) + u % 3] += step;
   }
   OKIN_PHASE_END
@@ -873,14 +881,16 @@ OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
 
 // ---------------------------------------------------------------------------------------
 // One sweep step: Gauss-Newton on the pinned least-squares system, Marquardt damping only
-// after a step that fails to reduce ||r||^2, and a chord step that both verifies and finishes the
-// convergence.  Returns the number of residual evaluations (the SolverInfo.nfev analogue).
-// On return r[] holds the residuals one chord step (<= step_tol) before the final point, rg[]
-// and the factor storage the last undamped linearisation (used for the tangents).
+// after a step that fails to reduce ||r||^2.  A step below fine_tol ends the iteration (error
+// second order in it); a step below coarse_tol is verified and finished by a chord step.
+// Returns the number of residual evaluations (the SolverInfo.nfev analogue).  On return r[] holds
+// the residuals at (within step_tol of) the final point, vec[1..NT] the tangents of the last
+// undamped linearisation when *tangents_ready.
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
 OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tval, const OkinSolverCfg& cfg,
                             OkinState& st, bool* converged, bool* tangents_ready) {
+  const int nt = pr.hdr[OKIN_H_NT];
   int nfev = 0;
   *tangents_ready = false;
   st.mu = 0.0;
@@ -889,14 +899,17 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
   ++nfev;
   *converged = false;
   for (int it = 0; it < cfg.max_iter; ++it) {
+    // The factorisation carries the step right-hand side and the tangent right-hand sides as
+    // extra rows, so one backward pass yields the step and dq/dt_j of this linearisation.
     okin_assemble(pr, sm, st.mu, false);
+    okin_tangent_rhs(pr, sm);
     okin_factor(pr, sm, st);
     if (st.notpd) {  // rank-deficient normal matrix: damp and retry from the same point
       st.mu = st.mu > 0.0 ? st.mu * 10.0 : cfg.mu_init;
       if (st.mu > 1e12) break;
       continue;
     }
-    okin_solve(pr, sm, 0, 1, true);  // forward substitution was carried by the factorisation
+    okin_solve(pr, sm, 0, 1 + nt, true);
     const double hmax = okin_apply_step(pr, sm, 0, 1.0, true);
     if (!(hmax == hmax)) {  // NaN step: invalid geometry
       okin_restore(pr, sm);
@@ -904,22 +917,24 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
     }
     const double f2_old = st.f2;
     if (st.mu == 0.0 && hmax <= cfg.coarse_tol) {
-      // Small undamped step: verify with a chord step h2 = -(J0^T J0)^{-1} J0^T r(x1) that reuses
-      // the factor and the row gradients of the previous linearisation (residual-only
-      // evaluation, g-only assembly, one triangular solve).  Near the solution |h2| ~ k |h1|^2.
-      okin_eval_rows(pr, sm, tval, false, st);
+      okin_eval_rows(pr, sm, tval, false, st);   // residuals at the new point (also the reported max|r|)
       ++nfev;
-      // The tangent systems share the factor: solve them in the same pass (1 + NT right-hand sides).
+      *tangents_ready = true;                    // linearised within hmax of the solution
+      if (hmax <= cfg.fine_tol) {                // error left ~ k hmax^2: done without verification
+        *converged = true;
+        break;
+      }
+      // Verify with a chord step h2 = -(J0^T J0)^{-1} J0^T r(x1) that reuses the factor and the row
+      // gradients of the linearisation (g-only assembly, one forward/backward pass).
       okin_assemble(pr, sm, 0.0, true);
-      okin_tangent_rhs(pr, sm);
-      okin_solve(pr, sm, 0, 1 + pr.hdr[OKIN_H_NT], false);
+      okin_solve(pr, sm, 0, 1, false);
       const double h2 = okin_apply_step(pr, sm, 0, 1.0, true);
       if (h2 <= cfg.step_tol) {
         *converged = true;
-        *tangents_ready = true;
         break;
       }
       okin_restore(pr, sm);
+      *tangents_ready = false;
       // Not contracting fast enough: relinearise at the current point.
       okin_eval_rows(pr, sm, tval, true, st);
       ++nfev;
@@ -954,7 +969,6 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
   }
   return nfev;
 }
-
 
 // ---------------------------------------------------------------------------------------
 // Metrics (csrc/okin_metrics.cuh holds the response kernels and record layouts).
@@ -1295,7 +1309,8 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   int status = invalid ? OKIN_STATUS_INVALID_GEOMETRY : OKIN_STATUS_OK, failed = invalid ? 0 : -1;
   double tcur[OKIN_MAX_TARGETS], tprev[OKIN_MAX_TARGETS];
   for (int j = 0; j < OKIN_MAX_TARGETS; ++j) { tcur[j] = 0.0; tprev[j] = 0.0; }
-  bool have_tangent = false, have_pprev = false;
+  bool have_tangent = false;
+  int history = 0;
   double dtprev[OKIN_MAX_TARGETS];
   for (int j = 0; j < OKIN_MAX_TARGETS; ++j) dtprev[j] = 0.0;
 
@@ -1304,14 +1319,15 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       for (int j = 0; j < nt; ++j) { tprev[j] = tcur[j]; tcur[j] = OKIN_LDG(tvals + j * n_steps + s); }
       if (cfg.use_predictor && have_tangent) {
         double dt[OKIN_MAX_TARGETS];
-        bool same = have_pprev;
+        bool same = true;
         for (int j = 0; j < OKIN_MAX_TARGETS; ++j) {
           dt[j] = tcur[j] - tprev[j];
           if (fabs(dt[j] - dtprev[j]) > 1e-9 * (fabs(dt[j]) + fabs(dtprev[j]))) same = false;
           dtprev[j] = dt[j];
         }
-        okin_predict(pr, sm, dt, same && cfg.use_predictor > 1);
-        have_pprev = true;
+        history = same ? history + 1 : 1;   // consecutive predictor steps with the same increments
+        const int order = history < cfg.use_predictor ? history : cfg.use_predictor;
+        okin_predict(pr, sm, dt, order);
       }
       bool conv = false, tangents_ready = false;
       const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready);
@@ -1338,9 +1354,9 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
           okin_eval_rows(pr, sm, tcur, true, st);
           st.rmax = rmax;
           okin_assemble(pr, sm, 0.0, false);
-          okin_factor(pr, sm, st);
           okin_tangent_rhs(pr, sm);
-          okin_solve(pr, sm, 1, nt, false);
+          okin_factor(pr, sm, st);
+          okin_solve(pr, sm, 1, nt, true);
         }
         okin_derived_update(pr, sm, false);
         have_tangent = true;

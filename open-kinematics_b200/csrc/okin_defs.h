@@ -106,6 +106,7 @@ enum okin_hdr_slot {
   OKIN_H_NPARAM,   // per-instance scalar parameters (doubles)
   OKIN_H_NDROW,    // distance rows on the fast evaluation path
   OKIN_H_NGROW,    // rows on the generic evaluation path (ROW_ORDER entries)
+  OKIN_H_OFF_PPREV2,  // second predictor-history vector
   OKIN_H_SEC0 = 64,                      // room for 64 scalar slots,
   OKIN_H_FSEC0 = 64 + 2 * 64,            // 64 int32 sections
   OKIN_HDR_SIZE = 64 + 2 * 64 + 2 * 8    // and 8 double sections
@@ -132,7 +133,7 @@ enum okin_isec {
   OKIN_S_UPD_PTR,        // [n_upd+1]
   OKIN_S_UPD_CON,        // (offA << 16) | offB : acc[c] -= sum_t sm[offA+t]*sm[offB+3c+t]
   OKIN_S_LEV_SCL,        // [NLEV+1] ranges into SCL
-  OKIN_S_SCL,            // [..][4] = {elim col j, diag block offset, row offset, 0}
+  OKIN_S_SCL,            // [..] = diag block offset | row offset << 16 (shared-memory offsets)
   OKIN_S_LEV_COL_PTR,    // [NLEV+1]
   OKIN_S_LEV_COL,        // elimination columns of each level
   OKIN_S_FW_PTR,         // [NF+1]
@@ -154,7 +155,7 @@ enum okin_isec {
   OKIN_S_MAXLE,          // [NMAXLE][OKIN_MAXLE_STRIDE]
   OKIN_S_SHIM,           // [NSHIM][OKIN_SHIM_STRIDE]
   OKIN_S_SHIM_PTS,       // point lists referenced by SHIM (upright attachments, rocker group)
-  OKIN_S_DROW,           // [NDROW][4] = {p0 | p1 << 16, cst_off | rg_off << 16, row, 0}: plain distance rows
+  OKIN_S_DROW,           // [3][NDROW] = {p0 | p1 << 16}, {cst_off | rg_off << 16}, {row}: plain distance rows
   OKIN_S_DIAG_OFF,       // [NF] shared-memory offset of the diagonal block of elimination column j
   OKIN_S_COUNT
 };
@@ -176,7 +177,7 @@ enum okin_row_slot {
   OKIN_R_RULE,  // design-constant rule
   OKIN_R_S0, OKIN_R_S1, OKIN_R_S2, OKIN_R_S3, // slot map: -1 none, <OKIN_SLOT_DER direct eff index, else derived descriptor
   OKIN_R_AUX,   // target index for target rows
-  OKIN_ROW_STRIDE = 16
+  OKIN_ROW_STRIDE = 17   // odd: lanes reading the same field of consecutive rows hit distinct banks
 };
 #define OKIN_SLOT_DER 64
 

@@ -10,12 +10,12 @@
 extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const double* fb, long n_instances,
                               int n_steps, const double* hardpoints, const double* params, const double* tvals,
                               double step_tol,
-                              double coarse_tol, double residual_tol, double mu_init, int max_iter, int use_predictor,
+                              double coarse_tol, double fine_tol, double residual_tol, double mu_init, int max_iter, int use_predictor,
                               double* positions, int32_t* iters, double* max_residual, double* tangents,
                               double* metrics, double* design, int32_t* status, int32_t* failed_step) {
   if (hdr[OKIN_H_MAGIC] != OKIN_MAGIC) return -1;
   OkinProgram pr{hdr, ib, fb};
-  OkinSolverCfg cfg{step_tol, coarse_tol, residual_tol, mu_init, max_iter, use_predictor};
+  OkinSolverCfg cfg{step_tol, coarse_tol, fine_tol, residual_tol, mu_init, max_iter, use_predictor};
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
   std::vector<double> sm(hdr[OKIN_H_SMEM_DOUBLES]);
   for (long i = 0; i < n_instances; ++i) {

@@ -138,14 +138,14 @@ def emu_lib():
         lib.okin_emu_sweep.argtypes = (
             [ctypes.c_void_p] * 3 + [ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
-                                     ctypes.c_int, ctypes.c_int]
+                                     ctypes.c_double, ctypes.c_int, ctypes.c_int]
             + [ctypes.c_void_p] * 8)
         _EMU = lib
     return _EMU
 
 
 def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, step_tol=1e-6, coarse_tol=1e-3,
-              residual_tol=1e-3, mu_init=1e-3, max_iter=50, use_predictor=2, params=None) -> dict:
+              fine_tol=2e-5, residual_tol=1e-3, mu_init=1e-3, max_iter=50, use_predictor=3, params=None) -> dict:
     hp = np.ascontiguousarray(hardpoints, dtype=np.float64).reshape(-1, 3 * program.n_in)
     tv = np.ascontiguousarray(values, dtype=np.float64)
     n_inst, n_steps, nt, n = hp.shape[0], tv.shape[1], tv.shape[0], program.n_unknowns
@@ -161,7 +161,7 @@ def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, step_tol=1e-6
     rc = emu_lib().okin_emu_sweep(
         hdr.ctypes.data, program.iblob.ctypes.data, program.fblob.ctypes.data, n_inst, n_steps,
         hp.ctypes.data, None if par is None else par.ctypes.data, tv.ctypes.data, step_tol, coarse_tol,
-        residual_tol, mu_init, max_iter, use_predictor,
+        fine_tol, residual_tol, mu_init, max_iter, use_predictor,
         out["positions"].ctypes.data, out["iters"].ctypes.data, out["max_residual"].ctypes.data,
         out["tangents"].ctypes.data, out["metrics"].ctypes.data if program.metric_names else None,
         out["design"].ctypes.data, out["status"].ctypes.data, out["failed_step"].ctypes.data)
