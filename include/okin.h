@@ -84,7 +84,8 @@ typedef struct okin_solver_cfg {
   double coarse_tol;     /* mm; an undamped Gauss-Newton step this small triggers the chord step;
                             default 1e-3 */
   double fine_tol;       /* mm; an undamped Gauss-Newton step this small ends the iteration without the
-                            chord step (error left ~ curvature x fine_tol^2); default 2e-5 */
+                            chord step (error left ~ curvature x fine_tol^2, i.e. ~1e-10 mm for
+                            mm-scale linkages); default 1e-4 */
   double residual_tol;   /* default 1e-3 */
   double mu_init;        /* first Marquardt damping after a rejected step; default 1e-3 */
   int32_t max_iter;      /* factorisations per step; default 50 */

@@ -228,7 +228,7 @@ int okin_default_cfg(okin_solver_cfg* out) {
   if (!out) return fail(OKIN_ERR_USAGE, "null out");
   out->step_tol = 1e-6;
   out->coarse_tol = 1e-3;
-  out->fine_tol = 2e-5;
+  out->fine_tol = 1e-4;
   out->residual_tol = 1e-3;
   out->mu_init = 1e-3;
   out->max_iter = 50;

@@ -145,7 +145,7 @@ def emu_lib():
 
 
 def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, step_tol=1e-6, coarse_tol=1e-3,
-              fine_tol=2e-5, residual_tol=1e-3, mu_init=1e-3, max_iter=50, use_predictor=3, params=None) -> dict:
+              fine_tol=1e-4, residual_tol=1e-3, mu_init=1e-3, max_iter=50, use_predictor=3, params=None) -> dict:
     hp = np.ascontiguousarray(hardpoints, dtype=np.float64).reshape(-1, 3 * program.n_in)
     tv = np.ascontiguousarray(values, dtype=np.float64)
     n_inst, n_steps, nt, n = hp.shape[0], tv.shape[1], tv.shape[0], program.n_unknowns

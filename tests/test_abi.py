@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_usage_errors_do_not_need_a_device():
     lib = _lib.load()
     cfg = _lib.default_cfg()
-    assert cfg.step_tol == 1e-6 and cfg.coarse_tol == 1e-3 and cfg.fine_tol == 2e-5 and cfg.residual_tol == 1e-3 and cfg.max_iter == 50
+    assert cfg.step_tol == 1e-6 and cfg.coarse_tol == 1e-3 and cfg.fine_tol == 1e-4 and cfg.residual_tol == 1e-3 and cfg.max_iter == 50
     handle = ctypes.c_void_p()
     assert lib.okin_topology_create(None, ctypes.byref(handle)) == -1
     assert "null" in _lib.last_error()
