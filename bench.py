@@ -354,6 +354,11 @@ def run_cuda(args) -> None:
             traffic_src = tj["source"]
         except (OSError, KeyError):
             pass
+        executed = None
+        try:
+            executed = json.load(open(os.path.join(ROOT, "profiles", "fp64_flops.json")))["executed_fp64_flops_per_state"]
+        except (OSError, KeyError):
+            pass
         geo = topo.launch_geometry(n_inst, local)
         base = cpu_baseline(sample_instances=args.cpu_sample, processes=1)
         line = {
@@ -377,6 +382,7 @@ def run_cuda(args) -> None:
                 "traffic_source": traffic_src,
                 "peak_source": "okin_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic_flops_per_state": flops_state, "kernel_ms": k_ms,
+                "executed_flops_per_state_ncu": executed,
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                         "algorithmic_bytes_per_state": alg_bytes_state,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
