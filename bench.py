@@ -263,12 +263,15 @@ def run_cuda(args) -> None:
     iters = torch.empty((n_inst, S), device=dev, dtype=torch.int32)
     maxres = torch.empty((n_inst, S), device=dev, dtype=torch.float64)
 
+    d_io = _lib.BatchIO.of(hardpoints=hp.data_ptr(), target_values=tv.data_ptr(), positions=pos.data_ptr(),
+                           status=status.data_ptr(), failed_step=failed.data_ptr(), iters=iters.data_ptr(),
+                           max_residual=maxres.data_ptr())
+
     def launch():
         stream = torch.cuda.current_stream().cuda_stream
         _lib.check(lib.okin_solve_batch_device(
-            topo.handle, ctypes.byref(cfg), local, ctypes.c_void_p(stream), n_inst, S,
-            hp.data_ptr(), None, tv.data_ptr(), pos.data_ptr(), status.data_ptr(), failed.data_ptr(),
-            iters.data_ptr(), maxres.data_ptr(), None, None, None), "okin_solve_batch_device")
+            topo.handle, ctypes.byref(cfg), local, ctypes.c_void_p(stream), n_inst, S, ctypes.byref(d_io)),
+            "okin_solve_batch_device")
 
     def barrier():
         if world > 1:
@@ -310,11 +313,13 @@ def run_cuda(args) -> None:
     h_maxres = torch.empty((e2e_inst, S), dtype=torch.float64, pin_memory=True)
     devs = np.array([local], dtype=np.int32)
 
+    h_io = _lib.BatchIO.of(hardpoints=h_hp.data_ptr(), target_values=h_tv.data_ptr(), positions=h_pos.data_ptr(),
+                           status=h_status.data_ptr(), failed_step=h_failed.data_ptr(), iters=h_iters.data_ptr(),
+                           max_residual=h_maxres.data_ptr())
+
     def e2e_call():
-        _lib.check(lib.okin_solve_batch(
-            topo.handle, ctypes.byref(cfg), e2e_inst, S, h_hp.data_ptr(), None, h_tv.data_ptr(), devs.ctypes.data, 1,
-            h_pos.data_ptr(), h_status.data_ptr(), h_failed.data_ptr(), h_iters.data_ptr(), h_maxres.data_ptr(),
-            None, None, None), "okin_solve_batch")
+        _lib.check(lib.okin_solve_batch(topo.handle, ctypes.byref(cfg), e2e_inst, S, ctypes.byref(h_io),
+                                        devs.ctypes.data, 1), "okin_solve_batch")
 
     for _ in range(2):
         e2e_call()

@@ -35,6 +35,13 @@
  *   iters_out       [n_instances][n_steps]           residual evaluations (SolverInfo.nfev)
  *   max_residual_out[n_instances][n_steps]           max |r| at the solution (SolverInfo.max_residual)
  *   tangents_out    [n_instances][n_steps][n_targets][n_unknowns]  dq/dt_j, reference column order
+ *   velocities_out  [n_instances][n_steps][n_targets][n_out_points*3]  TangentField.velocities: first-order
+ *                                                    response of every output point (free, fixed = 0,
+ *                                                    derived) to each target (sensitivity.py:115-141)
+ *   tangent_health_out [n_instances][n_steps][2]     TangentSolveInfo (sensitivity.py:42-55):
+ *                                                    {smallest singular value, condition number} of the
+ *                                                    pinned Jacobian, by power / inverse iteration with
+ *                                                    the Cholesky factor (estimates from inside)
  *   metrics_out     [n_instances][n_steps][n_metrics]  state / mechanism / derivative metric columns in
  *                                                    the reference's flat export order; NaN where the
  *                                                    reference yields None
@@ -42,7 +49,8 @@
  *                                                    pre-solve and derived points
  *   status_out      [n_instances]                    OKIN_STATUS_*
  *   failed_step_out [n_instances]                    -1 or the first failed step
- * Any *_out pointer except status_out / failed_step_out may be NULL.
+ * The buffers of one call travel in an okin_batch_io; every output pointer except status /
+ * failed_step may be NULL (not wanted).
  */
 #ifndef OKIN_H
 #define OKIN_H
@@ -97,27 +105,39 @@ typedef struct okin_topology_info {
   int32_t smem_bytes_per_instance, n_levels, n_metrics, n_params;
 } okin_topology_info;
 
+/* Buffers of one batch call (layouts in the header comment).  Host pointers for okin_solve_batch,
+ * device pointers for okin_solve_batch_device.  Zero-initialise, then set what is wanted. */
+typedef struct okin_batch_io {
+  const double* hardpoints;     /* required */
+  const double* params;         /* optional */
+  const double* target_values;  /* required when n_targets * n_steps > 0 */
+  int32_t* status;              /* required */
+  int32_t* failed_step;         /* required */
+  double* positions;
+  int32_t* iters;
+  double* max_residual;
+  double* tangents;
+  double* velocities;
+  double* tangent_health;
+  double* metrics;
+  double* design;
+} okin_batch_io;
+
 int okin_device_count(int* out);
 int okin_default_cfg(okin_solver_cfg* out);
 int okin_topology_create(const okin_topology_desc* desc, okin_topology** out);
 int okin_topology_destroy(okin_topology* topo);
 int okin_topology_get_info(const okin_topology* topo, okin_topology_info* out);
 
-/* Host buffers; instance range sharded evenly over device_ids (NULL / 0 => device 0). */
+/* Host buffers; instance range sharded evenly over device_ids (NULL / 0 => device 0).  Returns
+ * after every output has landed in the caller's buffers. */
 int okin_solve_batch(okin_topology* topo, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
-                     const double* hardpoints, const double* params, const double* target_values,
-                     const int32_t* device_ids, int32_t n_devices, double* positions_out, int32_t* status_out,
-                     int32_t* failed_step_out, int32_t* iters_out, double* max_residual_out, double* tangents_out,
-                     double* metrics_out, double* design_out);
+                     const okin_batch_io* io, const int32_t* device_ids, int32_t n_devices);
 
 /* Device buffers on `device`; enqueues on `stream` (a cudaStream_t, may be NULL) and returns
  * without synchronising. */
 int okin_solve_batch_device(okin_topology* topo, const okin_solver_cfg* cfg, int32_t device, void* stream,
-                            int64_t n_instances, int32_t n_steps, const double* d_hardpoints,
-                            const double* d_params, const double* d_target_values, double* d_positions_out,
-                            int32_t* d_status_out, int32_t* d_failed_step_out, int32_t* d_iters_out,
-                            double* d_max_residual_out, double* d_tangents_out, double* d_metrics_out,
-                            double* d_design_out);
+                            int64_t n_instances, int32_t n_steps, const okin_batch_io* d_io);
 
 /* Instance range [begin, begin+count) that shard k of n_shards owns: [k*N/G, (k+1)*N/G).  The
  * same rule splits a host batch over device_ids and a torchrun job over ranks. */

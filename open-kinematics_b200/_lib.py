@@ -37,6 +37,27 @@ class SolverCfg(ctypes.Structure):
                 ("max_iter", ctypes.c_int32), ("use_predictor", ctypes.c_int32)]
 
 
+class BatchIO(ctypes.Structure):
+    """``okin_batch_io``: the buffers of one batch call (host or device addresses)."""
+
+    INPUTS = ("hardpoints", "params", "target_values")
+    OUTPUTS = ("status", "failed_step", "positions", "iters", "max_residual", "tangents", "velocities",
+               "tangent_health", "metrics", "design")
+    _fields_ = [(n, ctypes.c_void_p) for n in INPUTS + OUTPUTS]
+
+    @classmethod
+    def of(cls, **buffers) -> "BatchIO":
+        """Build from numpy arrays / integer addresses / None, by field name."""
+        io = cls()
+        for name, buf in buffers.items():
+            if name not in cls.INPUTS + cls.OUTPUTS:
+                raise KeyError(name)
+            if buf is None:
+                continue
+            setattr(io, name, buf.ctypes.data if isinstance(buf, np.ndarray) else int(buf))
+        return io
+
+
 class TopologyInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "n_points", "n_in_points", "n_out_points", "n_unknowns", "n_targets", "n_rows",
@@ -51,14 +72,11 @@ SIGNATURES = {
     "okin_topology_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "okin_topology_get_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(TopologyInfo)]),
     "okin_solve_batch": (ctypes.c_int, [
-        ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int64, ctypes.c_int32,
-        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
-        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-        ctypes.c_void_p, ctypes.c_void_p]),
+        ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(BatchIO),
+        ctypes.c_void_p, ctypes.c_int32]),
     "okin_solve_batch_device": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.POINTER(SolverCfg), ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
-        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+        ctypes.POINTER(BatchIO)]),
     "okin_shard_range": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "okin_launch_geometry": (ctypes.c_int, [
@@ -186,7 +204,8 @@ class DeviceTopology:
     # -- host buffers ------------------------------------------------------------------
     def solve_batch(self, hardpoints: np.ndarray, target_values: np.ndarray, cfg: SolverCfg | None = None,
                     devices=None, want_positions=True, want_tangents=False, want_metrics=False,
-                    want_design=False, params: np.ndarray | None = None) -> dict:
+                    want_design=False, params: np.ndarray | None = None, want_velocities=False,
+                    want_health=False) -> dict:
         """hardpoints [n_inst, n_in*3]; target_values [n_targets, n_steps]."""
         require_device()
         prog = self.program
@@ -213,6 +232,8 @@ class DeviceTopology:
             "iters": np.empty((n_inst, n_steps), np.int32),
             "max_residual": np.empty((n_inst, n_steps)),
             "tangents": np.empty((n_inst, n_steps, nt, prog.n_unknowns)) if want_tangents else None,
+            "velocities": np.empty((n_inst, n_steps, nt, prog.n_out, 3)) if want_velocities else None,
+            "tangent_health": np.empty((n_inst, n_steps, 2)) if want_health else None,
             "metrics": np.empty((n_inst, n_steps, len(prog.metric_names))) if want_metrics else None,
             "design": np.empty((n_inst, prog.n_out, 3)) if want_design else None,
         }
@@ -220,11 +241,7 @@ class DeviceTopology:
             raise ValueError("This topology was compiled without a metric program")
         dev = np.ascontiguousarray(devices if devices is not None else [0], dtype=np.int32)
 
-        def p(a):
-            return None if a is None else a.ctypes.data
-
-        check(load().okin_solve_batch(
-            self.handle, ctypes.byref(cfg), n_inst, n_steps, p(hp), p(par), p(tv), p(dev), dev.size,
-            p(out["positions"]), p(out["status"]), p(out["failed_step"]), p(out["iters"]),
-            p(out["max_residual"]), p(out["tangents"]), p(out["metrics"]), p(out["design"])), "okin_solve_batch")
+        io = BatchIO.of(hardpoints=hp, params=par, target_values=tv, **out)
+        check(load().okin_solve_batch(self.handle, ctypes.byref(cfg), n_inst, n_steps, ctypes.byref(io),
+                                      dev.ctypes.data, dev.size), "okin_solve_batch")
         return out

@@ -41,6 +41,7 @@ MF_FRONT, MF_REAR, MF_HAS_BIAS, MF_DRIVEN_HERE = 1, 2, 4, 8
 @dataclass
 class MetricProgram:
     names: list = field(default_factory=list)
+    locations: list = field(default_factory=list)    # per column: (Side | None, key without side suffix)
     corners: list = field(default_factory=list)
     mops: list = field(default_factory=list)
     axle: list = field(default_factory=list)
@@ -53,11 +54,14 @@ class _Builder:
         self.heads, self.pidx = heads, pidx
         self.prog = MetricProgram()
         self._dslot: dict = {}
+        self.side, self.suffix = None, ""
 
     def col(self, name: str) -> int:
         if name in self.prog.names:
             raise ValueError(f"Duplicate metric column: {name}")
         self.prog.names.append(name)
+        located = self.side is not None and name.endswith(self.suffix)
+        self.prog.locations.append((self.side, name[:-len(self.suffix)]) if located else (None, name))
         return len(self.prog.names) - 1
 
     def dslot(self, key) -> int:
@@ -184,6 +188,7 @@ def build_metric_program(suspension, heads, pidx) -> MetricProgram:
             return sum(1 << j for j, h in enumerate(heads) if local_target(h.point_id) == point)
 
         suffix = "_" + side.name.lower()
+        b.side, b.suffix = side, suffix
         _corner_block(b, axle.corners[side], lambda pid, side=side: PointRef(side, pid), suffix, candidates)
         if isinstance(axle.anti_roll, ArbUBar):   # per-corner row appended after the derivatives
             arm = PointRef(side, P.DROPLINK_U_BAR)
@@ -192,6 +197,7 @@ def build_metric_program(suspension, heads, pidx) -> MetricProgram:
                   b.col("arb_arm_angle" + suffix), d0=b.dslot(arm), consts=[1.0])
 
     # axle state metrics
+    b.side, b.suffix = None, ""
     L, R = Side.LEFT, Side.RIGHT
     out_base = len(b.prog.names)
     for name in AXLE_STATE_METRICS:

@@ -124,6 +124,7 @@ class TopologyProgram:
     target_points: list
     stats: dict
     metric_names: list = field(default_factory=list)
+    metric_locations: list = field(default_factory=list)
     param_names: list = field(default_factory=list)
     param_default: np.ndarray = field(default_factory=lambda: np.zeros(0))
 
@@ -743,6 +744,7 @@ def compile_topology(
         hdr=hdr, iblob=iblob, fblob=fblob, point_keys=point_keys, free_order=free_order, in_keys=in_keys,
         out_keys=out_keys, n_constraints=len(constraints), row_source=[r.source for r in rows],
         target_points=[t.point_id for t in targets], stats=stats, metric_names=metric_names,
+        metric_locations=list(mprog.locations) if mprog else [],
         param_names=param_names, param_default=np.asarray(param_default, dtype=np.float64),
     )
 

@@ -73,10 +73,8 @@ struct okin_topology {
 // (only the once-per-instance shim pre-solve spills at that cap).
 __global__ void __launch_bounds__(OKIN_MAX_THREADS, 1)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
-                  long long n_instances, int n_steps, const double* __restrict__ hardpoints,
-                  const double* __restrict__ params, const double* __restrict__ tvals, OkinSolverCfg cfg,
-                  double* positions, int32_t* iters, double* max_residual, double* tangents, double* metrics,
-                  double* design, int32_t* status, int32_t* failed_step, int n_iblob, int table_doubles) {
+                  long long n_instances, int n_steps, OkinSolverCfg cfg, okin_batch_io io, int n_iblob,
+                  int table_doubles) {
   extern __shared__ double okin_smem[];
   int32_t* shdr = reinterpret_cast<int32_t*>(okin_smem);
   int32_t* tab = shdr + OKIN_HDR_SIZE;
@@ -99,16 +97,19 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
     const long long i = base + warp;
     if (i >= n_instances) continue;
     OkinOutputs out;
-    out.positions = positions ? positions + (size_t)i * n_steps * 3 * nout : nullptr;
-    out.iters = iters ? iters + (size_t)i * n_steps : nullptr;
-    out.max_residual = max_residual ? max_residual + (size_t)i * n_steps : nullptr;
-    out.tangents = tangents ? tangents + (size_t)i * n_steps * nt * n : nullptr;
-    out.metrics = metrics ? metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
-    out.design = design ? design + (size_t)i * 3 * nout : nullptr;
-    out.status = status + i;
-    out.failed_step = failed_step + i;
-    okin_sweep(pr, sm, hardpoints + (size_t)i * 3 * nin,
-               params ? params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, tvals, n_steps, cfg, out);
+    out.positions = io.positions ? io.positions + (size_t)i * n_steps * 3 * nout : nullptr;
+    out.iters = io.iters ? io.iters + (size_t)i * n_steps : nullptr;
+    out.max_residual = io.max_residual ? io.max_residual + (size_t)i * n_steps : nullptr;
+    out.tangents = io.tangents ? io.tangents + (size_t)i * n_steps * nt * n : nullptr;
+    out.velocities = io.velocities ? io.velocities + (size_t)i * n_steps * nt * 3 * nout : nullptr;
+    out.health = io.tangent_health ? io.tangent_health + (size_t)i * n_steps * 2 : nullptr;
+    out.metrics = io.metrics ? io.metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
+    out.design = io.design ? io.design + (size_t)i * 3 * nout : nullptr;
+    out.status = io.status + i;
+    out.failed_step = io.failed_step + i;
+    okin_sweep(pr, sm, io.hardpoints + (size_t)i * 3 * nin,
+               io.params ? io.params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, io.target_values, n_steps, cfg,
+               out);
     __syncwarp();
   }
 }
@@ -176,8 +177,7 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
 }
 
 int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStream_t stream, int64_t n_instances,
-           int32_t n_steps, const double* hp, const double* par, const double* tv, double* pos, int32_t* status,
-           int32_t* failed, int32_t* iters, double* maxres, double* tangents, double* metrics, double* design) {
+           int32_t n_steps, const okin_batch_io& io) {
   if (n_instances == 0) return OKIN_OK;
   OkinSolverCfg c{cfg->step_tol, cfg->coarse_tol, cfg->fine_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter,
                   cfg->use_predictor};
@@ -186,15 +186,15 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
   const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
   const int grid = (int)std::min<int64_t>(needed, resident);
   okin_sweep_kernel<<<grid, w * 32, d->smem_bytes, stream>>>(
-      d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, hp, par, tv, c, pos, iters, maxres, tangents, metrics,
-      design, status, failed, (int)t->ib.size(), d->table_doubles);
+      d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, c, io, (int)t->ib.size(), d->table_doubles);
   OKIN_CUDA(cudaGetLastError());
   return OKIN_OK;
 }
 
 int check_common(const okin_topology* t, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
-                 const void* hp, const void* tv, const void* status, const void* failed) {
-  if (!t || !cfg) return fail(OKIN_ERR_USAGE, "null topology or config");
+                 const okin_batch_io* io) {
+  if (!t || !cfg || !io) return fail(OKIN_ERR_USAGE, "null topology, config or io");
+  const void *hp = io->hardpoints, *tv = io->target_values, *status = io->status, *failed = io->failed_step;
   if (n_instances < 0 || n_steps < 0) return fail(OKIN_ERR_USAGE, "negative size");
   if (n_instances > 0 && (!hp || !status || !failed)) return fail(OKIN_ERR_USAGE, "null required buffer");
   if (n_steps > 0 && t->hdr[OKIN_H_NT] > 0 && !tv) return fail(OKIN_ERR_USAGE, "null target_values");
@@ -306,20 +306,14 @@ int okin_launch_geometry(okin_topology* t, int32_t device, int64_t n_instances, 
 }
 
 int okin_solve_batch_device(okin_topology* t, const okin_solver_cfg* cfg, int32_t device, void* stream,
-                            int64_t n_instances, int32_t n_steps, const double* d_hardpoints,
-                            const double* d_params, const double* d_target_values, double* d_positions_out,
-                            int32_t* d_status_out, int32_t* d_failed_step_out, int32_t* d_iters_out,
-                            double* d_max_residual_out, double* d_tangents_out, double* d_metrics_out,
-                            double* d_design_out) {
-  int rc = check_common(t, cfg, n_instances, n_steps, d_hardpoints, d_target_values, d_status_out, d_failed_step_out);
+                            int64_t n_instances, int32_t n_steps, const okin_batch_io* d_io) {
+  int rc = check_common(t, cfg, n_instances, n_steps, d_io);
   if (rc) return rc;
   DeviceCopy* d = nullptr;
   rc = ensure_device(t, device, &d);
   if (rc) return rc;
   OKIN_CUDA(cudaSetDevice(device));
-  return launch(t, d, cfg, (cudaStream_t)stream, n_instances, n_steps, d_hardpoints, d_params, d_target_values,
-                d_positions_out, d_status_out, d_failed_step_out, d_iters_out, d_max_residual_out, d_tangents_out,
-                d_metrics_out, d_design_out);
+  return launch(t, d, cfg, (cudaStream_t)stream, n_instances, n_steps, *d_io);
 }
 
 int okin_shard_range(int64_t n_instances, int32_t shard, int32_t n_shards, int64_t* begin, int64_t* count) {
@@ -331,11 +325,8 @@ int okin_shard_range(int64_t n_instances, int32_t shard, int32_t n_shards, int64
 }
 
 int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
-                     const double* hardpoints, const double* params, const double* target_values,
-                     const int32_t* device_ids, int32_t n_devices, double* positions_out, int32_t* status_out,
-                     int32_t* failed_step_out, int32_t* iters_out, double* max_residual_out, double* tangents_out,
-                     double* metrics_out, double* design_out) {
-  int rc = check_common(t, cfg, n_instances, n_steps, hardpoints, target_values, status_out, failed_step_out);
+                     const okin_batch_io* io, const int32_t* device_ids, int32_t n_devices) {
+  int rc = check_common(t, cfg, n_instances, n_steps, io);
   if (rc) return rc;
   const int32_t default_dev = 0;
   if (!device_ids || n_devices <= 0) {
@@ -346,24 +337,37 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
   const int32_t* h = t->hdr.data();
   const size_t nin3 = 3 * (size_t)h[OKIN_H_NIN], nout3 = 3 * (size_t)h[OKIN_H_NOUT];
   const size_t nt = h[OKIN_H_NT], n = 3 * (size_t)h[OKIN_H_NF];
+  const size_t nm = (size_t)h[OKIN_H_NM], npar = (size_t)h[OKIN_H_NPARAM];
   const size_t S = (size_t)n_steps;
 
   // Contiguous instance ranges [k*N/G, (k+1)*N/G) per device: the host-side "gather" is the D2H
   // copies.  Inside a device the range is cut into chunks that rotate over OKIN_PIPE_SLOTS streams,
   // so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k.
-  const size_t nm = (size_t)h[OKIN_H_NM], npar = (size_t)h[OKIN_H_NPARAM];
+  // Every per-instance array is one "lane" of a slot: (host pointer, bytes per instance).
+  struct Lane { const void* host; size_t per_inst; bool input; size_t bytes; };
+  Lane lanes[] = {
+      {io->hardpoints, nin3 * 8, true, 0},
+      {(io->params && npar) ? io->params : nullptr, npar * 8, true, 0},
+      {io->status, 4, false, 0},
+      {io->failed_step, 4, false, 0},
+      {io->positions, S * nout3 * 8, false, 0},
+      {io->iters, S * 4, false, 0},
+      {io->max_residual, S * 8, false, 0},
+      {io->tangents, S * nt * n * 8, false, 0},
+      {io->velocities, S * nt * nout3 * 8, false, 0},
+      {io->tangent_health, S * 2 * 8, false, 0},
+      {(io->metrics && nm) ? io->metrics : nullptr, S * nm * 8, false, 0},
+      {io->design, nout3 * 8, false, 0},
+  };
+  constexpr int n_lanes = (int)(sizeof(lanes) / sizeof(lanes[0]));
   auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t chunk = (size_t)std::min<int64_t>(std::max<int64_t>(n_instances, 1), OKIN_PIPE_CHUNK);
-  const size_t b_hp = align(chunk * nin3 * 8), b_tv = align(std::max<size_t>(nt * S, 1) * 8);
-  const size_t b_pos = positions_out ? align(chunk * S * nout3 * 8) : 0;
-  const size_t b_mr = max_residual_out ? align(chunk * S * 8) : 0;
-  const size_t b_tan = tangents_out ? align(chunk * S * nt * n * 8) : 0;
-  const size_t b_met = (metrics_out && nm) ? align(chunk * S * nm * 8) : 0;
-  const size_t b_par = (params && npar) ? align(chunk * npar * 8) : 0;
-  const size_t b_dsn = design_out ? align(chunk * nout3 * 8) : 0;
-  const size_t b_it = iters_out ? align(chunk * S * 4) : 0;
-  const size_t b_st = align(chunk * 4);
-  const size_t slot_bytes = b_hp + b_tv + b_pos + b_mr + b_tan + b_met + b_par + b_dsn + b_it + 2 * b_st;
+  const size_t b_tv = align(std::max<size_t>(nt * S, 1) * 8);
+  size_t slot_bytes = b_tv;
+  for (Lane& l : lanes) {
+    l.bytes = l.host ? align(chunk * std::max<size_t>(l.per_inst, 1)) : 0;
+    slot_bytes += l.bytes;
+  }
 
   std::vector<std::pair<int, DeviceCopy*>> used;
   for (int k = 0; k < n_devices; ++k) {
@@ -390,34 +394,39 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
       const size_t b0 = (size_t)(begin + done);
       cudaStream_t st = d->streams[slot];
       char* p = (char*)d->ws + slot_bytes * slot;
-      double* w_hp = (double*)p; p += b_hp;
-      double* w_tv = (double*)p; p += b_tv;
-      double* w_pos = b_pos ? (double*)p : nullptr; p += b_pos;
-      double* w_mr = b_mr ? (double*)p : nullptr; p += b_mr;
-      double* w_tan = b_tan ? (double*)p : nullptr; p += b_tan;
-      double* w_met = b_met ? (double*)p : nullptr; p += b_met;
-      double* w_par = b_par ? (double*)p : nullptr; p += b_par;
-      double* w_dsn = b_dsn ? (double*)p : nullptr; p += b_dsn;
-      int32_t* w_it = b_it ? (int32_t*)p : nullptr; p += b_it;
-      int32_t* w_st = (int32_t*)p; p += b_st;
-      int32_t* w_fs = (int32_t*)p;
-      OKIN_CUDA(cudaMemcpyAsync(w_hp, hardpoints + b0 * nin3, c * nin3 * 8, cudaMemcpyHostToDevice, st));
-      if (w_par) OKIN_CUDA(cudaMemcpyAsync(w_par, params + b0 * npar, c * npar * 8, cudaMemcpyHostToDevice, st));
+      void* dev[n_lanes];
+      double* w_tv = (double*)p;
+      p += b_tv;
+      for (int l = 0; l < n_lanes; ++l) {
+        dev[l] = lanes[l].bytes ? p : nullptr;
+        p += lanes[l].bytes;
+      }
+      for (int l = 0; l < n_lanes; ++l)
+        if (dev[l] && lanes[l].input)
+          OKIN_CUDA(cudaMemcpyAsync(dev[l], (const char*)lanes[l].host + b0 * lanes[l].per_inst, c * lanes[l].per_inst,
+                                    cudaMemcpyHostToDevice, st));
       if (nt * S && ck < slots)
-        OKIN_CUDA(cudaMemcpyAsync(w_tv, target_values, nt * S * 8, cudaMemcpyHostToDevice, st));
-      rc = launch(t, d, cfg, st, (int64_t)c, n_steps, w_hp, w_par, w_tv, w_pos, w_st, w_fs, w_it, w_mr, w_tan, w_met,
-                  w_dsn);
+        OKIN_CUDA(cudaMemcpyAsync(w_tv, io->target_values, nt * S * 8, cudaMemcpyHostToDevice, st));
+      okin_batch_io dio{};
+      dio.hardpoints = (const double*)dev[0];
+      dio.params = (const double*)dev[1];
+      dio.target_values = w_tv;
+      dio.status = (int32_t*)dev[2];
+      dio.failed_step = (int32_t*)dev[3];
+      dio.positions = (double*)dev[4];
+      dio.iters = (int32_t*)dev[5];
+      dio.max_residual = (double*)dev[6];
+      dio.tangents = (double*)dev[7];
+      dio.velocities = (double*)dev[8];
+      dio.tangent_health = (double*)dev[9];
+      dio.metrics = (double*)dev[10];
+      dio.design = (double*)dev[11];
+      rc = launch(t, d, cfg, st, (int64_t)c, n_steps, dio);
       if (rc) return rc;
-      if (w_pos)
-        OKIN_CUDA(cudaMemcpyAsync(positions_out + b0 * S * nout3, w_pos, c * S * nout3 * 8, cudaMemcpyDeviceToHost, st));
-      if (w_mr) OKIN_CUDA(cudaMemcpyAsync(max_residual_out + b0 * S, w_mr, c * S * 8, cudaMemcpyDeviceToHost, st));
-      if (w_tan)
-        OKIN_CUDA(cudaMemcpyAsync(tangents_out + b0 * S * nt * n, w_tan, c * S * nt * n * 8, cudaMemcpyDeviceToHost, st));
-      if (w_dsn) OKIN_CUDA(cudaMemcpyAsync(design_out + b0 * nout3, w_dsn, c * nout3 * 8, cudaMemcpyDeviceToHost, st));
-      if (w_met) OKIN_CUDA(cudaMemcpyAsync(metrics_out + b0 * S * nm, w_met, c * S * nm * 8, cudaMemcpyDeviceToHost, st));
-      if (w_it) OKIN_CUDA(cudaMemcpyAsync(iters_out + b0 * S, w_it, c * S * 4, cudaMemcpyDeviceToHost, st));
-      OKIN_CUDA(cudaMemcpyAsync(status_out + b0, w_st, c * 4, cudaMemcpyDeviceToHost, st));
-      OKIN_CUDA(cudaMemcpyAsync(failed_step_out + b0, w_fs, c * 4, cudaMemcpyDeviceToHost, st));
+      for (int l = 0; l < n_lanes; ++l)
+        if (dev[l] && !lanes[l].input && lanes[l].per_inst)
+          OKIN_CUDA(cudaMemcpyAsync((char*)const_cast<void*>(lanes[l].host) + b0 * lanes[l].per_inst, dev[l],
+                                    c * lanes[l].per_inst, cudaMemcpyDeviceToHost, st));
     }
   }
   for (auto& u : used) {

@@ -1271,11 +1271,119 @@ OKIN_FN void okin_metrics(const OkinProgram& pr, double* sm, double* out) {
   }
 }
 
+
+// z = L^T x (lt) or x = L z (plain) with the block factor; returns |result|^2 (warp-uniform).
+template <typename Dummy = void>
+OKIN_FN double okin_factor_multiply(const OkinProgram& pr, double* sm, const double* src, double* dst, bool lt) {
+  const int32_t* hdr = pr.hdr;
+  const int nf = hdr[OKIN_H_NF];
+  const int32_t* ptr = okin_sec(pr, lt ? OKIN_S_BW_PTR : OKIN_S_FW_PTR);
+  const int32_t* con = okin_sec(pr, lt ? OKIN_S_BW_CON : OKIN_S_FW_CON);
+  const int32_t* doffs = okin_sec(pr, OKIN_S_DIAG_OFF);
+  const double* Lb = sm;
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  double acc = 0.0;
+  for (int j = lane; j < nf; j += 32) {
+    const double* f = sm + OKIN_LDG(doffs + j);   // {l00,l10,l11,l20,l21,l22,...}
+    const double x0 = src[3 * j], x1 = src[3 * j + 1], x2 = src[3 * j + 2];
+    double t0, t1, t2;
+    if (lt) { t0 = f[0] * x0 + f[1] * x1 + f[3] * x2; t1 = f[2] * x1 + f[4] * x2; t2 = f[5] * x2; }
+    else { t0 = f[0] * x0; t1 = f[1] * x0 + f[2] * x1; t2 = f[3] * x0 + f[4] * x1 + f[5] * x2; }
+    for (int q = OKIN_LDG(ptr + j); q < OKIN_LDG(ptr + j + 1); ++q) {
+      const uint32_t w = (uint32_t)OKIN_LDG(con + q);
+      const double* B = Lb + (w >> 16);
+      const double* y = src + (w & 0xffffu);
+      if (lt) {
+        t0 += B[0] * y[0] + B[3] * y[1] + B[6] * y[2];
+        t1 += B[1] * y[0] + B[4] * y[1] + B[7] * y[2];
+        t2 += B[2] * y[0] + B[5] * y[1] + B[8] * y[2];
+      } else {
+        t0 += B[0] * y[0] + B[1] * y[1] + B[2] * y[2];
+        t1 += B[3] * y[0] + B[4] * y[1] + B[5] * y[2];
+        t2 += B[6] * y[0] + B[7] * y[1] + B[8] * y[2];
+      }
+    }
+    dst[3 * j] = t0; dst[3 * j + 1] = t1; dst[3 * j + 2] = t2;
+    acc += t0 * t0 + t1 * t1 + t2 * t2;
+  }
+  red[lane] = acc;
+  OKIN_PHASE_END
+  return okin_red_sum(red);
+}
+
+// v *= s; returns nothing.  |v|^2 helper below.
+template <typename Dummy = void>
+OKIN_FN double okin_scale_norm2(const OkinProgram& pr, double* sm, double* v, double s) {
+  const int n = 3 * pr.hdr[OKIN_H_NF];
+  double* red = sm + pr.hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  double acc = 0.0;
+  for (int u = lane; u < n; u += 32) {
+    const double x = v[u] * s;
+    v[u] = x;
+    acc += x * x;
+  }
+  red[lane] = acc;
+  OKIN_PHASE_END
+  return okin_red_sum(red);
+}
+
+// Numerical health of the tangent system at the current factorisation (TangentSolveInfo,
+// sensitivity.py:42-55, :97-113): the extreme singular values of the pinned Jacobian are the
+// square roots of the extreme eigenvalues of A = L L^T.  sigma_max by power iteration with the
+// factor, sigma_min by inverse iteration with the triangular solves; both are read off as
+// Rayleigh quotients x^T A x = |L^T x|^2, so they are estimates from inside (sigma_max from
+// below, sigma_min from above) whose error is quadratic in the eigenvector error.
+// out2 = {sigma_min, sigma_max / sigma_min}.  Scratch: the row-gradient storage (dead until the
+// next row evaluation) and vec[0].
+#define OKIN_HEALTH_ITERS 24
+template <typename Dummy = void>
+OKIN_FN void okin_tangent_health(const OkinProgram& pr, double* sm, bool notpd, double* out2) {
+  const int32_t* hdr = pr.hdr;
+  const int n = 3 * hdr[OKIN_H_NF];
+  double* x = sm + hdr[OKIN_H_OFF_RG];
+  double* z = x + n;
+  double* v0 = sm + hdr[OKIN_H_OFF_VEC];
+  OKIN_PHASE_BEGIN
+  for (int u = lane; u < n; u += 32) {
+    // deterministic start vectors: positive for the dominant direction, signed for the weakest
+    const uint32_t hsh = ((uint32_t)u + 1u) * 2654435761u;
+    x[u] = 1.0 + 0.37 * (double)((hsh >> 16) & 0xffu) / 256.0;
+    v0[u] = (double)((hsh >> 12) & 0xffffu) / 65536.0 - 0.5;
+  }
+  OKIN_PHASE_END
+  double smax2 = 0.0;
+  double nx = okin_scale_norm2(pr, sm, x, 1.0);
+  for (int it = 0; it < OKIN_HEALTH_ITERS; ++it) {
+    okin_scale_norm2(pr, sm, x, 1.0 / sqrt(nx));
+    smax2 = okin_factor_multiply(pr, sm, x, z, true);    // Rayleigh quotient of A at x
+    nx = okin_factor_multiply(pr, sm, z, x, false);      // x <- A x
+  }
+  double nv = okin_scale_norm2(pr, sm, v0, 1.0);
+  for (int it = 0; it < OKIN_HEALTH_ITERS; ++it) {
+    okin_scale_norm2(pr, sm, v0, 1.0 / sqrt(nv));
+    okin_solve(pr, sm, 0, 1, false);                      // v0 <- A^{-1} v0
+    nv = okin_scale_norm2(pr, sm, v0, 1.0);
+  }
+  okin_scale_norm2(pr, sm, v0, 1.0 / sqrt(nv));
+  const double smin2 = okin_factor_multiply(pr, sm, v0, z, true);
+  const bool good = !notpd && smin2 == smin2 && smin2 > 0.0 && smax2 == smax2;
+  OKIN_PHASE_BEGIN
+  if (lane == 0) {
+    out2[0] = good ? sqrt(smin2) : 0.0;
+    out2[1] = good ? sqrt(smax2 / smin2) : INFINITY;
+  }
+  OKIN_PHASE_END
+}
+
 struct OkinOutputs {
   double* positions;      // [n_steps][NOUT*3] or null
   int32_t* iters;         // [n_steps] or null
   double* max_residual;   // [n_steps] or null
   double* tangents;       // [n_steps][NT][3*NF] (reference column order) or null
+  double* velocities;     // [n_steps][NT][NOUT*3] velocity of every output point per target, or null
+  double* health;         // [n_steps][2] {sigma_min, cond} of the tangent system, or null
   double* metrics;        // [n_steps][NM] or null (NaN == the reference's None)
   double* design;         // [NOUT*3] design (setup) pose or null
   int32_t* status;        // [1]
@@ -1346,7 +1454,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
       if (status == OKIN_STATUS_OK) {
-        if (out.tangents || out.metrics || !tangents_ready) {
+        if (out.tangents || out.velocities || out.health || out.metrics || !tangents_ready) {
           // Exported tangents are taken at the solution itself: relinearise there.  (For the
           // predictor alone the factor of the last Gauss-Newton point, <= coarse_tol away, is
           // enough and was solved together with the chord step.)
@@ -1388,6 +1496,16 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
         OKIN_PHASE_END
       }
     }
+    if (out.velocities) {  // TangentField.velocities (sensitivity.py:115-141)
+      double* dst = out.velocities + (size_t)s * nt * 3 * nout;
+      OKIN_PHASE_BEGIN
+      for (int t = lane; t < nt * nout; t += 32) {
+        double v[3] = {NAN, NAN, NAN};
+        if (ok) okin_point_vel(pr, sm, OKIN_LDG(out_point + t % nout), t / nout, v);
+        dst[3 * t] = v[0]; dst[3 * t + 1] = v[1]; dst[3 * t + 2] = v[2];
+      }
+      OKIN_PHASE_END
+    }
     if (out.tangents) {
       double* dst = out.tangents + (size_t)s * nt * n;
       OKIN_PHASE_BEGIN
@@ -1396,6 +1514,15 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
         dst[j * n + 3 * OKIN_LDG(ecol + u / 3) + u % 3] = ok ? vec[n + j * n + u] : NAN;
       }
       OKIN_PHASE_END
+    }
+    if (out.health) {
+      if (ok) {
+        okin_tangent_health(pr, sm, st.notpd != 0, out.health + 2 * s);
+      } else {
+        OKIN_PHASE_BEGIN
+        if (lane == 0) { out.health[2 * s] = NAN; out.health[2 * s + 1] = NAN; }
+        OKIN_PHASE_END
+      }
     }
   }
   OKIN_PHASE_BEGIN

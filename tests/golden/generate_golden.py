@@ -13,6 +13,7 @@ Per sweep case:
   positions_default  reference solve with default tolerances                    [S, P, 3]
   nfev_*, max_residual_*                                                        [S]
   tangents           compute_state_tangents at the tight states                 [S, T, n]
+  velocities         TangentField.velocities of every point (sorted keys)    [S, T, P, 3]
   tangent_rank / tangent_sigma_min / tangent_cond                               [S]
 Per family: residual + jacobian rows at seeded random points (core/constraints.py, core/jacobians.py).
 Failure cases: first failed step and failure class for out-of-reach sweeps.
@@ -163,16 +164,18 @@ def run_case(name: str, geom: dict, sweep: dict, with_default=True) -> None:
         arrays["positions_default"] = positions_array(states_d, keys)
         arrays["nfev_default"] = np.array([s.nfev for s in stats_d])
         arrays["max_residual_default"] = np.array([s.max_residual for s in stats_d])
-    tang, rank, smin, cond = [], [], [], []
+    tang, rank, smin, cond, vel = [], [], [], [], []
     for step, st in enumerate(states_t):
         targets = convert_targets_to_absolute([sw[step] for sw in cfg.target_sweeps], init)
         fields, info = compute_state_tangents(st, cons, dm, targets)
         free = st.free_points_order
         tang.append([np.concatenate([f.velocities[k] for k in free]) for f in fields])
+        vel.append([[f.velocity(k) for k in keys] for f in fields])
         rank.append(info.rank)
         smin.append(info.smallest_singular_value)
         cond.append(info.condition_number)
     arrays["tangents"] = np.array(tang)
+    arrays["velocities"] = np.array(vel)
     arrays["tangent_rank"] = np.array(rank)
     arrays["tangent_sigma_min"] = np.array(smin)
     arrays["tangent_cond"] = np.array(cond)

@@ -130,42 +130,45 @@ def emu_lib():
         src = os.path.join(ROOT, "tests", "emu", "okin_emu.cpp")
         out = os.path.join(ROOT, "tests", "emu", "libokin_emu.so")
         csrc = os.path.join(ROOT, "open-kinematics_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".h", ".cuh"))]
+        deps = [src, os.path.join(ROOT, "include", "okin.h")]
+        deps += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".h", ".cuh"))]
         if not os.path.exists(out) or os.path.getmtime(out) < max(map(os.path.getmtime, deps)):
             subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17", f"-I{csrc}", "-o", out, src], check=True)
         lib = ctypes.CDLL(out)
         lib.okin_emu_sweep.restype = ctypes.c_int
-        lib.okin_emu_sweep.argtypes = (
-            [ctypes.c_void_p] * 3 + [ctypes.c_long, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                     ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
-                                     ctypes.c_double, ctypes.c_int, ctypes.c_int]
-            + [ctypes.c_void_p] * 8)
+        lib.okin_emu_sweep.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_long, ctypes.c_int] + [ctypes.c_void_p] * 2
         _EMU = lib
     return _EMU
 
 
-def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, step_tol=1e-6, coarse_tol=1e-3,
-              fine_tol=1e-4, residual_tol=1e-3, mu_init=1e-3, max_iter=50, use_predictor=3, params=None) -> dict:
+def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, want_health=False, **cfg) -> dict:
+    """Run the lane-emulation build of the device core; ``cfg`` overrides ``okin_solver_cfg`` fields."""
+    from open_kinematics_b200._lib import BatchIO, SolverCfg
     hp = np.ascontiguousarray(hardpoints, dtype=np.float64).reshape(-1, 3 * program.n_in)
     tv = np.ascontiguousarray(values, dtype=np.float64)
     n_inst, n_steps, nt, n = hp.shape[0], tv.shape[1], tv.shape[0], program.n_unknowns
     out = {
         "positions": np.zeros((n_inst, n_steps, program.n_out, 3)), "iters": np.zeros((n_inst, n_steps), np.int32),
         "max_residual": np.zeros((n_inst, n_steps)), "tangents": np.zeros((n_inst, n_steps, nt, n)),
+        "velocities": np.zeros((n_inst, n_steps, nt, program.n_out, 3)),
+        "tangent_health": np.zeros((n_inst, n_steps, 2)) if want_health else None,
         "status": np.zeros(n_inst, np.int32), "failed_step": np.zeros(n_inst, np.int32),
-        "metrics": np.zeros((n_inst, n_steps, max(len(program.metric_names), 1))),
+        "metrics": np.zeros((n_inst, n_steps, len(program.metric_names))) if program.metric_names else None,
         "design": np.zeros((n_inst, program.n_out, 3)),
     }
     par = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
+    settings = dict(step_tol=1e-6, coarse_tol=1e-3, fine_tol=1e-4, residual_tol=1e-3, mu_init=1e-3, max_iter=50,
+                    use_predictor=3)
+    settings.update(cfg)
+    c = SolverCfg(**settings)
     hdr = np.ascontiguousarray(program.hdr)
+    io = BatchIO.of(hardpoints=hp, params=par, target_values=tv, **out)
     rc = emu_lib().okin_emu_sweep(
         hdr.ctypes.data, program.iblob.ctypes.data, program.fblob.ctypes.data, n_inst, n_steps,
-        hp.ctypes.data, None if par is None else par.ctypes.data, tv.ctypes.data, step_tol, coarse_tol,
-        fine_tol, residual_tol, mu_init, max_iter, use_predictor,
-        out["positions"].ctypes.data, out["iters"].ctypes.data, out["max_residual"].ctypes.data,
-        out["tangents"].ctypes.data, out["metrics"].ctypes.data if program.metric_names else None,
-        out["design"].ctypes.data, out["status"].ctypes.data, out["failed_step"].ctypes.data)
+        ctypes.byref(c), ctypes.byref(io))
     assert rc == 0
+    if out["metrics"] is None:
+        out["metrics"] = np.zeros((n_inst, n_steps, 1))
     return out
 
 

@@ -65,6 +65,24 @@ def test_tangents_match_reference(case):
     assert np.abs(out["tangents"][0] - arr["tangents"]).max() <= 1e-7 * max(1.0, scale)
 
 
+@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c2_macpherson_bump_steer", "c3_rocker_ubar_coilover_roll",
+                                  "c4_tbar_heave_shim_bump"])
+def test_point_velocities_and_tangent_health_match_reference(case):
+    """TangentField.velocities of every point (free, fixed, derived) and TangentSolveInfo."""
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    prog, values = _program(sus, sweep)
+    out = emu_solve(prog, _nominal(sus, prog), values, want_health=True)
+    order = [prog.out_keys.index(key_from_name(n)) for n in meta["point_keys"]]
+    vel = out["velocities"][0][:, :, order]
+    assert np.abs(vel - arr["velocities"]).max() <= 1e-7 * max(1.0, np.abs(arr["velocities"]).max())
+    # Power / inverse iteration approach the extreme singular values from inside (the 1e-5 slack:
+    # the reference keeps the zero-gradient point-on-line rows next to their pins).
+    smin, cond = out["tangent_health"][0, :, 0], out["tangent_health"][0, :, 1]
+    assert (smin >= arr["tangent_sigma_min"] * (1 - 1e-5)).all() and (smin <= arr["tangent_sigma_min"] * 1.05).all()
+    assert (cond <= arr["tangent_cond"] * (1 + 1e-5)).all() and (cond >= arr["tangent_cond"] * 0.9).all()
+
+
 def test_predictor_does_not_change_the_answer():
     meta, arr = load_golden("c3_rocker_ubar_coilover_roll")
     sus, sweep = build_case(meta)
