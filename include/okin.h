@@ -47,6 +47,16 @@
  *                                                    reference yields None
  *   design_out      [n_instances][n_out_points*3]    design (setup) pose after the camber-shim
  *                                                    pre-solve and derived points
+ *   diagnostics_out [n_instances][n_steps][n_diagnostics]  sweep diagnostics as per-state reductions
+ *                                                    (diagnostics.py:136-226, axle/mechanisms.py:432-549):
+ *                                                    column 0 = OKIN_DIAG_* flag bits, 1 = number of free
+ *                                                    points that jumped into the step, 2 = largest such
+ *                                                    displacement, 3 = its output slot, 4 = its threshold,
+ *                                                    then the topology columns (U-bar branch volume and
+ *                                                    chirality margin, transmission margins; NaN = None)
+ *   jumps_out       [n_instances][n_steps][n_unknowns/3]  row 0: continuity threshold of each free point
+ *                                                    (reference column order); row s>0: displacement into
+ *                                                    step s where it exceeded the threshold, else 0
  *   status_out      [n_instances]                    OKIN_STATUS_*
  *   failed_step_out [n_instances]                    -1 or the first failed step
  * The buffers of one call travel in an okin_batch_io; every output pointer except status /
@@ -102,7 +112,7 @@ typedef struct okin_solver_cfg {
 
 typedef struct okin_topology_info {
   int32_t n_points, n_in_points, n_out_points, n_unknowns, n_targets, n_rows;
-  int32_t smem_bytes_per_instance, n_levels, n_metrics, n_params;
+  int32_t smem_bytes_per_instance, n_levels, n_metrics, n_params, n_diagnostics;
 } okin_topology_info;
 
 /* Buffers of one batch call (layouts in the header comment).  Host pointers for okin_solve_batch,
@@ -121,6 +131,8 @@ typedef struct okin_batch_io {
   double* tangent_health;
   double* metrics;
   double* design;
+  double* diagnostics;
+  double* jumps;
 } okin_batch_io;
 
 int okin_device_count(int* out);

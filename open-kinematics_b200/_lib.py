@@ -42,7 +42,7 @@ class BatchIO(ctypes.Structure):
 
     INPUTS = ("hardpoints", "params", "target_values")
     OUTPUTS = ("status", "failed_step", "positions", "iters", "max_residual", "tangents", "velocities",
-               "tangent_health", "metrics", "design")
+               "tangent_health", "metrics", "design", "diagnostics", "jumps")
     _fields_ = [(n, ctypes.c_void_p) for n in INPUTS + OUTPUTS]
 
     @classmethod
@@ -61,7 +61,7 @@ class BatchIO(ctypes.Structure):
 class TopologyInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "n_points", "n_in_points", "n_out_points", "n_unknowns", "n_targets", "n_rows",
-        "smem_bytes_per_instance", "n_levels", "n_metrics", "n_params")]
+        "smem_bytes_per_instance", "n_levels", "n_metrics", "n_params", "n_diagnostics")]
 
 
 # name -> (restype, argtypes); also the list the "exports every declared symbol" test checks.
@@ -205,7 +205,7 @@ class DeviceTopology:
     def solve_batch(self, hardpoints: np.ndarray, target_values: np.ndarray, cfg: SolverCfg | None = None,
                     devices=None, want_positions=True, want_tangents=False, want_metrics=False,
                     want_design=False, params: np.ndarray | None = None, want_velocities=False,
-                    want_health=False) -> dict:
+                    want_health=False, want_diagnostics=False) -> dict:
         """hardpoints [n_inst, n_in*3]; target_values [n_targets, n_steps]."""
         require_device()
         prog = self.program
@@ -236,7 +236,11 @@ class DeviceTopology:
             "tangent_health": np.empty((n_inst, n_steps, 2)) if want_health else None,
             "metrics": np.empty((n_inst, n_steps, len(prog.metric_names))) if want_metrics else None,
             "design": np.empty((n_inst, prog.n_out, 3)) if want_design else None,
+            "diagnostics": np.empty((n_inst, n_steps, len(prog.diagnostic_names))) if want_diagnostics else None,
+            "jumps": np.empty((n_inst, n_steps, prog.n_unknowns // 3)) if want_diagnostics else None,
         }
+        if want_diagnostics and not prog.diagnostic_names:
+            raise ValueError("This topology was compiled without a diagnostic program")
         if want_metrics and not prog.metric_names:
             raise ValueError("This topology was compiled without a metric program")
         dev = np.ascontiguousarray(devices if devices is not None else [0], dtype=np.int32)

@@ -8,7 +8,7 @@ from typing import Sequence
 
 from ..enums import PointID, SuspensionType
 from ..points.derived.manager import DerivedPointsSpec
-from ..primitives.point_ref import Side
+from ..primitives.point_ref import PointRef, Side
 from ..state import SuspensionState
 from ..targeting import ActuatorDOF, WorldAxisSystem
 
@@ -65,6 +65,42 @@ class Suspension:
         authored pose stands in for the design pose (a setup shim would need the device), which
         is all the topology compiler needs when design constants are recomputed per instance."""
         return self.initial_state(), self.constraints()
+
+    def default_state_targets(self) -> list:
+        """Targets that pin every degree of freedom of the mechanism at a state: hub height of each
+        wheel plus every physical actuator (used to re-pin a state when no tangents are given)."""
+        from ..enums import Axis
+        from ..targeting import PointTarget, PointTargetAxis, PointTargetVector
+        hubs = [PointRef(side, PointID.WHEEL_CENTER) for side in (Side.LEFT, Side.RIGHT)] if self.is_axle \
+            else [PointID.WHEEL_CENTER]
+        targets = [PointTarget(hub, PointTargetAxis(Axis.Z), 0.0) for hub in hubs]
+        targets += [PointTarget(dof.point_keys[0], PointTargetVector(dof.direction), 0.0)
+                    for dof in self.actuator_dofs()]
+        return targets
+
+    def compute_state_metrics(self, state: SuspensionState, tangents=None):
+        """Metric row(s) of one solved state (reference suspensions/base.py:198-204,
+        corner/base.py:93-101, axle/suspension.py:313-326): a ``MetricRow`` for a corner,
+        ``AxleMetricRows`` for an axle.  Derivative columns are present only when ``tangents``
+        (the state's ``TangentField`` list) is given; their targets select the drivers.  The
+        numbers come from the device's metric program evaluated at the state."""
+        if self.config is None:
+            raise ValueError("Suspension has no configuration")
+        from ..metrics.main import rows_from_columns
+        from ..sweep import evaluate_states_on_device
+        heads = [field.target for field in tangents] if tangents else self.default_state_targets()
+        res, solver, ramp = evaluate_states_on_device(self, heads, [state], want_metrics=True, ramp=5)
+        return rows_from_columns(res.metrics[0, ramp], solver.program.metric_locations, self.is_axle,
+                                 with_derivatives=bool(tangents))
+
+    def topology_diagnostics(self, states: list) -> list:
+        """Advisory checks owned by the concrete topology (reference suspensions/base.py:220-225,
+        axle/suspension.py:241-251), evaluated by the device's diagnostic program."""
+        from ..diagnostics import evaluate_diagnostics_on_device, topology_issues
+        if not states:
+            return []
+        diag, _, program = evaluate_diagnostics_on_device(self, states)
+        return topology_issues(program.diagnostic_checks, diag)
 
     def all_point_keys(self) -> set:
         """Every point present in a solved state (authored + derived)."""

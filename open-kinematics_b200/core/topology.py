@@ -125,6 +125,8 @@ class TopologyProgram:
     stats: dict
     metric_names: list = field(default_factory=list)
     metric_locations: list = field(default_factory=list)
+    diagnostic_names: list = field(default_factory=list)
+    diagnostic_checks: list = field(default_factory=list)
     param_names: list = field(default_factory=list)
     param_default: np.ndarray = field(default_factory=lambda: np.zeros(0))
 
@@ -287,6 +289,7 @@ def compile_topology(
     design_rules: bool = True,
     metrics=None,
     shims=None,
+    diagnostics=None,
 ) -> TopologyProgram:
     """Compile one topology.
 
@@ -671,6 +674,9 @@ def compile_topology(
     design_pts = mprog.design_pts if mprog else []
     mconst = mprog.fconst if mprog else []
     metric_names = list(mprog.names) if mprog else []
+    design_pts = list(design_pts)
+    dprog = diagnostics(pidx, design_pts) if diagnostics is not None else None
+    free_out = [out_keys.index(k) if k in out_keys else -1 for k in free_order]
     ndsn = len(design_pts)
     layout["OKIN_H_OFF_DSN"] = take(max(3 * ndsn, 1))
     layout["OKIN_H_OFF_MCTX"] = take(4 * max(len(mcorners), 2))
@@ -691,6 +697,7 @@ def compile_topology(
         "OKIN_S_DOP_LEV": dop_lev, "OKIN_S_POINT_ELIM": point_elim, "OKIN_S_POINT_DOP": point_dop,
         "OKIN_S_DESIGN_PT": design_pts, "OKIN_S_MCORNER": mcorners, "OKIN_S_MOP": mops, "OKIN_S_MAXLE": maxle,
         "OKIN_S_SHIM": shim_recs, "OKIN_S_SHIM_PTS": shim_pts,
+        "OKIN_S_FREE_OUT": free_out, "OKIN_S_DGOP": dprog.ops if dprog else [],
     }
     hdr = np.zeros(D["OKIN_HDR_SIZE"], np.int32)
     chunks, cursor = [], 0
@@ -727,6 +734,7 @@ def compile_topology(
         "OKIN_H_NMC": len(mcorners), "OKIN_H_NMOP": len(mops), "OKIN_H_NMAXLE": len(maxle), "OKIN_H_NDSN": ndsn,
         "OKIN_H_NSHIM": len(shim_recs), "OKIN_H_NPARAM": len(param_default),
         "OKIN_H_NDROW": len(fast_rows), "OKIN_H_NGROW": len(row_order),
+        "OKIN_H_NDIAG": len(dprog.names) if dprog else 0, "OKIN_H_NDGOP": len(dprog.ops) if dprog else 0,
         **layout,
     }
     for name, value in counts.items():
@@ -745,6 +753,8 @@ def compile_topology(
         out_keys=out_keys, n_constraints=len(constraints), row_source=[r.source for r in rows],
         target_points=[t.point_id for t in targets], stats=stats, metric_names=metric_names,
         metric_locations=list(mprog.locations) if mprog else [],
+        diagnostic_names=list(dprog.names) if dprog else [],
+        diagnostic_checks=list(dprog.checks) if dprog else [],
         param_names=param_names, param_default=np.asarray(param_default, dtype=np.float64),
     )
 
@@ -752,6 +762,7 @@ def compile_topology(
 def compile_suspension(suspension, sweep_config, output_points=None, design_rules: bool = True,
                        with_metrics: bool = True) -> TopologyProgram:
     """Compile a built suspension + sweep (first-step targets define the target rows)."""
+    from .diagnostics_program import build_diagnostic_program
     from .metrics_program import build_metric_program
     from .shim_program import shim_records
 
@@ -763,4 +774,5 @@ def compile_suspension(suspension, sweep_config, output_points=None, design_rule
         state, constraints, suspension.derived_spec(), targets,
         output_points=output_points, design_rules=design_rules, metrics=metrics,
         shims=shim_records(suspension) if design_rules else None,
+        diagnostics=lambda pidx, design_pts: build_diagnostic_program(suspension, pidx, design_pts),
     )

@@ -51,6 +51,7 @@ struct DeviceCopy {
   int warps_per_cta = 0;
   int smem_bytes = 0;
   int table_doubles = 0;
+  int smem_optin = 0;
   // grow-only workspace for the host-buffer entry point
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -105,11 +106,33 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
     out.health = io.tangent_health ? io.tangent_health + (size_t)i * n_steps * 2 : nullptr;
     out.metrics = io.metrics ? io.metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
     out.design = io.design ? io.design + (size_t)i * 3 * nout : nullptr;
+    out.diagnostics = io.diagnostics ? io.diagnostics + (size_t)i * n_steps * hdr[OKIN_H_NDIAG] : nullptr;
     out.status = io.status + i;
     out.failed_step = io.failed_step + i;
     okin_sweep(pr, sm, io.hardpoints + (size_t)i * 3 * nin,
                io.params ? io.params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, io.target_values, n_steps, cfg,
                out);
+    __syncwarp();
+  }
+}
+
+// Second pass of the sweep diagnostics: one warp per instance walks the instance's position rows
+// (okin_continuity).  Shared memory per warp: 32 displacement histories + thresholds + slots.
+__global__ void okin_continuity_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib,
+                                       long long n_instances, int n_steps, int stride,
+                                       const double* __restrict__ positions, const int32_t* __restrict__ failed_step,
+                                       double* diag, double* jumps) {
+  extern __shared__ double okin_smem[];
+  OkinProgram pr{hdr, ib, nullptr};
+  const int warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+  double* scratch = okin_smem + (size_t)warp * (32 * stride + 64);
+  const size_t nout3 = 3 * (size_t)hdr[OKIN_H_NOUT], nd = hdr[OKIN_H_NDIAG], nf = hdr[OKIN_H_NF];
+  for (long long i = (long long)blockIdx.x * warps_per_cta + warp; i < n_instances;
+       i += (long long)gridDim.x * warps_per_cta) {
+    const int failed = failed_step[i];
+    okin_continuity(pr, scratch, stride, positions + (size_t)i * n_steps * nout3, n_steps,
+                    failed < 0 ? n_steps : failed, diag + (size_t)i * n_steps * nd,
+                    jumps ? jumps + (size_t)i * n_steps * nf : nullptr);
     __syncwarp();
   }
 }
@@ -142,6 +165,7 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
     cudaDeviceProp prop;
     OKIN_CUDA(cudaGetDeviceProperties(&prop, device));
     d.num_sms = prop.multiProcessorCount;
+    d.smem_optin = (int)prop.sharedMemPerBlockOptin;
     // CTA shape: W warps sharing one copy of the tables; pick the W that keeps the most warps resident
     // (shared memory, the 64K-register file at OKIN_REGS_PER_THREAD, 1 KB per-CTA reservation).
     d.table_doubles = (int)(((t->ib.size() + OKIN_HDR_SIZE) * sizeof(int32_t) + 7) / 8);
@@ -188,6 +212,21 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
   okin_sweep_kernel<<<grid, w * 32, d->smem_bytes, stream>>>(
       d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, c, io, (int)t->ib.size(), d->table_doubles);
   OKIN_CUDA(cudaGetLastError());
+  if (io.diagnostics && t->hdr[OKIN_H_NDIAG] && n_steps > 0) {
+    // continuity pass over the position rows the sweep kernel just wrote (same stream)
+    const int stride = (n_steps - 1) | 1;   // odd: lanes walk their histories on different banks
+    const size_t per_warp = ((size_t)32 * stride + 64) * sizeof(double);
+    int cw = 4;
+    while (cw > 1 && cw * per_warp > (size_t)d->smem_optin) cw >>= 1;
+    if (cw * per_warp > (size_t)d->smem_optin) return fail(OKIN_ERR_USAGE, "too many sweep steps for the continuity diagnostics");
+    OKIN_CUDA(cudaFuncSetAttribute(okin_continuity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(cw * per_warp)));
+    const int cgrid = (int)std::min<int64_t>((n_instances + cw - 1) / cw, (int64_t)d->num_sms * 8);
+    okin_continuity_kernel<<<cgrid, cw * 32, cw * per_warp, stream>>>(
+        d->hdr, d->ib, (long long)n_instances, n_steps, stride, io.positions, io.failed_step, io.diagnostics,
+        io.jumps);
+    OKIN_CUDA(cudaGetLastError());
+  }
   return OKIN_OK;
 }
 
@@ -198,6 +237,9 @@ int check_common(const okin_topology* t, const okin_solver_cfg* cfg, int64_t n_i
   if (n_instances < 0 || n_steps < 0) return fail(OKIN_ERR_USAGE, "negative size");
   if (n_instances > 0 && (!hp || !status || !failed)) return fail(OKIN_ERR_USAGE, "null required buffer");
   if (n_steps > 0 && t->hdr[OKIN_H_NT] > 0 && !tv) return fail(OKIN_ERR_USAGE, "null target_values");
+  if ((io->diagnostics || io->jumps) && !t->hdr[OKIN_H_NDIAG])
+    return fail(OKIN_ERR_USAGE, "topology was compiled without a diagnostic program");
+  if (io->jumps && !io->diagnostics) return fail(OKIN_ERR_USAGE, "jumps output needs the diagnostics output");
   if (cfg->max_iter < 1 || !(cfg->step_tol > 0.0) || !(cfg->coarse_tol >= cfg->step_tol)) return fail(OKIN_ERR_USAGE, "invalid solver config");
   return OKIN_OK;
 }
@@ -288,6 +330,7 @@ int okin_topology_get_info(const okin_topology* t, okin_topology_info* out) {
   out->n_levels = h[OKIN_H_NLEV];
   out->n_metrics = h[OKIN_H_NM];
   out->n_params = h[OKIN_H_NPARAM];
+  out->n_diagnostics = h[OKIN_H_NDIAG];
   return OKIN_OK;
 }
 
@@ -309,6 +352,8 @@ int okin_solve_batch_device(okin_topology* t, const okin_solver_cfg* cfg, int32_
                             int64_t n_instances, int32_t n_steps, const okin_batch_io* d_io) {
   int rc = check_common(t, cfg, n_instances, n_steps, d_io);
   if (rc) return rc;
+  if (d_io->diagnostics && !d_io->positions && n_instances > 0)
+    return fail(OKIN_ERR_USAGE, "device-buffer diagnostics need the positions output (continuity pass reads it)");
   DeviceCopy* d = nullptr;
   rc = ensure_device(t, device, &d);
   if (rc) return rc;
@@ -344,20 +389,24 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
   // copies.  Inside a device the range is cut into chunks that rotate over OKIN_PIPE_SLOTS streams,
   // so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k.
   // Every per-instance array is one "lane" of a slot: (host pointer, bytes per instance).
-  struct Lane { const void* host; size_t per_inst; bool input; size_t bytes; };
+  // scratch: device buffer needed although the caller does not want the array back.
+  struct Lane { const void* host; size_t per_inst; bool input; bool scratch; size_t bytes; };
+  const size_t nd = (size_t)h[OKIN_H_NDIAG];
   Lane lanes[] = {
-      {io->hardpoints, nin3 * 8, true, 0},
-      {(io->params && npar) ? io->params : nullptr, npar * 8, true, 0},
-      {io->status, 4, false, 0},
-      {io->failed_step, 4, false, 0},
-      {io->positions, S * nout3 * 8, false, 0},
-      {io->iters, S * 4, false, 0},
-      {io->max_residual, S * 8, false, 0},
-      {io->tangents, S * nt * n * 8, false, 0},
-      {io->velocities, S * nt * nout3 * 8, false, 0},
-      {io->tangent_health, S * 2 * 8, false, 0},
-      {(io->metrics && nm) ? io->metrics : nullptr, S * nm * 8, false, 0},
-      {io->design, nout3 * 8, false, 0},
+      {io->hardpoints, nin3 * 8, true, false, 0},
+      {(io->params && npar) ? io->params : nullptr, npar * 8, true, false, 0},
+      {io->status, 4, false, false, 0},
+      {io->failed_step, 4, false, false, 0},
+      {io->positions, S * nout3 * 8, false, io->diagnostics && !io->positions, 0},
+      {io->iters, S * 4, false, false, 0},
+      {io->max_residual, S * 8, false, false, 0},
+      {io->tangents, S * nt * n * 8, false, false, 0},
+      {io->velocities, S * nt * nout3 * 8, false, false, 0},
+      {io->tangent_health, S * 2 * 8, false, false, 0},
+      {(io->metrics && nm) ? io->metrics : nullptr, S * nm * 8, false, false, 0},
+      {io->design, nout3 * 8, false, false, 0},
+      {io->diagnostics, S * nd * 8, false, false, 0},
+      {io->jumps, S * (n / 3) * 8, false, false, 0},
   };
   constexpr int n_lanes = (int)(sizeof(lanes) / sizeof(lanes[0]));
   auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -365,7 +414,7 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
   const size_t b_tv = align(std::max<size_t>(nt * S, 1) * 8);
   size_t slot_bytes = b_tv;
   for (Lane& l : lanes) {
-    l.bytes = l.host ? align(chunk * std::max<size_t>(l.per_inst, 1)) : 0;
+    l.bytes = (l.host || l.scratch) ? align(chunk * std::max<size_t>(l.per_inst, 1)) : 0;
     slot_bytes += l.bytes;
   }
 
@@ -421,10 +470,12 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
       dio.tangent_health = (double*)dev[9];
       dio.metrics = (double*)dev[10];
       dio.design = (double*)dev[11];
+      dio.diagnostics = (double*)dev[12];
+      dio.jumps = (double*)dev[13];
       rc = launch(t, d, cfg, st, (int64_t)c, n_steps, dio);
       if (rc) return rc;
       for (int l = 0; l < n_lanes; ++l)
-        if (dev[l] && !lanes[l].input && lanes[l].per_inst)
+        if (dev[l] && lanes[l].host && !lanes[l].input && lanes[l].per_inst)
           OKIN_CUDA(cudaMemcpyAsync((char*)const_cast<void*>(lanes[l].host) + b0 * lanes[l].per_inst, dev[l],
                                     c * lanes[l].per_inst, cudaMemcpyDeviceToHost, st));
     }

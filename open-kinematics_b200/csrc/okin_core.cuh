@@ -1272,6 +1272,188 @@ OKIN_FN void okin_metrics(const OkinProgram& pr, double* sm, double* out) {
 }
 
 
+
+// ---------------------------------------------------------------------------------------
+// Sweep diagnostics.  Topology checks are evaluated per state inside the sweep (the state is in
+// shared memory); the continuity check needs a point's whole displacement history and runs as a
+// second pass over the instance's position rows (okin_continuity).
+// ---------------------------------------------------------------------------------------
+#define OKIN_TRANSMISSION_WARN 0.15   // axle/mechanisms.py:70
+#define OKIN_JUMP_FLOOR_MM 5.0        // diagnostics.py:30-31
+#define OKIN_JUMP_MEDIAN_FACTOR 4.0
+
+OKIN_HD double okin_stp(const double* o, const double* a, const double* b, const double* c) {
+  const double ax = a[0] - o[0], ay = a[1] - o[1], az = a[2] - o[2];
+  const double bx = b[0] - o[0], by = b[1] - o[1], bz = b[2] - o[2];
+  const double cx = c[0] - o[0], cy = c[1] - o[1], cz = c[2] - o[2];
+  return ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
+}
+
+// One state's diagnostic row: flags + topology columns (the jump columns are zeroed here and
+// filled by okin_continuity).  ok: the state was accepted; status: the instance status so far.
+template <typename Dummy = void>
+OKIN_FN void okin_diagnostics(const OkinProgram& pr, double* sm, double* row, bool ok, int status) {
+  const int32_t* hdr = pr.hdr;
+  const int nd = hdr[OKIN_H_NDIAG], nop = hdr[OKIN_H_NDGOP];
+  const double* pos = sm + hdr[OKIN_H_OFF_POS];
+  const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < nd; t += 32) row[t] = t == 3 ? -1.0 : (t < OKIN_DIAG_BASE || ok ? 0.0 : NAN);
+  red[lane] = 0.0;
+  OKIN_PHASE_END
+  if (ok) {
+    OKIN_PHASE_BEGIN
+    for (int t = lane; t < nop; t += 32) {
+      const int32_t* rec = okin_sec(pr, OKIN_S_DGOP) + t * OKIN_DGOP_STRIDE;
+      const int col = OKIN_LDG(rec + 6);
+      int flags = 0;
+      if (OKIN_LDG(rec) == OKIN_DG_CHIRALITY) {
+        const double* a = pos + 3 * OKIN_LDG(rec + 1);
+        const double* b = pos + 3 * OKIN_LDG(rec + 2);
+        const double* r = pos + 3 * OKIN_LDG(rec + 3);
+        const double* u = pos + 3 * OKIN_LDG(rec + 4);
+        const double vol = okin_stp(a, b, r, u);
+        const double design = okin_stp(dsn + 3 * OKIN_LDG(rec + 7), dsn + 3 * OKIN_LDG(rec + 8),
+                                       dsn + 3 * OKIN_LDG(rec + 9), dsn + 3 * OKIN_LDG(rec + 10));
+        double n[3] = {0.0, 0.0, 0.0};
+        const double* q[3] = {b, r, u};
+        for (int k = 0; k < 3; ++k)
+          n[k] = sqrt((q[k][0] - a[0]) * (q[k][0] - a[0]) + (q[k][1] - a[1]) * (q[k][1] - a[1]) +
+                      (q[k][2] - a[2]) * (q[k][2] - a[2]));
+        const double scale = n[0] * n[1] * n[2];
+        const double margin = scale <= OKIN_GEOM_EPS ? 0.0 : vol / scale;
+        const int sv = (vol > 0.0) - (vol < 0.0), sd = (design > 0.0) - (design < 0.0);
+        if (fabs(margin) <= OKIN_GEOM_EPS) flags = OKIN_DIAG_CHIRALITY_BOUNDARY;
+        else if (sv != sd) flags = OKIN_DIAG_CHIRALITY_INVERTED;
+        row[col] = vol;
+        row[col + 1] = margin;
+        row[col + 2] = flags == OKIN_DIAG_CHIRALITY_BOUNDARY ? 1.0 : (flags ? 2.0 : 0.0);
+      } else {  // OKIN_DG_TRANSMISSION (axle/mechanisms.py:143-163)
+        const double* drv = pos + 3 * OKIN_LDG(rec + 1);
+        const double* a = pos + 3 * OKIN_LDG(rec + 2);
+        const double* b = pos + 3 * OKIN_LDG(rec + 3);
+        const double* l0 = pos + 3 * OKIN_LDG(rec + 4);
+        const double* l1 = pos + 3 * OKIN_LDG(rec + 5);
+        double ax[3], lk[3], rad[3];
+        for (int k = 0; k < 3; ++k) { ax[k] = b[k] - a[k]; lk[k] = l1[k] - l0[k]; rad[k] = drv[k] - a[k]; }
+        const double an = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+        const double ln = sqrt(lk[0] * lk[0] + lk[1] * lk[1] + lk[2] * lk[2]);
+        double margin = NAN;
+        if (an != 0.0 && ln != 0.0) {
+          for (int k = 0; k < 3; ++k) ax[k] /= an;
+          const double along = rad[0] * ax[0] + rad[1] * ax[1] + rad[2] * ax[2];
+          for (int k = 0; k < 3; ++k) rad[k] -= ax[k] * along;
+          const double tg[3] = {ax[1] * rad[2] - ax[2] * rad[1], ax[2] * rad[0] - ax[0] * rad[2],
+                                ax[0] * rad[1] - ax[1] * rad[0]};
+          const double tn = sqrt(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]);
+          if (tn != 0.0) margin = fabs((lk[0] * tg[0] + lk[1] * tg[1] + lk[2] * tg[2]) / (ln * tn));
+        }
+        if (margin < OKIN_TRANSMISSION_WARN) flags = OKIN_DIAG_TRANSMISSION;
+        row[col] = margin;
+      }
+      red[t & 31] = (double)((int)red[t & 31] | flags);
+    }
+    OKIN_PHASE_END
+  }
+  OKIN_PHASE_BEGIN
+  if (lane == 0) {
+    int flags = 0;
+    for (int k = 0; k < 32; ++k) flags |= (int)red[k];
+    if (!ok && status == OKIN_STATUS_RESIDUAL_REJECTED) flags |= OKIN_DIAG_RESIDUAL;
+    else if (!ok && status != OKIN_STATUS_OK) flags |= OKIN_DIAG_NOT_CONVERGED;
+    row[0] = (double)flags;
+  }
+  OKIN_PHASE_END
+}
+
+// Continuity check of one instance (diagnostics.py:176-226): per free point the Euclidean
+// displacement of every sweep transition, the median of the non-zero ones, threshold
+// max(5 mm, 4 x median); displacements above it are jumps into the later step.
+//   scratch   [32][stride] doubles + [32] thresholds + [32] slots (stride >= n_steps - 1)
+//   positions [n_steps][NOUT*3] of this instance; n_ok solved states lead the rows
+//   diag      [n_steps][NDIAG] rows of this instance (columns 0..4 updated)
+//   jumps     optional [n_steps][NF]: row 0 = each point's threshold, row s>0 = displacement into
+//             step s where it exceeded the threshold, else 0
+template <typename Dummy = void>
+OKIN_HD void okin_continuity(const OkinProgram& pr, double* scratch, int stride, const double* positions,
+                             int n_steps, int n_ok, double* diag, double* jumps) {
+  const int32_t* hdr = pr.hdr;
+  const int nf = hdr[OKIN_H_NF], nout3 = 3 * hdr[OKIN_H_NOUT], nd = hdr[OKIN_H_NDIAG];
+  const int32_t* free_out = okin_sec(pr, OKIN_S_FREE_OUT);
+  const int ntr = n_ok > 1 ? n_ok - 1 : 0;
+  double* thr = scratch + 32 * stride;
+  double* slots = thr + 32;
+  if (jumps) {
+    OKIN_PHASE_BEGIN
+    for (int t = lane; t < n_steps * nf; t += 32) jumps[t] = 0.0;
+    OKIN_PHASE_END
+  }
+  for (int base = 0; base < nf; base += 32) {
+    OKIN_PHASE_BEGIN     // lane = free point: displacement history, median, threshold
+    const int k = base + lane;
+    const int slot = k < nf ? OKIN_LDG(free_out + k) : -1;
+    double* d = scratch + lane * stride;
+    double threshold = INFINITY;
+    if (slot >= 0 && ntr > 0) {
+      const double* p = positions + 3 * slot;
+      double px = p[0], py = p[1], pz = p[2];
+      int nz = 0;
+      for (int t = 0; t < ntr; ++t) {
+        const double* c = p + (size_t)(t + 1) * nout3;
+        const double dx = c[0] - px, dy = c[1] - py, dz = c[2] - pz;
+        d[t] = sqrt(dx * dx + dy * dy + dz * dz);
+        nz += d[t] > 0.0;
+        px = c[0]; py = c[1]; pz = c[2];
+      }
+      double med = 0.0;
+      if (nz > 0) {  // statistics.median of the non-zero displacements
+        const int lo = (nz - 1) / 2, hi = nz / 2;
+        double vlo = 0.0, vhi = 0.0;
+        for (int i = 0; i < ntr; ++i) {
+          const double di = d[i];
+          if (!(di > 0.0)) continue;
+          int rank = 0;
+          for (int j = 0; j < ntr; ++j) {
+            const double dj = d[j];
+            rank += (dj > 0.0) && (dj < di || (dj == di && j < i));
+          }
+          if (rank == lo) vlo = di;
+          if (rank == hi) vhi = di;
+        }
+        med = 0.5 * (vlo + vhi);
+      }
+      threshold = fmax(OKIN_JUMP_FLOOR_MM, OKIN_JUMP_MEDIAN_FACTOR * med);
+      if (jumps) {
+        jumps[k] = threshold;
+        for (int t = 0; t < ntr; ++t)
+          if (d[t] > threshold) jumps[(size_t)(t + 1) * nf + k] = d[t];
+      }
+    }
+    thr[lane] = threshold;
+    slots[lane] = (double)slot;
+    OKIN_PHASE_END
+    OKIN_PHASE_BEGIN     // lane = transition: fold this group of points into the step's row
+    for (int t = lane; t < ntr; t += 32) {
+      double* row = diag + (size_t)(t + 1) * nd;
+      double count = row[1], worst = row[2], wslot = row[3], wthr = row[4];
+      for (int q = 0; q < 32; ++q) {
+        if (slots[q] < 0.0) continue;
+        const double v = scratch[q * stride + t];
+        if (v > thr[q]) {
+          count += 1.0;
+          if (v > worst) { worst = v; wslot = slots[q]; wthr = thr[q]; }
+        }
+      }
+      if (count > row[1]) {
+        row[0] = (double)((int)row[0] | OKIN_DIAG_JUMP);
+        row[1] = count; row[2] = worst; row[3] = wslot; row[4] = wthr;
+      }
+    }
+    OKIN_PHASE_END
+  }
+}
+
 // z = L^T x (lt) or x = L z (plain) with the block factor; returns |result|^2 (warp-uniform).
 template <typename Dummy = void>
 OKIN_FN double okin_factor_multiply(const OkinProgram& pr, double* sm, const double* src, double* dst, bool lt) {
@@ -1386,6 +1568,7 @@ struct OkinOutputs {
   double* health;         // [n_steps][2] {sigma_min, cond} of the tangent system, or null
   double* metrics;        // [n_steps][NM] or null (NaN == the reference's None)
   double* design;         // [NOUT*3] design (setup) pose or null
+  double* diagnostics;    // [n_steps][NDIAG] or null
   int32_t* status;        // [1]
   int32_t* failed_step;   // [1]
 };
@@ -1515,6 +1698,9 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
     }
+    if (out.diagnostics && hdr[OKIN_H_NDIAG])
+      okin_diagnostics(pr, sm, out.diagnostics + (size_t)s * hdr[OKIN_H_NDIAG], ok,
+                       failed == s ? status : OKIN_STATUS_OK);
     if (out.health) {
       if (ok) {
         okin_tangent_health(pr, sm, st.notpd != 0, out.health + 2 * s);

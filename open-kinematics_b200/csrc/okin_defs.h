@@ -59,6 +59,22 @@
 #define OKIN_RULE_TARGET_BASE 3  // c[3] = dir . design position (relative target), else 0
 
 // Per-instance status (okin_solve_batch status_out).
+// Sweep diagnostics (reference core/diagnostics.py:136-226, axle/mechanisms.py:119-163, :432-549).
+// Per state: column 0 = OKIN_DIAG_* flag bits (as a double), 1 = number of free points that jumped
+// into this step, 2 = largest such displacement (mm), 3 = its output point slot, 4 = its
+// threshold; then the topology columns of the diagnostic ops.
+#define OKIN_DIAG_BASE 5
+#define OKIN_DIAG_NOT_CONVERGED 1
+#define OKIN_DIAG_RESIDUAL 2
+#define OKIN_DIAG_JUMP 4
+#define OKIN_DIAG_CHIRALITY_BOUNDARY 8
+#define OKIN_DIAG_CHIRALITY_INVERTED 16
+#define OKIN_DIAG_TRANSMISSION 32
+// diagnostic op record: {kind, p0..p4, column, design slots d0..d3}
+#define OKIN_DGOP_STRIDE 12
+#define OKIN_DG_CHIRALITY 0      // points axis_a, axis_b, rocker pickup, bar pickup -> (signed volume, margin, 0 ok | 1 boundary | 2 inverted)
+#define OKIN_DG_TRANSMISSION 1   // points driven, axis_a, axis_b, link_from, link_to -> margin (NaN = undefined)
+
 #define OKIN_STATUS_OK 0
 #define OKIN_STATUS_NOT_CONVERGED 1
 #define OKIN_STATUS_RESIDUAL_REJECTED 2
@@ -107,6 +123,8 @@ enum okin_hdr_slot {
   OKIN_H_NDROW,    // distance rows on the fast evaluation path
   OKIN_H_NGROW,    // rows on the generic evaluation path (ROW_ORDER entries)
   OKIN_H_OFF_PPREV2,  // second predictor-history vector
+  OKIN_H_NDIAG,    // diagnostic columns per state (OKIN_DIAG_BASE + topology columns), 0 = no program
+  OKIN_H_NDGOP,    // topology diagnostic ops
   OKIN_H_SEC0 = 64,                      // room for 64 scalar slots,
   OKIN_H_FSEC0 = 64 + 2 * 64,            // 64 int32 sections
   OKIN_HDR_SIZE = 64 + 2 * 64 + 2 * 8    // and 8 double sections
@@ -157,6 +175,8 @@ enum okin_isec {
   OKIN_S_SHIM_PTS,       // point lists referenced by SHIM (upright attachments, rocker group)
   OKIN_S_DROW,           // [3][NDROW] = {p0 | p1 << 16}, {cst_off | rg_off << 16}, {row}: plain distance rows
   OKIN_S_DIAG_OFF,       // [NF] shared-memory offset of the diagonal block of elimination column j
+  OKIN_S_FREE_OUT,       // [NF] output slot of free point k (reference column order), -1 = not exported
+  OKIN_S_DGOP,           // [NDGOP][OKIN_DGOP_STRIDE] topology diagnostic ops
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000

@@ -27,11 +27,21 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
     out.health = io->tangent_health ? io->tangent_health + (size_t)i * n_steps * 2 : nullptr;
     out.metrics = io->metrics ? io->metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
     out.design = io->design ? io->design + (size_t)i * 3 * nout : nullptr;
+    const int nd = hdr[OKIN_H_NDIAG];
+    out.diagnostics = (io->diagnostics && nd) ? io->diagnostics + (size_t)i * n_steps * nd : nullptr;
     out.status = io->status + i;
     out.failed_step = io->failed_step + i;
     okin_sweep(pr, sm.data(), io->hardpoints + (size_t)i * 3 * nin,
                io->params ? io->params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, io->target_values, n_steps, cfg,
                out);
+    if (out.diagnostics && n_steps > 0) {  // continuity pass, as the product's second kernel does
+      const int stride = (n_steps - 1) | 1;
+      std::vector<double> scratch((size_t)32 * stride + 64);
+      const int failed = io->failed_step[i];
+      okin_continuity(pr, scratch.data(), stride, io->positions + (size_t)i * n_steps * 3 * nout, n_steps,
+                      failed < 0 ? n_steps : failed, out.diagnostics,
+                      io->jumps ? io->jumps + (size_t)i * n_steps * (n / 3) : nullptr);
+    }
   }
   return 0;
 }

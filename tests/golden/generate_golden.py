@@ -16,6 +16,8 @@ Per sweep case:
   velocities         TangentField.velocities of every point (sorted keys)    [S, T, P, 3]
   tangent_rank / tangent_sigma_min / tangent_cond                               [S]
 Per family: residual + jacobian rows at seeded random points (core/constraints.py, core/jacobians.py).
+Diagnostics: diagnose_sweep issues, continuity thresholds and U-bar chirality / transmission
+quantities on sweeps with an uneven step (diagnostics.json / .npz).
 Failure cases: first failed step and failure class for out-of-reach sweeps.
 """
 
@@ -336,6 +338,94 @@ def run_families() -> None:
     print("families:", sorted(recs))
 
 
+# --------------------------------------------------------------------------- sweep diagnostics
+def values_sweep(targets: list) -> dict:
+    """Sweep with explicit per-step values: [(point, side, axis, [values...]), ...]."""
+    out = []
+    for point, side, axis, values in targets:
+        t = {"point": point, "direction": {"axis": axis}, "mode": "relative", "values": [float(v) for v in values]}
+        if side:
+            t["side"] = side
+        out.append(t)
+    return {"version": 1, "targets": out}
+
+
+def run_diagnostics() -> None:
+    """diagnose_sweep (core/diagnostics.py:118-134) on sweeps with a deliberately uneven step (a
+    jump), plus the U-bar chirality / transmission quantities per state."""
+    from statistics import median
+
+    from kinematics.core.diagnostics import (CONTINUITY_ABS_FLOOR_MM, CONTINUITY_MEDIAN_FACTOR, diagnose_sweep,
+                                             _point_step_displacements)
+    from kinematics.core.primitives.point_ref import PointRef, Side
+    from kinematics.core.suspensions.axle.mechanisms import (ArbUBar, calculate_arb_branch_volume,
+                                                            calculate_arb_chirality_margin,
+                                                            calculate_transmission_margin)
+    c1 = load("tests/data/geometry.yaml")
+    c3 = add_coilovers(load("tests/data/axle_geometry_rocker.yaml"))
+    z1 = [0, 2, 4, 6, 8, 10, 12, 14, 16, 50, 52, 54]
+    z3 = [-4, -2, 0, 2, 4, 6, 30, 32]
+    cases = {
+        "c1_uneven_bump": (c1, values_sweep([("trackrod_inboard", None, "y", [0.0] * len(z1)),
+                                             ("wheel_center", None, "z", z1)])),
+        "c3_uneven_roll": (c3, values_sweep([("wheel_center", "left", "z", z3),
+                                             ("wheel_center", "right", "z", [-v for v in z3]),
+                                             ("trackrod_inboard", "left", "y", [0.0] * len(z3))])),
+        "c3_roll_pm45": (c3, roll_sweep(19, 45.0)),
+    }
+    out, arrays = {}, {}
+    for label, (geom, sweep) in cases.items():
+        sus = build_suspension(geom)
+        cfg = build_sweep(sweep, sus)
+        init = sus.initial_state()
+        states, stats = solve_suspension_sweep(init, sus.constraints(), cfg, DerivedPointsManager(sus.derived_spec()), TIGHT)
+        report = diagnose_sweep(sus, states, stats)
+        issues = [{"step": i.step, "category": str(i.category.value), "severity": str(i.severity.value),
+                   "value": i.value, "message": i.message} for i in report.issues]
+        thresholds = {}
+        for key in sus.free_points():
+            disp = _point_step_displacements(states, key)
+            nonzero = [d for d in disp if d > 0]
+            thresholds[key_name(key)] = max(CONTINUITY_ABS_FLOOR_MM,
+                                            CONTINUITY_MEDIAN_FACTOR * (median(nonzero) if nonzero else 0.0))
+        rec = {"geometry": geom, "sweep": sweep, "issues": issues, "thresholds": thresholds,
+               "free_points": [key_name(k) for k in sus.free_points()]}
+        arb = getattr(sus, "anti_roll", None)
+        if isinstance(arb, ArbUBar):
+            cols, names = [], []
+            for side in (Side.LEFT, Side.RIGHT):
+                tag = side.name.lower()
+                names += [f"arb_branch_volume_{tag}", f"arb_chirality_margin_{tag}",
+                          f"transmission_droplink_at_droplink_u_bar_{tag}",
+                          f"transmission_pushrod_at_pushrod_inboard_{tag}",
+                          f"transmission_droplink_at_droplink_rocker_{tag}"]
+            for st in states:
+                row = []
+                a = st.get(PointRef(Side.CENTER, PointID.ARB_U_BAR_AXIS_A)).data
+                b = st.get(PointRef(Side.CENTER, PointID.ARB_U_BAR_AXIS_B)).data
+                for side in (Side.LEFT, Side.RIGHT):
+                    pt = lambda pid: st.get(PointRef(side, pid)).data   # noqa: E731
+                    drop = pt(PointID.DROPLINK_U_BAR) - pt(PointID.DROPLINK_ROCKER)
+                    ra = pt(PointID.ROCKER_AXIS_A)
+                    rax = pt(PointID.ROCKER_AXIS_B) - ra
+                    push = pt(PointID.PUSHROD_OUTBOARD) - pt(PointID.PUSHROD_INBOARD)
+                    margins = [calculate_transmission_margin(pt(PointID.DROPLINK_U_BAR), a, b - a, drop),
+                               calculate_transmission_margin(pt(PointID.PUSHROD_INBOARD), ra, rax, push),
+                               calculate_transmission_margin(pt(PointID.DROPLINK_ROCKER), ra, rax, drop)]
+                    row += [calculate_arb_branch_volume(st, side), calculate_arb_chirality_margin(st, side),
+                            *[np.nan if m is None else m for m in margins]]
+                cols.append(row)
+            arrays[label + "_columns"] = np.array(cols)
+            rec["column_names"] = names
+        keys = sorted(init.positions)
+        arrays[label + "_positions"] = positions_array(states, keys)
+        rec["point_keys"] = [key_name(k) for k in keys]
+        out[label] = rec
+        print(label, "issues:", [(i["step"], i["category"]) for i in issues])
+    json.dump(out, open(os.path.join(OUT, "diagnostics.json"), "w"), indent=1)
+    np.savez_compressed(os.path.join(OUT, "diagnostics.npz"), **arrays)
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for case, (g, s) in CASES.items():
@@ -349,3 +439,5 @@ if __name__ == "__main__":
         run_failures()
     if not only or "families" in only:
         run_families()
+    if not only or "diagnostics" in only:
+        run_diagnostics()

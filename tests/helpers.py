@@ -155,6 +155,8 @@ def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, 
         "status": np.zeros(n_inst, np.int32), "failed_step": np.zeros(n_inst, np.int32),
         "metrics": np.zeros((n_inst, n_steps, len(program.metric_names))) if program.metric_names else None,
         "design": np.zeros((n_inst, program.n_out, 3)),
+        "diagnostics": np.zeros((n_inst, n_steps, len(program.diagnostic_names))) if program.diagnostic_names else None,
+        "jumps": np.zeros((n_inst, n_steps, n // 3)) if program.diagnostic_names else None,
     }
     par = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
     settings = dict(step_tol=1e-6, coarse_tol=1e-3, fine_tol=1e-4, residual_tol=1e-3, mu_init=1e-3, max_iter=50,

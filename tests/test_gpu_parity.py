@@ -224,3 +224,131 @@ def test_per_instance_shim_thickness_batch():
     assert np.all(steps > 0) or np.all(steps < 0)
     assert abs(met[order_t[-1], mid, cam] - met[order_t[0], mid, cam]) > 0.1
     solver.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Boundaries B2 (compute_state_tangents) and B3 (compute_state_metrics) and the sweep facade,
+# called with the reference's own call shapes on states built from the golden tight run.
+# ---------------------------------------------------------------------------------------------
+def _golden_states(sus, meta, arr, steps):
+    from open_kinematics_b200.core.primitives.geometry import Point3
+    from open_kinematics_b200.core.state import SuspensionState
+    keys = [key_from_name(n) for n in meta["point_keys"]]
+    free = set(sus.initial_state().free_points)
+    return [SuspensionState(positions={k: Point3(arr["positions_tight"][s, i]) for i, k in enumerate(keys)},
+                            free_points=set(free)) for s in steps], keys
+
+
+@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll"])
+def test_reference_boundary_compute_state_tangents(case):
+    from open_kinematics_b200.core.points.derived.manager import DerivedPointsManager
+    from open_kinematics_b200.core.sensitivity import TangentField, TangentSolveInfo, compute_state_tangents
+    from open_kinematics_b200.core.solver import convert_targets_to_absolute
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    steps = [0, sweep.n_steps // 2, sweep.n_steps - 1]
+    states, keys = _golden_states(sus, meta, arr, steps)
+    initial, constraints = sus.initial_state(), sus.constraints()
+    manager = DerivedPointsManager(sus.derived_spec())
+    for s, state in zip(steps, states):
+        before = {k: p.data.copy() for k, p in state.positions.items()}
+        targets = convert_targets_to_absolute([dim[s] for dim in sweep.target_sweeps], initial)
+        fields, info = compute_state_tangents(state, constraints, manager, targets)
+        assert all(np.array_equal(before[k], state.positions[k].data) for k in before)
+        assert isinstance(info, TangentSolveInfo) and not info.rank_deficient
+        assert info.n_variables == meta["n_unknowns"] == info.rank
+        assert 1 - 1e-5 <= info.smallest_singular_value / arr["tangent_sigma_min"][s] <= 1.05
+        assert 0.9 <= info.condition_number / arr["tangent_cond"][s] <= 1 + 1e-5
+        assert len(fields) == len(targets) and all(isinstance(f, TangentField) for f in fields)
+        for j, f in enumerate(fields):
+            assert f.target_index == j and f.target == targets[j]
+            got = np.array([f.velocity(k) for k in keys])
+            assert np.abs(got - arr["velocities"][s, j]).max() <= 1e-7 * max(1.0, np.abs(arr["velocities"]).max())
+    assert compute_state_tangents(states[0], constraints, manager, []) == (
+        [], TangentSolveInfo(n_variables=0, rank=0, smallest_singular_value=0.0, condition_number=1.0))
+
+
+@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c4_tbar_heave_shim_roll"])
+def test_reference_boundary_metrics_of_solved_states(case):
+    """compute_sweep_metrics / compute_sweep_tangents / compute_state_metrics on given states."""
+    from open_kinematics_b200.core.metrics.main import AxleMetricRows
+    from open_kinematics_b200.core.sweep import compute_sweep_metrics, compute_sweep_tangents
+    from test_emu_metrics import check_metrics
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    states, keys = _golden_states(sus, meta, arr, range(sweep.n_steps))
+    result = compute_sweep_metrics(sus, sweep, states)
+    assert result.derivative_error is None and len(result.rows) == sweep.n_steps
+    assert all(not info.rank_deficient for info in result.tangent_solve_infos)
+    flat = [row.flat_row() if isinstance(row, AxleMetricRows) else row for row in result.rows]
+    assert isinstance(result.rows[0], AxleMetricRows) == sus.is_axle
+    assert all(list(r.keys()) == meta["metric_names"] for r in flat)
+    got = np.array([[np.nan if r[k] is None else r[k] for k in meta["metric_names"]] for r in flat])
+    check_metrics(meta["metric_names"], got, arr["metrics"])
+
+    tangents = compute_sweep_tangents(sus, sweep, states)
+    assert len(tangents.per_step) == len(tangents.solve_infos) == sweep.n_steps
+    s = sweep.n_steps - 1
+    vel = np.array([[f.velocity(k) for k in keys] for f in tangents.per_step[s]])
+    assert np.abs(vel - arr["velocities"][s]).max() <= 1e-7 * max(1.0, np.abs(arr["velocities"]).max())
+
+    # one state, with and without tangents (derivative columns only with tangents)
+    row = sus.compute_state_metrics(states[s], tangents.per_step[s])
+    flat_row = row.flat_row() if isinstance(row, AxleMetricRows) else row
+    got1 = np.array([[np.nan if flat_row[k] is None else flat_row[k] for k in meta["metric_names"]]])
+    check_metrics(meta["metric_names"], got1, arr["metrics"][s:s + 1])
+    bare = sus.compute_state_metrics(states[s])
+    bare = bare.flat_row() if isinstance(bare, AxleMetricRows) else bare
+    assert list(bare.keys()) == [k for k in meta["metric_names"] if not k.startswith("deriv_")]
+    assert all(bare[k] == flat_row[k] or abs(bare[k] - flat_row[k]) <= 1e-9 * max(1.0, abs(flat_row[k]))
+               for k in bare if flat_row[k] is not None)
+
+
+def test_sweep_diagnostics_match_reference():
+    """diagnose_sweep issue for issue, continuity thresholds and U-bar quantities against the
+    reference on sweeps with an uneven step (tests/golden/diagnostics.*), plus the batch arrays."""
+    from open_kinematics_b200.core.diagnostics import DiagnosticCategory, diagnose_sweep
+    from open_kinematics_b200.core.sweep import BatchSolver, solve_evaluated_sweep, solve_sweep
+    from open_kinematics_b200.csrc_defs import D
+    cases = json.load(open(os.path.join(GOLDEN, "diagnostics.json")))
+    arrays = np.load(os.path.join(GOLDEN, "diagnostics.npz"))
+    for label, rec in cases.items():
+        sus, sweep = build_case(rec)
+        states, stats = solve_sweep(sus, sweep)
+        report = diagnose_sweep(sus, states, stats)
+        got = [(i.step, str(i.category.value), str(i.severity.value), i.message) for i in report.issues]
+        ref = [(i["step"], i["category"], i["severity"], i["message"]) for i in rec["issues"]]
+        assert got == ref, label
+        for i, r in zip(report.issues, rec["issues"]):
+            assert abs(i.value - r["value"]) <= 1e-6 * max(1.0, abs(r["value"]))
+        assert report.ok == (not any(r["severity"] == "error" for r in rec["issues"]))
+
+        # batch arrays: the nominal instance twice
+        solver = BatchSolver(sus, sweep)
+        try:
+            hp = np.repeat(solver.nominal_hardpoints()[None, :], 2, axis=0)
+            res = solver.solve(hp, want_diagnostics=True)
+        finally:
+            solver.close()
+        prog = solver.program
+        assert res.diagnostics.shape == (2, sweep.n_steps, len(prog.diagnostic_names))
+        assert np.array_equal(res.diagnostics[0], res.diagnostics[1], equal_nan=True)
+        thresholds = np.array([rec["thresholds"][k.name.lower()] for k in prog.free_order])
+        assert np.abs(res.jumps[0, 0] - thresholds).max() <= 1e-6
+        jump_steps = sorted({r["step"] for r in rec["issues"] if r["category"] == "jump"})
+        flagged = [s for s in range(sweep.n_steps) if int(res.diagnostics[0, s, 0]) & D["OKIN_DIAG_JUMP"]]
+        assert flagged == jump_steps
+        for s in jump_steps:
+            n_ref = sum(1 for r in rec["issues"] if r["category"] == "jump" and r["step"] == s)
+            worst = max(r["value"] for r in rec["issues"] if r["category"] == "jump" and r["step"] == s)
+            assert res.diagnostics[0, s, 1] == n_ref and abs(res.diagnostics[0, s, 2] - worst) <= 1e-6
+        if "column_names" in rec:
+            cols = [prog.diagnostic_names.index(n) for n in rec["column_names"]]
+            ref_cols = arrays[label + "_columns"]
+            got_cols = res.diagnostics[0][:, cols]
+            assert np.abs(got_cols - ref_cols).max() <= 1e-6 * max(1.0, np.abs(ref_cols).max())
+    # facade: solve + metrics + diagnostics in one call
+    sus, sweep = build_case(cases["c1_uneven_bump"])
+    evaluated = solve_evaluated_sweep(sus, sweep)
+    assert len(evaluated.states) == len(evaluated.metrics.rows) == sweep.n_steps
+    assert [i.category for i in evaluated.diagnostics] == [DiagnosticCategory.JUMP] * 5
