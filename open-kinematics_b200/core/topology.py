@@ -640,6 +640,11 @@ def compile_topology(
         pts = row.points + [-1] * (4 - len(row.points))
         rec = [row.fam, *pts, row.cst_off, row.rg_off, len(row.eff), row.rule, *row.slotmap, row.aux]
         row_tab.append(rec + [0] * (D["OKIN_ROW_STRIDE"] - len(rec)))
+    row_hot = []
+    for i in row_order:
+        rec = list(row_tab[i])
+        rec[D["OKIN_R_ROWID"]] = i
+        row_hot.append(rec)
     cst_init = [v for row in rows for v in row.consts]
 
     point_elim = [-1] * P
@@ -699,9 +704,18 @@ def compile_topology(
         "OKIN_S_SHIM": shim_recs, "OKIN_S_SHIM_PTS": shim_pts,
         "OKIN_S_FREE_OUT": free_out, "OKIN_S_DGOP": dprog.ops if dprog else [],
     }
+    isecs["OKIN_S_ROW_HOT"] = row_hot
+    # Cold sections (setup, outputs requested per state, metrics, diagnostics) go last: the kernel
+    # copies only the hot prefix of the blob to shared memory.
+    cold = ["OKIN_S_ROW", "OKIN_S_ROW_ORDER", "OKIN_S_IN_POINT", "OKIN_S_PAR_MODE", "OKIN_S_POINT_KIND",
+            "OKIN_S_DESIGN_PT", "OKIN_S_POINT_ELIM", "OKIN_S_POINT_DOP", "OKIN_S_MCORNER", "OKIN_S_MOP",
+            "OKIN_S_MAXLE", "OKIN_S_SHIM", "OKIN_S_SHIM_PTS", "OKIN_S_FREE_OUT", "OKIN_S_DGOP", "OKIN_S_ELIM_COL"]
+    isecs = {**{k: v for k, v in isecs.items() if k not in cold}, **{k: isecs[k] for k in cold}}
     hdr = np.zeros(D["OKIN_HDR_SIZE"], np.int32)
-    chunks, cursor = [], 0
+    chunks, cursor, n_hot = [], 0, None
     for name, data in isecs.items():
+        if name == cold[0]:
+            n_hot = cursor
         arr = np.asarray(data, dtype=np.int64).reshape(-1)
         if arr.size and (arr.max() > 2**32 - 1 or arr.min() < -(2**31)):
             raise ValueError(f"section {name} overflows 32 bits")
@@ -734,7 +748,7 @@ def compile_topology(
         "OKIN_H_NMC": len(mcorners), "OKIN_H_NMOP": len(mops), "OKIN_H_NMAXLE": len(maxle), "OKIN_H_NDSN": ndsn,
         "OKIN_H_NSHIM": len(shim_recs), "OKIN_H_NPARAM": len(param_default),
         "OKIN_H_NDROW": len(fast_rows), "OKIN_H_NGROW": len(row_order),
-        "OKIN_H_NDIAG": len(dprog.names) if dprog else 0, "OKIN_H_NDGOP": len(dprog.ops) if dprog else 0,
+        "OKIN_H_NHOT": n_hot, "OKIN_H_NDIAG": len(dprog.names) if dprog else 0, "OKIN_H_NDGOP": len(dprog.ops) if dprog else 0,
         **layout,
     }
     for name, value in counts.items():

@@ -80,10 +80,11 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
   int32_t* shdr = reinterpret_cast<int32_t*>(okin_smem);
   int32_t* tab = shdr + OKIN_HDR_SIZE;
   for (int i = threadIdx.x; i < OKIN_HDR_SIZE; i += blockDim.x) shdr[i] = hdr[i];
-  for (int i = threadIdx.x; i < n_iblob; i += blockDim.x) tab[i] = ib[i];
+  const int n_hot = hdr[OKIN_H_NHOT];
+  for (int i = threadIdx.x; i < n_hot; i += blockDim.x) tab[i] = ib[i];
   __syncthreads();
   hdr = shdr;
-  OkinProgram pr{shdr, tab, fb};
+  OkinProgram pr{shdr, tab, fb, ib};
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   double* sm = okin_smem + table_doubles + (size_t)warp * hdr[OKIN_H_SMEM_DOUBLES];
@@ -123,7 +124,7 @@ __global__ void okin_continuity_kernel(const int32_t* __restrict__ hdr, const in
                                        const double* __restrict__ positions, const int32_t* __restrict__ failed_step,
                                        double* diag, double* jumps) {
   extern __shared__ double okin_smem[];
-  OkinProgram pr{hdr, ib, nullptr};
+  OkinProgram pr{hdr, ib, nullptr, ib};
   const int warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
   double* scratch = okin_smem + (size_t)warp * (32 * stride + 64);
   const size_t nout3 = 3 * (size_t)hdr[OKIN_H_NOUT], nd = hdr[OKIN_H_NDIAG], nf = hdr[OKIN_H_NF];
@@ -168,7 +169,7 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
     d.smem_optin = (int)prop.sharedMemPerBlockOptin;
     // CTA shape: W warps sharing one copy of the tables; pick the W that keeps the most warps resident
     // (shared memory, the 64K-register file at OKIN_REGS_PER_THREAD, 1 KB per-CTA reservation).
-    d.table_doubles = (int)(((t->ib.size() + OKIN_HDR_SIZE) * sizeof(int32_t) + 7) / 8);
+    d.table_doubles = (int)((((size_t)t->hdr[OKIN_H_NHOT] + OKIN_HDR_SIZE) * sizeof(int32_t) + 7) / 8);
     const size_t table_bytes = (size_t)d.table_doubles * 8;
     const size_t slice_bytes = (size_t)t->hdr[OKIN_H_SMEM_DOUBLES] * sizeof(double);
     const size_t sm_budget = prop.sharedMemPerMultiprocessor;
@@ -291,6 +292,8 @@ int okin_topology_create(const okin_topology_desc* desc, okin_topology** out) {
     const int64_t off = desc->hdr[OKIN_H_FSEC0 + 2 * s], len = desc->hdr[OKIN_H_FSEC0 + 2 * s + 1];
     if (off < 0 || len < 0 || off + len > desc->n_fblob) return fail(OKIN_ERR_USAGE, "double section out of range");
   }
+  if (desc->hdr[OKIN_H_NHOT] < 0 || desc->hdr[OKIN_H_NHOT] > desc->n_iblob)
+    return fail(OKIN_ERR_USAGE, "hot prefix out of range");
   if (desc->hdr[OKIN_H_NT] > OKIN_MAX_TARGETS) return fail(OKIN_ERR_USAGE, "too many targets");
   okin_topology* t = new okin_topology();
   t->hdr.assign(desc->hdr, desc->hdr + OKIN_HDR_SIZE);

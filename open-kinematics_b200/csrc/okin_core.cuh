@@ -75,8 +75,9 @@ OKIN_HD double okin_red_max(const double* red) {
 
 struct OkinProgram {
   const int32_t* hdr;  // [OKIN_HDR_SIZE]
-  const int32_t* ib;   // int32 blob
+  const int32_t* ib;   // int32 blob: at least its hot prefix hdr[OKIN_H_NHOT] (shared memory in the kernel)
   const double* fb;    // double blob
+  const int32_t* ibc;  // whole int32 blob (global memory); cold sections are read from here
 };
 
 struct OkinSolverCfg {
@@ -90,7 +91,10 @@ struct OkinSolverCfg {
   int32_t use_predictor;  // continuation predictor order: 0 warm start only, 1..3 (Adams-Bashforth on the tangents)
 };
 
-OKIN_HD const int32_t* okin_sec(const OkinProgram& pr, int s) { return pr.ib + pr.hdr[OKIN_H_SEC0 + 2 * s]; }
+OKIN_HD const int32_t* okin_sec(const OkinProgram& pr, int s) {
+  const int off = pr.hdr[OKIN_H_SEC0 + 2 * s];
+  return (off < pr.hdr[OKIN_H_NHOT] ? pr.ib : pr.ibc) + off;
+}
 OKIN_HD int okin_sec_len(const OkinProgram& pr, int s) { return pr.hdr[OKIN_H_SEC0 + 2 * s + 1]; }
 OKIN_HD const double* okin_fsec(const OkinProgram& pr, int s) { return pr.fb + pr.hdr[OKIN_H_FSEC0 + 2 * s]; }
 
@@ -469,7 +473,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   if (with_grad) okin_derived_jacobians(pr, sm);
   const int nls = hdr[OKIN_H_NROW];
   const int nrows = nls + hdr[OKIN_H_NREP];
-  const int32_t* rows = okin_sec(pr, OKIN_S_ROW);
+  const int32_t* rows = okin_sec(pr, OKIN_S_ROW_HOT);
   const int32_t* der = okin_sec(pr, OKIN_S_DER);
   const double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* cst = sm + hdr[OKIN_H_OFF_CST];
@@ -477,7 +481,6 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   double* r = sm + hdr[OKIN_H_OFF_R];
   double* rg = sm + hdr[OKIN_H_OFF_RG];
   double* red = sm + hdr[OKIN_H_OFF_RED];
-  const int32_t* order = okin_sec(pr, OKIN_S_ROW_ORDER);
   const int32_t* drow = okin_sec(pr, OKIN_S_DROW);
   const int ndrow = hdr[OKIN_H_NDROW], ngrow = hdr[OKIN_H_NGROW];
   OKIN_PHASE_BEGIN
@@ -502,8 +505,8 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
     }
   }
   for (int slot = lane; slot < ngrow; slot += 32) {
-    const int t = OKIN_LDG(order + slot);
-    const int32_t* rec = rows + t * OKIN_ROW_STRIDE;
+    const int32_t* rec = rows + slot * OKIN_ROW_STRIDE;
+    const int t = OKIN_LDG(rec + OKIN_R_ROWID);
     const int fam = OKIN_LDG(rec + OKIN_R_FAM);
     const double* c = cst + OKIN_LDG(rec + OKIN_R_CST);
     double p[12], g[12];

@@ -123,6 +123,8 @@ enum okin_hdr_slot {
   OKIN_H_NDROW,    // distance rows on the fast evaluation path
   OKIN_H_NGROW,    // rows on the generic evaluation path (ROW_ORDER entries)
   OKIN_H_OFF_PPREV2,  // second predictor-history vector
+  OKIN_H_NHOT,     // int32 words of the hot prefix of the int blob (sections used inside the
+                   // iteration; the kernel keeps them in shared memory, the rest stays in global memory)
   OKIN_H_NDIAG,    // diagnostic columns per state (OKIN_DIAG_BASE + topology columns), 0 = no program
   OKIN_H_NDGOP,    // topology diagnostic ops
   OKIN_H_SEC0 = 64,                      // room for 64 scalar slots,
@@ -177,6 +179,8 @@ enum okin_isec {
   OKIN_S_DIAG_OFF,       // [NF] shared-memory offset of the diagonal block of elimination column j
   OKIN_S_FREE_OUT,       // [NF] output slot of free point k (reference column order), -1 = not exported
   OKIN_S_DGOP,           // [NDGOP][OKIN_DGOP_STRIDE] topology diagnostic ops
+  OKIN_S_ROW_HOT,        // [NGROW][OKIN_ROW_STRIDE] records of the generic-path rows in evaluation order
+                         // (grouped by family), each carrying its row index in OKIN_R_ROWID
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000
@@ -197,6 +201,7 @@ enum okin_row_slot {
   OKIN_R_RULE,  // design-constant rule
   OKIN_R_S0, OKIN_R_S1, OKIN_R_S2, OKIN_R_S3, // slot map: -1 none, <OKIN_SLOT_DER direct eff index, else derived descriptor
   OKIN_R_AUX,   // target index for target rows
+  OKIN_R_ROWID, // row index (OKIN_S_ROW_HOT records)
   OKIN_ROW_STRIDE = 17   // odd: lanes reading the same field of consecutive rows hit distinct banks
 };
 #define OKIN_SLOT_DER 64
