@@ -107,12 +107,7 @@ typedef struct okin_solver_cfg {
   double residual_tol;   /* default 1e-3 */
   double mu_init;        /* first Marquardt damping after a rejected step; default 1e-3 */
   int32_t max_iter;      /* factorisations per step; default 50 */
-  int32_t use_predictor; /* continuation predictor order 0..3 (Adams-Bashforth on the tangents when tangents
-                            are solved per state, polynomial extrapolation of the path otherwise); default 3 */
-  int32_t chord_max_age; /* sweep steps one factorisation is reused for chord iterations
-                            x <- x - (J0^T J0)^{-1} J0^T r(x) before the system is relinearised; 0 = never
-                            reuse; default 4 */
-  double chord_start_tol; /* mm; a first chord step larger than this hands over to Gauss-Newton; default 0.05 */
+  int32_t use_predictor; /* continuation predictor order 0..3 (Adams-Bashforth on the tangents); default 3 */
 } okin_solver_cfg;
 
 typedef struct okin_topology_info {

@@ -34,8 +34,7 @@ class SolverCfg(ctypes.Structure):
     _fields_ = [("step_tol", ctypes.c_double), ("coarse_tol", ctypes.c_double), ("fine_tol", ctypes.c_double),
                 ("residual_tol", ctypes.c_double),
                 ("mu_init", ctypes.c_double),
-                ("max_iter", ctypes.c_int32), ("use_predictor", ctypes.c_int32),
-                ("chord_max_age", ctypes.c_int32), ("chord_start_tol", ctypes.c_double)]
+                ("max_iter", ctypes.c_int32), ("use_predictor", ctypes.c_int32)]
 
 
 class BatchIO(ctypes.Structure):

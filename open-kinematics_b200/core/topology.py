@@ -539,36 +539,29 @@ def compile_topology(
     lev_cols = [[j for j in range(NF) if level[j] == lv] for lv in range(NLEV)]
     lev_upd, upd_dst, upd_ptr, upd_con = [0], [], [0], []
     lev_scl, scl = [0], []
-    lev_upd_t, lev_scl_t = [], []   # per level: where the tangent right-hand-side tasks start
     LB, VEC = "LB", "VEC"      # symbolic bases, resolved once the layout is known
     for lv in range(NLEV):
-        # matrix rows and the step right-hand side first, the tangent right-hand sides last, so
-        # that a factorisation that does not need tangents simply stops early in each level
-        for tangent_pass in (False, True):
-            for j in lev_cols[lv]:
-                if not tangent_pass:
-                    for i in [j] + struct[j]:
-                        ks = [k for k in cols_with[j] if i == j or i in struct[k]]
-                        if not ks:
-                            continue
-                        for r in range(3):
-                            upd_dst.append((LB, boff(i, j) + 3 * r))
-                            for k in ks:
-                                upd_con.append(((LB, boff(i, k) + 3 * r), (LB, boff(j, k))))
-                            upd_ptr.append(len(upd_con))
-                    for i in struct[j]:
-                        for r in range(3):
-                            scl.append(((LB, boff(j, j)), (LB, boff(i, j) + 3 * r)))
-                for rhs in ([0] if not tangent_pass else range(1, 1 + len(targets))):
-                    if cols_with[j]:
-                        upd_dst.append((VEC, rhs * 3 * NF + 3 * j))
-                        for k in cols_with[j]:
-                            upd_con.append(((VEC, rhs * 3 * NF + 3 * k), (LB, boff(j, k))))
-                        upd_ptr.append(len(upd_con))
-                    scl.append(((LB, boff(j, j)), (VEC, rhs * 3 * NF + 3 * j)))
-            if not tangent_pass:
-                lev_upd_t.append(len(upd_dst))
-                lev_scl_t.append(len(scl))
+        for j in lev_cols[lv]:
+            for i in [j] + struct[j]:
+                ks = [k for k in cols_with[j] if i == j or i in struct[k]]
+                if not ks:
+                    continue
+                for r in range(3):
+                    upd_dst.append((LB, boff(i, j) + 3 * r))
+                    for k in ks:
+                        upd_con.append(((LB, boff(i, k) + 3 * r), (LB, boff(j, k))))
+                    upd_ptr.append(len(upd_con))
+            if cols_with[j]:
+                for rhs in range(1 + len(targets)):     # carried right-hand sides: step + tangents
+                    upd_dst.append((VEC, rhs * 3 * NF + 3 * j))
+                    for k in cols_with[j]:
+                        upd_con.append(((VEC, rhs * 3 * NF + 3 * k), (LB, boff(j, k))))
+                    upd_ptr.append(len(upd_con))
+            for i in struct[j]:
+                for r in range(3):
+                    scl.append(((LB, boff(j, j)), (LB, boff(i, j) + 3 * r)))
+            for rhs in range(1 + len(targets)):
+                scl.append(((LB, boff(j, j)), (VEC, rhs * 3 * NF + 3 * j)))
         lev_upd.append(len(upd_dst))
         lev_scl.append(len(scl))
 
@@ -701,7 +694,6 @@ def compile_topology(
         "OKIN_S_G_PTR": g_ptr, "OKIN_S_G_CON": g_con,
         "OKIN_S_LEV_UPD": lev_upd, "OKIN_S_UPD_DST": upd_dst, "OKIN_S_UPD_PTR": upd_ptr, "OKIN_S_UPD_CON": upd_con,
         "OKIN_S_LEV_SCL": lev_scl, "OKIN_S_SCL": scl,
-        "OKIN_S_LEV_UPD_T": lev_upd_t, "OKIN_S_LEV_SCL_T": lev_scl_t,
         "OKIN_S_LEV_COL_PTR": lev_col_ptr, "OKIN_S_LEV_COL": lev_col,
         "OKIN_S_FW_PTR": fw_ptr, "OKIN_S_FW_CON": fw_con, "OKIN_S_BW_PTR": bw_ptr, "OKIN_S_BW_CON": bw_con,
         "OKIN_S_ELIM_POINT": elim_point, "OKIN_S_ELIM_COL": elim_col,

@@ -205,7 +205,7 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
            int32_t n_steps, const okin_batch_io& io) {
   if (n_instances == 0) return OKIN_OK;
   OkinSolverCfg c{cfg->step_tol, cfg->coarse_tol, cfg->fine_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter,
-                  cfg->use_predictor, cfg->chord_max_age, cfg->chord_start_tol};
+                  cfg->use_predictor};
   const int w = d->warps_per_cta;
   const int64_t needed = (n_instances + w - 1) / w;
   const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
@@ -276,8 +276,6 @@ int okin_default_cfg(okin_solver_cfg* out) {
   out->mu_init = 1e-3;
   out->max_iter = 50;
   out->use_predictor = 3;
-  out->chord_max_age = 4;
-  out->chord_start_tol = 0.05;
   return OKIN_OK;
 }
 

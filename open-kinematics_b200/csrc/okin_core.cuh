@@ -88,9 +88,7 @@ struct OkinSolverCfg {
   double residual_tol;  // accept a state when max|r| <= residual_tol   (reference constants.py:20)
   double mu_init;       // first Marquardt damping factor after a rejected Gauss-Newton step
   int32_t max_iter;     // factorisations per step before "not converged"
-  int32_t use_predictor;  // continuation predictor order: 0 warm start only, 1..3
-  int32_t chord_max_age;  // sweep steps a factorisation is reused for chord iterations (0: refactor every step)
-  double chord_start_tol; // a first chord step larger than this (mm) hands over to Gauss-Newton at once
+  int32_t use_predictor;  // continuation predictor order: 0 warm start only, 1..3 (Adams-Bashforth on the tangents)
 };
 
 OKIN_HD const int32_t* okin_sec(const OkinProgram& pr, int s) {
@@ -106,8 +104,6 @@ struct OkinState {
   double rmax;  // max|r| over all rows at the current point
   double mu;    // current damping (0 = pure Gauss-Newton)
   int notpd;    // factorisation hit a non-positive pivot
-  int factor_age;  // sweep steps since the factor / row gradients in shared memory were computed;
-                   // < 0: not usable for chord iterations (damped, failed, or overwritten)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -654,7 +650,7 @@ OKIN_HD void okin_write_diag_factor(double* sm, int doff, double* red, int lane)
 }
 
 template <typename Dummy = void>
-OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, bool carry_tangents) {
+OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
   const int32_t* hdr = pr.hdr;
   const int nlev = hdr[OKIN_H_NLEV];
   const int32_t* lev_upd = okin_sec(pr, OKIN_S_LEV_UPD);
@@ -666,15 +662,12 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, bool 
   const int32_t* lcp = okin_sec(pr, OKIN_S_LEV_COL_PTR);
   const int32_t* lcol = okin_sec(pr, OKIN_S_LEV_COL);
   const int32_t* doffs = okin_sec(pr, OKIN_S_DIAG_OFF);
-  // without tangents each level's task ranges stop before the tangent right-hand-side tasks
-  const int32_t* upd_end = carry_tangents ? lev_upd + 1 : okin_sec(pr, OKIN_S_LEV_UPD_T);
-  const int32_t* scl_end = carry_tangents ? lev_scl + 1 : okin_sec(pr, OKIN_S_LEV_SCL_T);
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   red[lane] = 0.0;
   OKIN_PHASE_END
   for (int lv = 0; lv <= nlev; ++lv) {
-    const int ub = lv < nlev ? OKIN_LDG(lev_upd + lv) : 0, ue = lv < nlev ? OKIN_LDG(upd_end + lv) : 0;
+    const int ub = lv < nlev ? OKIN_LDG(lev_upd + lv) : 0, ue = lv < nlev ? OKIN_LDG(lev_upd + lv + 1) : 0;
     const int wb = lv > 0 ? OKIN_LDG(lcp + lv - 1) : 0, we = lv > 0 ? OKIN_LDG(lcp + lv) : 0;
     if (ue > ub || we > wb) {
       OKIN_PHASE_BEGIN
@@ -700,7 +693,7 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, bool 
       OKIN_PHASE_END
     }
     if (lv == nlev) break;
-    const int sb = OKIN_LDG(lev_scl + lv), se = OKIN_LDG(scl_end + lv);
+    const int sb = OKIN_LDG(lev_scl + lv), se = OKIN_LDG(lev_scl + lv + 1);
     OKIN_PHASE_BEGIN
     for (int t = sb + lane; t < se; t += 32) {
       const uint32_t w = (uint32_t)OKIN_LDG(scl + t);
@@ -783,10 +776,9 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
   }
 }
 
-// pos[free] += scale * vec[which]; returns max|vec[which]| (warp-uniform).  acc (optional, elimination
-// order) accumulates the same increment: the displacement of this sweep step being built up.
+// pos[free] += scale * vec[which]; returns max|vec[which]| (warp-uniform).
 template <typename Dummy = void>
-OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, double scale, double* acc) {
+OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, double scale, bool save) {
   const int32_t* hdr = pr.hdr;
   const int n = 3 * hdr[OKIN_H_NF];
   const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
@@ -800,7 +792,6 @@ OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, dou
     const double x = pos[idx];
     const double h = v[u];
     pos[idx] = x + scale * h;
-    if (acc) acc[u] += scale * h;
     const double ah = fabs(h);
     mx = (ah > mx || ah != ah) ? ah : mx;
   }
@@ -810,17 +801,14 @@ OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, dou
 }
 
 template <typename Dummy = void>
-OKIN_FN void okin_restore(const OkinProgram& pr, double* sm, double* acc) {
+OKIN_FN void okin_restore(const OkinProgram& pr, double* sm) {
   const int32_t* hdr = pr.hdr;
   const int n = 3 * hdr[OKIN_H_NF];
   const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* h = sm + hdr[OKIN_H_OFF_VEC];   // the step just applied (vec[0], scale 1)
   OKIN_PHASE_BEGIN
-  for (int u = lane; u < n; u += 32) {
-    pos[3 * OKIN_LDG(ep + u / 3) + u % 3] -= h[u];
-    if (acc) acc[u] -= h[u];
-  }
+  for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(ep + u / 3) + u % 3] -= h[u];
   OKIN_PHASE_END
 }
 
@@ -870,29 +858,6 @@ OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, i
   OKIN_PHASE_END
 }
 
-// Continuation predictor without tangents: polynomial extrapolation of the solution path from the
-// displacements of the last `order` sweep steps (equal target increments): d1, 2 d1 - d2 or
-// 3 d1 - 3 d2 + d3.  The predicted displacement is written to `cur` (the accumulator of the step
-// that starts now; may alias the oldest history slot, which is read before it is written).
-template <typename Dummy = void>
-OKIN_FN void okin_extrapolate(const OkinProgram& pr, double* sm, int order, const double* d1, const double* d2,
-                              const double* d3, double* cur) {
-  const int32_t* hdr = pr.hdr;
-  const int n = 3 * hdr[OKIN_H_NF];
-  const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
-  double* pos = sm + hdr[OKIN_H_OFF_POS];
-  OKIN_PHASE_BEGIN
-  for (int u = lane; u < n; u += 32) {
-    double e = 0.0;
-    if (order == 1) e = d1[u];
-    else if (order == 2) e = 2.0 * d1[u] - d2[u];
-    else if (order >= 3) e = 3.0 * (d1[u] - d2[u]) + d3[u];
-    cur[u] = e;
-    pos[3 * OKIN_LDG(ep + u / 3) + u % 3] += e;
-  }
-  OKIN_PHASE_END
-}
-
 // Right-hand sides of the tangent systems A dq/dt_j = J_target_j^T into vec[1..NT]
 // (sensitivity.py:89-101 solved through the normal equations: with full column rank
 // lstsq([J; pins], e_j) == (J^T J)^{-1} J^T e_j).  Uses the target rows of rg[].
@@ -925,68 +890,39 @@ OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
 // the residuals at (within step_tol of) the final point, vec[1..NT] the tangents of the last
 // undamped linearisation when *tangents_ready.
 // ---------------------------------------------------------------------------------------
-#define OKIN_CHORD_ACCEPT_RESIDUAL 1e-5
 template <typename Dummy = void>
 OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tval, const OkinSolverCfg& cfg,
-                            OkinState& st, bool* converged, bool* tangents_ready, double* acc, bool carry_tangents,
-                            bool try_chord) {
+                            OkinState& st, bool* converged, bool* tangents_ready) {
   const int nt = pr.hdr[OKIN_H_NT];
   int nfev = 0;
   *tangents_ready = false;
-  *converged = false;
-  if (try_chord) {
-    // Chord iterations x <- x - (J0^T J0)^{-1} J0^T r(x) with the factor and row gradients of an
-    // earlier linearisation on the path: a residual-only evaluation and one forward/backward pass
-    // each, contraction ~ |J - J0| (a few per cent per sweep step of age).  Any doubt (NaN, a large
-    // first step, slow contraction, iteration cap) hands over to the Gauss-Newton iteration below,
-    // which starts from wherever the chord steps got to.
-    double hprev = 0.0;
-    for (int c = 0; c < 4; ++c) {
-      okin_eval_rows(pr, sm, tval, false, st);
-      ++nfev;
-      okin_assemble(pr, sm, 0.0, true);
-      okin_solve(pr, sm, 0, 1, false);
-      const double h = okin_apply_step(pr, sm, 0, 1.0, acc);
-      if (!(h == h)) { okin_restore(pr, sm, acc); break; }
-      if (h <= cfg.step_tol) {
-        // Accept only a clean root (residuals at the soft-norm bias level, ~1e-6): a chord
-        // iteration also settles on least-squares compromises near a kinematic limit, and those
-        // must be judged by the Gauss-Newton iteration exactly as before.
-        if (st.rmax <= OKIN_CHORD_ACCEPT_RESIDUAL) { *converged = true; return nfev; }
-        break;
-      }
-      if (c == 0 ? h > cfg.chord_start_tol : h > 0.2 * hprev) break;
-      hprev = h;
-    }
-  }
-  st.factor_age = -1;
   st.mu = 0.0;
   double nu = 2.0;
   okin_eval_rows(pr, sm, tval, true, st);
   ++nfev;
+  *converged = false;
   for (int it = 0; it < cfg.max_iter; ++it) {
-    // The factorisation carries the step right-hand side (and, when wanted, the tangent right-hand
-    // sides) as extra rows, so one backward pass yields the step and dq/dt_j of this linearisation.
+    // The factorisation carries the step right-hand side and the tangent right-hand sides as
+    // extra rows, so one backward pass yields the step and dq/dt_j of this linearisation.
     okin_assemble(pr, sm, st.mu, false);
-    if (carry_tangents) okin_tangent_rhs(pr, sm);
-    okin_factor(pr, sm, st, carry_tangents);
+    okin_tangent_rhs(pr, sm);
+    okin_factor(pr, sm, st);
     if (st.notpd) {  // rank-deficient normal matrix: damp and retry from the same point
       st.mu = st.mu > 0.0 ? st.mu * 10.0 : cfg.mu_init;
       if (st.mu > 1e12) break;
       continue;
     }
-    okin_solve(pr, sm, 0, carry_tangents ? 1 + nt : 1, true);
-    const double hmax = okin_apply_step(pr, sm, 0, 1.0, acc);
+    okin_solve(pr, sm, 0, 1 + nt, true);
+    const double hmax = okin_apply_step(pr, sm, 0, 1.0, true);
     if (!(hmax == hmax)) {  // NaN step: invalid geometry
-      okin_restore(pr, sm, acc);
+      okin_restore(pr, sm);
       break;
     }
     const double f2_old = st.f2;
     if (st.mu == 0.0 && hmax <= cfg.coarse_tol) {
       okin_eval_rows(pr, sm, tval, false, st);   // residuals at the new point (also the reported max|r|)
       ++nfev;
-      *tangents_ready = carry_tangents;          // linearised within hmax of the solution
-      st.factor_age = 0;
+      *tangents_ready = true;                    // linearised within hmax of the solution
       if (hmax <= cfg.fine_tol) {                // error left ~ k hmax^2: done without verification
         *converged = true;
         break;
@@ -995,14 +931,13 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       // gradients of the linearisation (g-only assembly, one forward/backward pass).
       okin_assemble(pr, sm, 0.0, true);
       okin_solve(pr, sm, 0, 1, false);
-      const double h2 = okin_apply_step(pr, sm, 0, 1.0, acc);
+      const double h2 = okin_apply_step(pr, sm, 0, 1.0, true);
       if (h2 <= cfg.step_tol) {
         *converged = true;
         break;
       }
-      okin_restore(pr, sm, acc);
+      okin_restore(pr, sm);
       *tangents_ready = false;
-      st.factor_age = -1;
       // Not contracting fast enough: relinearise at the current point.
       okin_eval_rows(pr, sm, tval, true, st);
       ++nfev;
@@ -1027,7 +962,7 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       }
       nu = 2.0;
     } else {
-      okin_restore(pr, sm, acc);
+      okin_restore(pr, sm);
       okin_eval_rows(pr, sm, tval, true, st);
       ++nfev;
       st.mu = st.mu > 0.0 ? st.mu * nu : cfg.mu_init;
@@ -1664,59 +1599,32 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   }
 
   OkinState st;
-  st.f2 = 0.0; st.rmax = 0.0; st.mu = 0.0; st.notpd = 0; st.factor_age = -1;
+  st.f2 = 0.0; st.rmax = 0.0; st.mu = 0.0; st.notpd = 0;
   int status = invalid ? OKIN_STATUS_INVALID_GEOMETRY : OKIN_STATUS_OK, failed = invalid ? 0 : -1;
   double tcur[OKIN_MAX_TARGETS], tprev[OKIN_MAX_TARGETS];
   for (int j = 0; j < OKIN_MAX_TARGETS; ++j) { tcur[j] = 0.0; tprev[j] = 0.0; }
+  bool have_tangent = false;
+  int history = 0;
   double dtprev[OKIN_MAX_TARGETS];
   for (int j = 0; j < OKIN_MAX_TARGETS; ++j) dtprev[j] = 0.0;
-  // Two continuation modes.  When tangents are wanted per state (tangents, velocities, health,
-  // metrics) every state is relinearised at its solution anyway: the predictor is Adams-Bashforth
-  // on those tangents and the relinearised factor serves the next state's chord iterations.
-  // Otherwise no tangent is ever solved: the predictor extrapolates the last displacements
-  // (history in PPREV, PPREV2 and the unused tangent slot vec[1]) and a factorisation is reused
-  // for chord iterations over up to chord_max_age sweep steps.
-  const bool want_tangents = out.tangents || out.velocities || out.health || out.metrics;
-  bool have_tangent = false;
-  int history = 0;   // tangent mode: consecutive predictor steps with equal increments
-                     // extrapolation mode: stored displacements that belong to the last increment
-  double* hist[3] = {sm + hdr[OKIN_H_OFF_PPREV], sm + hdr[OKIN_H_OFF_PPREV2], nt > 0 ? vec + n : nullptr};
-  const int nhist = nt > 0 ? 3 : 2;
 
   for (int s = 0; s < n_steps; ++s) {
     if (status == OKIN_STATUS_OK) {
       for (int j = 0; j < nt; ++j) { tprev[j] = tcur[j]; tcur[j] = OKIN_LDG(tvals + j * n_steps + s); }
-      double dt[OKIN_MAX_TARGETS];
-      bool same = true;
-      for (int j = 0; j < OKIN_MAX_TARGETS; ++j) {
-        dt[j] = tcur[j] - tprev[j];
-        if (fabs(dt[j] - dtprev[j]) > 1e-9 * (fabs(dt[j]) + fabs(dtprev[j]))) same = false;
-        dtprev[j] = dt[j];
-      }
-      bool predicted = false;
-      double* acc = nullptr;
-      if (want_tangents) {
-        if (cfg.use_predictor && have_tangent) {
-          history = same ? history + 1 : 1;
-          const int order = history < cfg.use_predictor ? history : cfg.use_predictor;
-          okin_predict(pr, sm, dt, order);
-          predicted = true;
+      if (cfg.use_predictor && have_tangent) {
+        double dt[OKIN_MAX_TARGETS];
+        bool same = true;
+        for (int j = 0; j < OKIN_MAX_TARGETS; ++j) {
+          dt[j] = tcur[j] - tprev[j];
+          if (fabs(dt[j] - dtprev[j]) > 1e-9 * (fabs(dt[j]) + fabs(dtprev[j]))) same = false;
+          dtprev[j] = dt[j];
         }
-      } else {
-        // slot s % nhist receives this step's displacement; the previous ones sit behind it
-        acc = hist[s % nhist];
-        if (!same) history = 0;
-        int order = history < cfg.use_predictor ? history : cfg.use_predictor;
-        if (order > nhist) order = nhist;
-        // (the oldest slot is acc itself: okin_extrapolate reads it before overwriting it)
-        okin_extrapolate(pr, sm, order, hist[(s + 2 * nhist - 1) % nhist], hist[(s + 2 * nhist - 2) % nhist],
-                         hist[(s + 2 * nhist - 3) % nhist], acc);
-        predicted = order > 0;
+        history = same ? history + 1 : 1;   // consecutive predictor steps with the same increments
+        const int order = history < cfg.use_predictor ? history : cfg.use_predictor;
+        okin_predict(pr, sm, dt, order);
       }
       bool conv = false, tangents_ready = false;
-      const bool try_chord = predicted && st.factor_age >= 0 && st.factor_age < cfg.chord_max_age;
-      if (st.factor_age >= 0) ++st.factor_age;
-      const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready, acc, want_tangents, try_chord);
+      const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready);
       const bool valid = st.rmax == st.rmax;
       if (!conv || !valid) {
         status = valid ? OKIN_STATUS_NOT_CONVERGED : OKIN_STATUS_INVALID_GEOMETRY;
@@ -1732,21 +1640,20 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
       if (status == OKIN_STATUS_OK) {
-        if (want_tangents) {
-          // Exported tangents are taken at the solution itself: relinearise there.
+        if (out.tangents || out.velocities || out.health || out.metrics || !tangents_ready) {
+          // Exported tangents are taken at the solution itself: relinearise there.  (For the
+          // predictor alone the factor of the last Gauss-Newton point, <= coarse_tol away, is
+          // enough and was solved together with the chord step.)
           const double rmax = st.rmax;
           okin_eval_rows(pr, sm, tcur, true, st);
           st.rmax = rmax;
           okin_assemble(pr, sm, 0.0, false);
           okin_tangent_rhs(pr, sm);
-          okin_factor(pr, sm, st, true);
+          okin_factor(pr, sm, st);
           okin_solve(pr, sm, 1, nt, true);
-          st.factor_age = st.notpd ? -1 : 0;
-          have_tangent = true;
-        } else {
-          history = history < nhist ? history + 1 : nhist;
         }
         okin_derived_update(pr, sm, false);
+        have_tangent = true;
       }
     } else {
       OKIN_PHASE_BEGIN
@@ -1800,7 +1707,6 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
     if (out.health) {
       if (ok) {
         okin_tangent_health(pr, sm, st.notpd != 0, out.health + 2 * s);
-        st.factor_age = -1;   // the estimate used the row-gradient storage as scratch
       } else {
         OKIN_PHASE_BEGIN
         if (lane == 0) { out.health[2 * s] = NAN; out.health[2 * s + 1] = NAN; }

@@ -179,8 +179,6 @@ enum okin_isec {
   OKIN_S_DIAG_OFF,       // [NF] shared-memory offset of the diagonal block of elimination column j
   OKIN_S_FREE_OUT,       // [NF] output slot of free point k (reference column order), -1 = not exported
   OKIN_S_DGOP,           // [NDGOP][OKIN_DGOP_STRIDE] topology diagnostic ops
-  OKIN_S_LEV_UPD_T,      // [NLEV] end of level lv's update tasks when tangent right-hand sides are not carried
-  OKIN_S_LEV_SCL_T,      // [NLEV] same for the scale tasks
   OKIN_S_ROW_HOT,        // [NGROW][OKIN_ROW_STRIDE] records of the generic-path rows in evaluation order
                          // (grouped by family), each carrying its row index in OKIN_R_ROWID
   OKIN_S_COUNT

@@ -13,7 +13,7 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
   if (hdr[OKIN_H_MAGIC] != OKIN_MAGIC) return -1;
   OkinProgram pr{hdr, ib, fb, ib};
   OkinSolverCfg cfg{c->step_tol, c->coarse_tol, c->fine_tol, c->residual_tol, c->mu_init, c->max_iter,
-                    c->use_predictor, c->chord_max_age, c->chord_start_tol};
+                    c->use_predictor};
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
   std::vector<double> sm(hdr[OKIN_H_SMEM_DOUBLES]);
   for (long i = 0; i < n_instances; ++i) {

@@ -141,8 +141,7 @@ def emu_lib():
     return _EMU
 
 
-def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, want_health=False,
-              positions_only=False, **cfg) -> dict:
+def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, want_health=False, **cfg) -> dict:
     """Run the lane-emulation build of the device core; ``cfg`` overrides ``okin_solver_cfg`` fields."""
     from open_kinematics_b200._lib import BatchIO, SolverCfg
     hp = np.ascontiguousarray(hardpoints, dtype=np.float64).reshape(-1, 3 * program.n_in)
@@ -161,14 +160,11 @@ def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, 
     }
     par = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
     settings = dict(step_tol=1e-6, coarse_tol=1e-3, fine_tol=1e-4, residual_tol=1e-3, mu_init=1e-3, max_iter=50,
-                    use_predictor=3, chord_max_age=4, chord_start_tol=0.05)
+                    use_predictor=3)
     settings.update(cfg)
     c = SolverCfg(**settings)
     hdr = np.ascontiguousarray(program.hdr)
     io = BatchIO.of(hardpoints=hp, params=par, target_values=tv, **out)
-    if positions_only:   # the continuation mode without per-state tangents (extrapolation + chord reuse)
-        for name in ("tangents", "velocities", "tangent_health", "metrics", "diagnostics", "jumps"):
-            setattr(io, name, None)
     rc = emu_lib().okin_emu_sweep(
         hdr.ctypes.data, program.iblob.ctypes.data, program.fblob.ctypes.data, n_inst, n_steps,
         ctypes.byref(c), ctypes.byref(io))

@@ -90,24 +90,8 @@ def test_predictor_does_not_change_the_answer():
     hp = _nominal(sus, prog)
     a = emu_solve(prog, hp, values, use_predictor=1)
     b = emu_solve(prog, hp, values, use_predictor=0)
-    assert np.abs(a["positions"] - b["positions"]).max() < 1e-7
+    assert np.abs(a["positions"] - b["positions"]).max() < 1e-8
     assert a["iters"].sum() < b["iters"].sum()
-
-
-@pytest.mark.parametrize("case", SWEEP_CASES)
-def test_positions_only_mode_matches_reference(case):
-    """Without per-state tangents the continuation extrapolates the path and reuses a factorisation
-    for chord iterations over several sweep steps; same answers, with and without the reuse."""
-    meta, arr = load_golden(case)
-    sus, sweep = build_case(meta)
-    prog, values = _program(sus, sweep)
-    order = [prog.out_keys.index(key_from_name(n)) for n in meta["point_keys"]]
-    for age in (4, 0):
-        out = emu_solve(prog, _nominal(sus, prog), values, positions_only=True, chord_max_age=age)
-        assert out["status"][0] == 0
-        diff = np.abs(out["positions"][0][:, order] - arr["positions_tight"]).max()
-        assert diff <= POS_TOL_MM, (age, diff)
-        assert out["max_residual"].max() < 1e-5
 
 
 @pytest.mark.parametrize("batch,case", [("batch_c1", "c1_dw_corner_bump"), ("batch_c2", "c2_macpherson_bump_steer"),
@@ -133,10 +117,9 @@ def check_failure_flags(solve, cases: dict) -> None:
     * reference residual rejection (2)  -> failed, first failed step within one sweep increment;
     * reference "failed to converge" (1) is MINPACK exhausting 100*n evaluations on the
       rank-deficient system (hard part 3).  The target may still be
-      feasible: the device solve may then carry on (to the end of the sweep, or to a later
-      failure of its own), and every state it accepts past the reference's failed step must
-      verify as a root of the reference's own residuals (checked with the oracle).  It never
-      fails more than one sweep increment earlier.  The failure class itself is best-effort.
+      feasible: then the device solve may succeed, and the returned state must verify as a root
+      of the reference's own residuals (checked with the oracle); otherwise it must fail within
+      one sweep increment.  The failure class itself is best-effort.
     """
     from oracle.solve import ResidualComputer, design_setup, target_bases
 
@@ -150,18 +133,16 @@ def check_failure_flags(solve, cases: dict) -> None:
             assert ok, label
             continue
         if not ok:
+            assert abs(failed - rec["failed_step"]) <= 1, (label, failed, rec["failed_step"])
             assert np.isnan(out["positions"][0, failed:]).all()
             assert np.isfinite(out["positions"][0, :failed]).all()
-        if rec["status"] == 2 or (not ok and failed <= rec["failed_step"] + 1):
-            # a residual rejection must never be accepted
-            assert not ok and abs(failed - rec["failed_step"]) <= 1, (label, failed, rec["failed_step"])
             continue
-        last = values.shape[1] if ok else failed
+        assert rec["status"] == 1, label  # a residual rejection must never be accepted
         problem, _ = oracle_problem(sus, sweep)
         pos0, consts = design_setup(problem, authored_positions(sus))
         rc = ResidualComputer(problem, pos0, consts)
         bases = target_bases(problem, pos0)
-        for s in range(rec["failed_step"], last):
+        for s in range(rec["failed_step"], values.shape[1]):
             x = np.concatenate([out["positions"][0, s, prog.out_keys.index(k)] for k in problem.free_order])
             assert np.abs(rc.compute(x, bases + values[:, s])).max() <= 1e-3, (label, s)
 
