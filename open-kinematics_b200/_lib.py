@@ -15,7 +15,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libokin.so")
+# OKIN_LIB points at an alternative build of the same library (kernel experiments); default in-tree.
+LIB_PATH = os.environ.get("OKIN_LIB") or os.path.join(CSRC, "libokin.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

@@ -72,6 +72,7 @@ struct okin_topology {
 // load instead of a global one (ncu round 1: long-scoreboard stalls on __ldg were the top stall).
 // Register cap 128 = 65536 / 512: up to 16 resident warps per SM in any CTA shape the host picks
 // (only the once-per-instance shim pre-solve spills at that cap).
+template <bool FULL, bool SHIM>
 __global__ void __launch_bounds__(OKIN_MAX_THREADS, 1)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, OkinSolverCfg cfg, okin_batch_io io, int n_iblob,
@@ -110,7 +111,7 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
     out.diagnostics = io.diagnostics ? io.diagnostics + (size_t)i * n_steps * hdr[OKIN_H_NDIAG] : nullptr;
     out.status = io.status + i;
     out.failed_step = io.failed_step + i;
-    okin_sweep(pr, sm, io.hardpoints + (size_t)i * 3 * nin,
+    okin_sweep<FULL, SHIM>(pr, sm, io.hardpoints + (size_t)i * 3 * nin,
                io.params ? io.params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, io.target_values, n_steps, cfg,
                out);
     __syncwarp();
@@ -189,9 +190,15 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
       return fail(OKIN_ERR_USAGE, "topology needs more shared memory per CTA than the device offers");
     d.warps_per_cta = best_w;
     d.smem_bytes = (int)(table_bytes + best_w * slice_bytes);
-    OKIN_CUDA(cudaFuncSetAttribute(okin_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_bytes));
-    OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.ctas_per_sm, okin_sweep_kernel, best_w * 32,
-                                                            d.smem_bytes));
+    // The four instantiations share one launch shape (same register cap, same shared memory).
+    d.ctas_per_sm = 1 << 30;
+    for (const void* kernel : {(const void*)okin_sweep_kernel<false, false>, (const void*)okin_sweep_kernel<false, true>,
+                               (const void*)okin_sweep_kernel<true, false>, (const void*)okin_sweep_kernel<true, true>}) {
+      OKIN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_bytes));
+      int ctas = 0;
+      OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, best_w * 32, d.smem_bytes));
+      d.ctas_per_sm = std::min(d.ctas_per_sm, ctas);
+    }
     if (d.ctas_per_sm < 1) return fail(OKIN_ERR_CUDA, "kernel does not fit on an SM");
     for (int k = 0; k < OKIN_PIPE_SLOTS; ++k)
       OKIN_CUDA(cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking));
@@ -210,7 +217,12 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
   const int64_t needed = (n_instances + w - 1) / w;
   const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
   const int grid = (int)std::min<int64_t>(needed, resident);
-  okin_sweep_kernel<<<grid, w * 32, d->smem_bytes, stream>>>(
+  // lean instantiation when no per-state tangent / metric / diagnostic output is wanted
+  const bool full = io.tangents || io.velocities || io.tangent_health || io.metrics || io.diagnostics;
+  const bool shim = t->hdr[OKIN_H_NSHIM] > 0;
+  auto kernel = full ? (shim ? okin_sweep_kernel<true, true> : okin_sweep_kernel<true, false>)
+                     : (shim ? okin_sweep_kernel<false, true> : okin_sweep_kernel<false, false>);
+  kernel<<<grid, w * 32, d->smem_bytes, stream>>>(
       d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, c, io, (int)t->ib.size(), d->table_doubles);
   OKIN_CUDA(cudaGetLastError());
   if (io.diagnostics && t->hdr[OKIN_H_NDIAG] && n_steps > 0) {

@@ -44,6 +44,20 @@
 #define OKIN_LDG(p) (*(p))
 #endif
 
+// Unroll factor of the gather loops over a task's contributions (factor update, triangular solves,
+// assembly).  Not unrolled by default: the trip counts are 1-8 and data dependent, and the smaller
+// code measured 5 % faster than the compiler's own 4x unrolling (profiles/r01_g_*).
+#ifndef OKIN_INNER_UNROLL
+#define OKIN_INNER_UNROLL 1
+#endif
+#define OKIN_STR2(x) #x
+#define OKIN_STR(x) OKIN_STR2(x)
+#if defined(__CUDA_ARCH__)
+#define OKIN_UNROLL_INNER _Pragma(OKIN_STR(unroll OKIN_INNER_UNROLL))
+#else
+#define OKIN_UNROLL_INNER
+#endif
+
 // Warp reductions over the per-lane partials a phase left in red[0..32): shuffles on the device
 // (every lane ends with the result), a plain loop in the lane emulation.  NaN propagates in max.
 #if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
@@ -362,7 +376,7 @@ OKIN_FN void okin_shim_presolve(const OkinProgram& pr, double* sm, const double*
 // ---------------------------------------------------------------------------------------
 // Setup: inputs -> pos, derived parameters, design pose, per-instance constants.
 // ---------------------------------------------------------------------------------------
-template <typename Dummy = void>
+template <bool SHIM>
 OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints,
                         const double* __restrict__ params, int* invalid) {
   const int32_t* hdr = pr.hdr;
@@ -374,7 +388,7 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
   OKIN_PHASE_BEGIN
   for (int t = lane; t < 3 * nin; t += 32) pos[3 * OKIN_LDG(in_point + t / 3) + t % 3] = hardpoints[t];
   OKIN_PHASE_END
-  okin_shim_presolve(pr, sm, params ? params : okin_fsec(pr, OKIN_F_PARAM_DEFAULT), invalid);
+  if (SHIM) okin_shim_presolve(pr, sm, params ? params : okin_fsec(pr, OKIN_F_PARAM_DEFAULT), invalid);
 
   // Derived-op parameters.  A design projection reads the *authored* position of the derived
   // point (macpherson.py:199-204), which is what pos[] still holds at this moment.
@@ -587,6 +601,7 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
       // one 3x3 block of A: sum of outer products ga gb^T over the rows coupling the two points
       const int b = OKIN_LDG(aptr + t), e = OKIN_LDG(aptr + t + 1);
       double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
+      OKIN_UNROLL_INNER
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(acon + q);
         const double* ga = rg + ((w >> 16) & 0x7fffu);
@@ -606,6 +621,7 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
       const int j = t - nat;
       const int b = OKIN_LDG(gptr + j), e = OKIN_LDG(gptr + j + 1);
       double g0 = 0, g1 = 0, g2 = 0;
+      OKIN_UNROLL_INNER
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(gcon + q);
         const double* ga = rg + ((w >> 16) & 0x7fffu);
@@ -676,7 +692,8 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
         const int b = OKIN_LDG(uptr + t), e = OKIN_LDG(uptr + t + 1);
         double* dst = sm + OKIN_LDG(udst + t);
         double c0 = dst[0], c1 = dst[1], c2 = dst[2];
-        for (int q = b; q < e; ++q) {
+        OKIN_UNROLL_INNER
+      for (int q = b; q < e; ++q) {
           const uint32_t w = (uint32_t)OKIN_LDG(ucon + q);
           const double* a = sm + (w >> 16);
           const double* B = sm + (w & 0xffffu);
@@ -735,6 +752,7 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
       const int j = OKIN_LDG(lcol + cb + t / nrhs);
       double* v = vec + (t % nrhs) * n;
       double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2];
+      OKIN_UNROLL_INNER
       for (int q = OKIN_LDG(fptr + j); q < OKIN_LDG(fptr + j + 1); ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(fcon + q);
         const double* B = Lb + (w >> 16);
@@ -758,6 +776,7 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
       const int j = OKIN_LDG(lcol + cb + t / nrhs);
       double* v = vec + (t % nrhs) * n;
       double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2];
+      OKIN_UNROLL_INNER
       for (int q = OKIN_LDG(bptr + j); q < OKIN_LDG(bptr + j + 1); ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(bcon + q);
         const double* B = Lb + (w >> 16);
@@ -1578,7 +1597,11 @@ struct OkinOutputs {
 
 // Whole sweep for one instance (solver.py:716-774).  tvals: [NT][n_steps] relative/absolute
 // sweep values shared by all instances of the launch.
-template <typename Dummy = void>
+// FULL: tangents / velocities / health / metrics / diagnostics outputs are compiled in (the lean
+// instantiation only writes positions, solver statistics and the design pose: the throughput
+// path, whose code footprint matters -- see profiles/r01_g_*).  SHIM: the topology has camber-shim
+// records (the pre-solve is a large, once-per-instance piece of code).
+template <bool FULL, bool SHIM>
 OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints,
                         const double* __restrict__ params, const double* __restrict__ tvals, int n_steps,
                         const OkinSolverCfg& cfg, const OkinOutputs& out) {
@@ -1590,8 +1613,14 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   const int32_t* ecol = okin_sec(pr, OKIN_S_ELIM_COL);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
+  // outputs only the full instantiation knows about
+  double* const o_tangents = FULL ? out.tangents : nullptr;
+  double* const o_velocities = FULL ? out.velocities : nullptr;
+  double* const o_health = FULL ? out.health : nullptr;
+  double* const o_metrics = FULL ? out.metrics : nullptr;
+  double* const o_diagnostics = FULL ? out.diagnostics : nullptr;
   int invalid = 0;
-  okin_setup(pr, sm, hardpoints, params, &invalid);
+  okin_setup<SHIM>(pr, sm, hardpoints, params, &invalid);
   if (out.design) {  // design (setup) pose of every output point
     OKIN_PHASE_BEGIN
     for (int t = lane; t < 3 * nout; t += 32) out.design[t] = pos[3 * OKIN_LDG(out_point + t / 3) + t % 3];
@@ -1640,7 +1669,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
       if (status == OKIN_STATUS_OK) {
-        if (out.tangents || out.velocities || out.health || out.metrics || !tangents_ready) {
+        if (o_tangents || o_velocities || o_health || o_metrics || !tangents_ready) {
           // Exported tangents are taken at the solution itself: relinearise there.  (For the
           // predictor alone the factor of the last Gauss-Newton point, <= coarse_tol away, is
           // enough and was solved together with the chord step.)
@@ -1671,9 +1700,9 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
         dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
       OKIN_PHASE_END
     }
-    if (out.metrics) {
+    if (FULL && o_metrics) {
       const int nm = hdr[OKIN_H_NM];
-      double* dst = out.metrics + (size_t)s * nm;
+      double* dst = o_metrics + (size_t)s * nm;
       if (ok) {
         okin_metrics(pr, sm, dst);
       } else {
@@ -1682,8 +1711,8 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
         OKIN_PHASE_END
       }
     }
-    if (out.velocities) {  // TangentField.velocities (sensitivity.py:115-141)
-      double* dst = out.velocities + (size_t)s * nt * 3 * nout;
+    if (FULL && o_velocities) {  // TangentField.velocities (sensitivity.py:115-141)
+      double* dst = o_velocities + (size_t)s * nt * 3 * nout;
       OKIN_PHASE_BEGIN
       for (int t = lane; t < nt * nout; t += 32) {
         double v[3] = {NAN, NAN, NAN};
@@ -1692,8 +1721,8 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
     }
-    if (out.tangents) {
-      double* dst = out.tangents + (size_t)s * nt * n;
+    if (FULL && o_tangents) {
+      double* dst = o_tangents + (size_t)s * nt * n;
       OKIN_PHASE_BEGIN
       for (int t = lane; t < nt * n; t += 32) {
         const int j = t / n, u = t % n;  // u: elimination-ordered unknown
@@ -1701,15 +1730,15 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
     }
-    if (out.diagnostics && hdr[OKIN_H_NDIAG])
-      okin_diagnostics(pr, sm, out.diagnostics + (size_t)s * hdr[OKIN_H_NDIAG], ok,
+    if (FULL && o_diagnostics && hdr[OKIN_H_NDIAG])
+      okin_diagnostics(pr, sm, o_diagnostics + (size_t)s * hdr[OKIN_H_NDIAG], ok,
                        failed == s ? status : OKIN_STATUS_OK);
-    if (out.health) {
+    if (FULL && o_health) {
       if (ok) {
-        okin_tangent_health(pr, sm, st.notpd != 0, out.health + 2 * s);
+        okin_tangent_health(pr, sm, st.notpd != 0, o_health + 2 * s);
       } else {
         OKIN_PHASE_BEGIN
-        if (lane == 0) { out.health[2 * s] = NAN; out.health[2 * s + 1] = NAN; }
+        if (lane == 0) { o_health[2 * s] = NAN; o_health[2 * s + 1] = NAN; }
         OKIN_PHASE_END
       }
     }

@@ -31,7 +31,7 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
     out.diagnostics = (io->diagnostics && nd) ? io->diagnostics + (size_t)i * n_steps * nd : nullptr;
     out.status = io->status + i;
     out.failed_step = io->failed_step + i;
-    okin_sweep(pr, sm.data(), io->hardpoints + (size_t)i * 3 * nin,
+    okin_sweep<true, true>(pr, sm.data(), io->hardpoints + (size_t)i * 3 * nin,
                io->params ? io->params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, io->target_values, n_steps, cfg,
                out);
     if (out.diagnostics && n_steps > 0) {  // continuity pass, as the product's second kernel does
