@@ -45,3 +45,12 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
   }
   return 0;
 }
+
+// One constraint row of the generated family functions (csrc/okin_gen_constraints.cuh): residual via
+// both entry points and the gradient, for the family-row golden vectors.
+extern "C" int okin_emu_family(int fam, const double* p, const double* c, double* res, double* res_only, double* g) {
+  for (int k = 0; k < 12; ++k) g[k] = 0.0;
+  *res = okin_family_resgrad(fam, p, c, g);
+  *res_only = okin_family_res(fam, p, c);
+  return 0;
+}

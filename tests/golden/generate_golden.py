@@ -426,6 +426,88 @@ def run_diagnostics() -> None:
     np.savez_compressed(os.path.join(OUT, "diagnostics.npz"), **arrays)
 
 
+# --------------------------------------------------------------------------- generic families
+def generic_mechanism() -> dict:
+    """A synthetic one-degree-of-freedom linkage written with the generic constraint families
+    that no shipped topology uses: planar four-bar A-B-C-D in the XZ
+    plane, coupler point E on the bisector of BC, out-of-plane point F."""
+    A, D = np.array([0.0, 0.0, 0.0]), np.array([300.0, 0.0, 0.0])
+    B, C = np.array([30.0, 0.0, 95.0]), np.array([260.0, 0.0, 150.0])
+    bc = (C - B) / np.linalg.norm(C - B)
+    E = B + (C - B) / 2 + 100.0 * np.array([-bc[2], 0.0, bc[0]])
+    F = E + np.array([0.0, 120.0, 0.0])
+    pts = {"lower_wishbone_inboard_front": A, "lower_wishbone_inboard_rear": D, "lower_wishbone_outboard": B,
+           "upper_wishbone_outboard": C, "axle_inboard": E, "axle_outboard": F}
+    a, d, b, c, e, f = pts
+    v1, v2 = B - E, C - E
+    alpha = float(np.arctan2(np.linalg.norm(np.cross(v1, v2)), v1 @ v2))
+    dist = lambda p, q: float(np.linalg.norm(pts[p] - pts[q]))   # noqa: E731
+    cons = [
+        {"family": "distance", "points": [a, b], "value": dist(a, b)},
+        {"family": "point_on_plane", "points": [b], "plane_point": [0, 0, 0], "plane_normal": [0, 1, 0]},
+        {"family": "distance", "points": [b, c], "value": dist(b, c)},
+        {"family": "distance", "points": [c, d], "value": dist(c, d)},
+        {"family": "fixed_axis", "points": [c], "axis": 1, "value": 0.0},
+        {"family": "equal_distance", "points": [b, e, c, e]},
+        {"family": "three_point_angle", "points": [b, e, c], "value": alpha},
+        {"family": "coplanar", "points": [a, d, b, e]},
+        {"family": "distance", "points": [e, f], "value": dist(e, f)},
+        {"family": "vectors_perpendicular", "points": [e, f, b, c]},
+        {"family": "vectors_perpendicular", "points": [e, f, a, d]},
+    ]
+    return {"points": {k: v.tolist() for k, v in pts.items()}, "free": [b, c, e, f], "constraints": cons,
+            "target": {"point": b, "axis": 2, "values": np.linspace(0.0, -45.0, 16).tolist()}}
+
+
+def run_generic() -> None:
+    from kinematics.core.state import SuspensionState
+    from kinematics.core.points.derived.manager import DerivedPointsSpec
+    from kinematics.core.targeting import PointTarget, PointTargetAxis, SweepConfig
+    from kinematics.core.enums import TargetPositionMode
+    spec = generic_mechanism()
+    key = lambda name: PointID[name.upper()]   # noqa: E731
+    state = SuspensionState(positions={key(k): Point3(np.array(v, float)) for k, v in spec["points"].items()},
+                            free_points={key(k) for k in spec["free"]})
+    cons = []
+    for c in spec["constraints"]:
+        k = [key(n) for n in c["points"]]
+        fam = c["family"]
+        if fam == "distance":
+            cons.append(C.DistanceConstraint(k[0], k[1], c["value"]))
+        elif fam == "point_on_plane":
+            cons.append(C.PointOnPlaneConstraint(k[0], Point3(np.array(c["plane_point"], float)),
+                                                 Direction3(np.array(c["plane_normal"], float))))
+        elif fam == "fixed_axis":
+            cons.append(C.FixedAxisConstraint(k[0], Axis(c["axis"]), c["value"]))
+        elif fam == "equal_distance":
+            cons.append(C.EqualDistanceConstraint(*k))
+        elif fam == "three_point_angle":
+            cons.append(C.ThreePointAngleConstraint(*k, c["value"]))
+        elif fam == "coplanar":
+            cons.append(C.CoplanarPointsConstraint(*k))
+        elif fam == "vectors_perpendicular":
+            cons.append(C.VectorsPerpendicularConstraint(*k))
+        else:
+            raise KeyError(fam)
+    t = spec["target"]
+    sweep = SweepConfig([[PointTarget(key(t["point"]), PointTargetAxis(Axis(t["axis"])), v, TargetPositionMode.RELATIVE)
+                          for v in t["values"]]])
+    dm = DerivedPointsManager(DerivedPointsSpec(functions={}, dependencies={}))
+    states, stats = solve_suspension_sweep(state, cons, sweep, dm, TIGHT)
+    keys = sorted(state.positions)
+    vel = []
+    for step, st in enumerate(states):
+        targets = convert_targets_to_absolute([sw[step] for sw in sweep.target_sweeps], state)
+        fields, info = compute_state_tangents(st, cons, dm, targets)
+        assert not info.rank_deficient
+        vel.append([[fld.velocity(k) for k in keys] for fld in fields])
+    np.savez_compressed(os.path.join(OUT, "generic_mechanism.npz"), positions_tight=positions_array(states, keys),
+                        velocities=np.array(vel), max_residual=np.array([s.max_residual for s in stats]))
+    spec["point_keys"] = [key_name(k) for k in keys]
+    json.dump(spec, open(os.path.join(OUT, "generic_mechanism.json"), "w"), indent=1)
+    print("generic mechanism:", len(states), "states, max residual", max(s.max_residual for s in stats))
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for case, (g, s) in CASES.items():
@@ -441,3 +523,5 @@ if __name__ == "__main__":
         run_families()
     if not only or "diagnostics" in only:
         run_diagnostics()
+    if not only or "generic" in only:
+        run_generic()

@@ -137,8 +137,63 @@ def emu_lib():
         lib = ctypes.CDLL(out)
         lib.okin_emu_sweep.restype = ctypes.c_int
         lib.okin_emu_sweep.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_long, ctypes.c_int] + [ctypes.c_void_p] * 2
+        lib.okin_emu_family.restype = ctypes.c_int
+        lib.okin_emu_family.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 5
         _EMU = lib
     return _EMU
+
+
+def emu_family(fam_code: int, points: np.ndarray, consts) -> tuple:
+    """(residual from okin_family_resgrad, residual from okin_family_res, gradient[n_points, 3])."""
+    p = np.zeros(12)
+    p[:points.size] = np.asarray(points, dtype=np.float64).reshape(-1)
+    c = np.zeros(8)
+    c[:len(consts)] = consts
+    res, res_only, g = np.zeros(1), np.zeros(1), np.zeros(12)
+    emu_lib().okin_emu_family(fam_code, p.ctypes.data, c.ctypes.data, res.ctypes.data, res_only.ctypes.data,
+                              g.ctypes.data)
+    return float(res[0]), float(res_only[0]), g[:points.size].reshape(-1, 3)
+
+
+def generic_mechanism():
+    """Mirror-class build of tests/golden/generic_mechanism.json (generic constraint families):
+    ``(initial_state, constraints, sweep_config, derived_manager, spec, arrays)``."""
+    from open_kinematics_b200.core.enums import Axis
+    from open_kinematics_b200.core.points.derived.manager import DerivedPointsManager, DerivedPointsSpec
+    from open_kinematics_b200.core.primitives.geometry import Direction3, Point3
+    from open_kinematics_b200.core.state import SuspensionState
+    from open_kinematics_b200.core.targeting import PointTarget, PointTargetAxis, SweepConfig
+    spec = json.load(open(os.path.join(GOLDEN, "generic_mechanism.json")))
+    arrays = np.load(os.path.join(GOLDEN, "generic_mechanism.npz"))
+    key = lambda name: PointID[name.upper()]   # noqa: E731
+    state = SuspensionState(positions={key(k): Point3(np.array(v, float)) for k, v in spec["points"].items()},
+                            free_points={key(k) for k in spec["free"]})
+    cons = []
+    for c in spec["constraints"]:
+        k = [key(n) for n in c["points"]]
+        fam = c["family"]
+        if fam == "distance":
+            cons.append(PC.DistanceConstraint(k[0], k[1], c["value"]))
+        elif fam == "point_on_plane":
+            cons.append(PC.PointOnPlaneConstraint(k[0], Point3(np.array(c["plane_point"], float)),
+                                                  Direction3(np.array(c["plane_normal"], float))))
+        elif fam == "fixed_axis":
+            cons.append(PC.FixedAxisConstraint(k[0], Axis(c["axis"]), c["value"]))
+        elif fam == "equal_distance":
+            cons.append(PC.EqualDistanceConstraint(*k))
+        elif fam == "three_point_angle":
+            cons.append(PC.ThreePointAngleConstraint(*k, c["value"]))
+        elif fam == "coplanar":
+            cons.append(PC.CoplanarPointsConstraint(*k))
+        elif fam == "vectors_perpendicular":
+            cons.append(PC.VectorsPerpendicularConstraint(*k))
+        else:
+            raise KeyError(fam)
+    t = spec["target"]
+    sweep = SweepConfig([[PointTarget(key(t["point"]), PointTargetAxis(Axis(t["axis"])), float(v),
+                                      TargetPositionMode.RELATIVE) for v in t["values"]]])
+    manager = DerivedPointsManager(DerivedPointsSpec(functions={}, dependencies={}))
+    return state, cons, sweep, manager, spec, arrays
 
 
 def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, want_health=False, **cfg) -> dict:

@@ -201,3 +201,26 @@ def test_camber_shim_presolve_matches_reference(case):
     auth = authored_positions(sus)
     for k, v in auth.items():
         assert np.array_equal(out3["design"][0][prog.out_keys.index(k)], v)
+
+
+def test_generated_family_rows_match_reference():
+    """Every generated constraint family (csrc/okin_gen_constraints.cuh, all 12) against the rows the
+    reference's own residual()/jac_*() produced (tests/golden/families.json)."""
+    from helpers import emu_family
+    from open_kinematics_b200.core.topology import FAMILY_CODE
+    recs = json.load(open(os.path.join(GOLDEN, "families.json")))
+    assert set(recs) == set(FAMILY_CODE) - {"target"}
+    for fam, rec in recs.items():
+        for pts, consts, res, jac in zip(rec["points"], rec["consts"], rec["residual"], rec["jacobian"]):
+            pts, jac = np.array(pts), np.array(jac)
+            got, got_only, grad = emu_family(FAMILY_CODE[fam], pts, consts)
+            scale = max(1.0, abs(res))
+            assert abs(got - res) <= 1e-11 * scale and abs(got_only - res) <= 1e-11 * scale, fam
+            assert np.abs(grad - jac).max() <= 1e-11 * max(1.0, np.abs(jac).max()), fam
+
+
+def test_generic_family_mechanism_matches_reference(emu_device):
+    """Boundary B1 / B2 on a linkage written with the generic families no shipped topology uses
+    (three-point angle, equal distance, vectors perpendicular, fixed axis, point on plane, coplanar)."""
+    import test_gpu_parity as G
+    G.test_generic_family_mechanism_matches_reference()

@@ -352,3 +352,24 @@ def test_sweep_diagnostics_match_reference():
     evaluated = solve_evaluated_sweep(sus, sweep)
     assert len(evaluated.states) == len(evaluated.metrics.rows) == sweep.n_steps
     assert [i.category for i in evaluated.diagnostics] == [DiagnosticCategory.JUMP] * 5
+
+
+def test_generic_family_mechanism_matches_reference():
+    """Boundary B1 / B2 on a linkage written with the generic constraint families no shipped topology
+    uses: positions vs the reference's tight run, velocities vs
+    compute_state_tangents."""
+    from helpers import generic_mechanism
+    from open_kinematics_b200.core.sensitivity import compute_state_tangents
+    from open_kinematics_b200.core.solver import convert_targets_to_absolute, solve_suspension_sweep
+    state, cons, sweep, manager, spec, arr = generic_mechanism()
+    states, stats = solve_suspension_sweep(state, cons, sweep, manager)
+    keys = [key_from_name(n) for n in spec["point_keys"]]
+    got = np.array([[st.positions[k].data for k in keys] for st in states])
+    assert np.abs(got - arr["positions_tight"]).max() <= POS_TOL_MM
+    assert max(s.max_residual for s in stats) < 1e-6
+    for s in (0, len(states) - 1):
+        targets = convert_targets_to_absolute([dim[s] for dim in sweep.target_sweeps], state)
+        fields, info = compute_state_tangents(states[s], cons, manager, targets)
+        assert not info.rank_deficient
+        vel = np.array([[f.velocity(k) for k in keys] for f in fields])
+        assert np.abs(vel - arr["velocities"][s]).max() <= 1e-7 * max(1.0, np.abs(arr["velocities"]).max())
