@@ -508,6 +508,33 @@ def run_generic() -> None:
     print("generic mechanism:", len(states), "states, max residual", max(s.max_residual for s in stats))
 
 
+# --------------------------------------------------------------------------- result files
+def run_result_files() -> None:
+    """The reference's own sweep file for the C1 case (cli/commands/sweep.py:39-79 -> CSV, format
+    version 3) and the unit symbol of every flat metric column of every golden case."""
+    import tempfile
+    from pathlib import Path
+
+    from kinematics.cli.commands.sweep import run_sweep_files
+    from kinematics.core.metrics.registry import flat_specs_for_suspension
+    units = {}
+    for case, (geom, _sweep) in CASES.items():
+        sus = build_suspension(geom)
+        units.update({k: spec.unit.symbol for k, spec in flat_specs_for_suspension(sus).items()})
+    geom, sweep = CASES["c1_dw_corner_bump_steer"]
+    with tempfile.TemporaryDirectory() as tmp:
+        gp, sp, op = Path(tmp) / "geometry.yaml", Path(tmp) / "sweep.yaml", Path(tmp) / "out.csv"
+        gp.write_text(yaml.safe_dump(geom))
+        sp.write_text(yaml.safe_dump(sweep))
+        run_sweep_files(gp, sp, op)
+        lines = op.read_text().splitlines()
+    keep = [ln for ln in lines if not ln.startswith(("# timestamp", "# geometry_", "# sweep_"))]
+    open(os.path.join(OUT, "e2e_c1_bump_steer.csv"), "w").write("\n".join(keep) + "\n")
+    json.dump({"metric_units": units, "case": "c1_dw_corner_bump_steer"},
+              open(os.path.join(OUT, "result_files.json"), "w"), indent=1)
+    print("result files:", len(units), "metric units,", len(keep), "csv lines")
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])
     for case, (g, s) in CASES.items():
@@ -525,3 +552,5 @@ if __name__ == "__main__":
         run_diagnostics()
     if not only or "generic" in only:
         run_generic()
+    if not only or "results" in only:
+        run_result_files()

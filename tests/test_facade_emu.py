@@ -24,3 +24,7 @@ def test_solve_suspension_sweep_boundary(emu_device):
 
 def test_sweep_diagnostics(emu_device):
     G.test_sweep_diagnostics_match_reference()
+
+
+def test_result_files(emu_device, tmp_path):
+    G.test_result_files_match_reference(tmp_path)

@@ -373,3 +373,65 @@ def test_generic_family_mechanism_matches_reference():
         assert not info.rank_deficient
         vel = np.array([[f.velocity(k) for k in keys] for f in fields])
         assert np.abs(vel - arr["velocities"][s]).max() <= 1e-7 * max(1.0, np.abs(arr["velocities"]).max())
+
+
+def test_result_files_match_reference(tmp_path):
+    """Wide-form sweep file against the reference's own CSV for the same inputs (reference e2e test,
+    tests/e2e/test_e2e.py:203-213: same columns in the same order, values at atol=rtol=1e-3 with the
+    solver columns excluded -- here 1e-4 absolute on a 1e-5 mm reference), same unit metadata;
+    CSV and Parquet carry the same table; batch table has the same columns per (instance, step)."""
+    import csv
+
+    import pyarrow.parquet as pq
+
+    from open_kinematics_b200.core.sweep import BatchSolver
+    from open_kinematics_b200.io.results_writer import (METADATA_KEY, batch_table, metric_unit, run_sweep,
+                                                        write_batch_parquet)
+    info = json.load(open(os.path.join(GOLDEN, "result_files.json")))
+    for name, unit in info["metric_units"].items():
+        assert metric_unit(name) == unit, name
+    ref_lines = open(os.path.join(GOLDEN, "e2e_c1_bump_steer.csv")).read().splitlines()
+    ref_units = json.loads(next(ln for ln in ref_lines if ln.startswith("# column_units: "))[len("# column_units: "):])
+    ref_rows = list(csv.reader(ln for ln in ref_lines if not ln.startswith("#")))
+
+    meta, arr = load_golden(info["case"])
+    sus, sweep = build_case(meta)
+    run_sweep(sus, sweep, tmp_path / "out.csv")
+    run_sweep(sus, sweep, tmp_path / "out.parquet")
+    lines = (tmp_path / "out.csv").read_text().splitlines()
+    assert lines[0] == "# format_version: 3"
+    units = json.loads(next(ln for ln in lines if ln.startswith("# column_units: "))[len("# column_units: "):])
+    assert units == ref_units
+    rows = list(csv.reader(ln for ln in lines if not ln.startswith("#")))
+    assert rows[0] == ref_rows[0] and len(rows) == len(ref_rows)
+    solver_cols = {"solver_converged", "solver_max_residual", "solver_nfev"}
+    for got, ref in zip(rows[1:], ref_rows[1:]):
+        for name, g, r in zip(rows[0], got, ref):
+            if name in solver_cols:
+                continue
+            assert (g == "") == (r == ""), name
+            if g != "":
+                assert abs(float(g) - float(r)) <= 1e-4 * max(1.0, abs(float(r))), (name, g, r)
+
+    table = pq.read_table(tmp_path / "out.parquet")
+    assert table.column_names == rows[0]
+    assert json.loads(table.schema.metadata[METADATA_KEY])["format_version"] == "3"
+    assert table.schema.field("camber").metadata[b"unit"] == b"deg"
+    assert table.schema.field("wheel_center_z").metadata[b"unit"] == b"mm"
+    col = table.column("wheel_center_z").to_pylist()
+    assert all(abs(v - float(r[rows[0].index("wheel_center_z")])) < 1e-9 for v, r in zip(col, rows[1:]))
+
+    solver = BatchSolver(sus, sweep, output_points=list(sus.output_points()))
+    try:
+        hp = np.repeat(solver.nominal_hardpoints()[None, :], 3, axis=0)
+        res = solver.solve(hp, want_metrics=True)
+    finally:
+        solver.close()
+    bt = batch_table(res)
+    assert bt.column_names == ["instance_index"] + rows[0]
+    assert bt.num_rows == 3 * sweep.n_steps
+    assert np.allclose(bt.column("camber").to_numpy()[:sweep.n_steps], table.column("camber").to_numpy(), atol=1e-9)
+    write_batch_parquet(tmp_path / "batch.parquet", res, instances_per_row_group=2)
+    back = pq.read_table(tmp_path / "batch.parquet")
+    assert back.num_rows == bt.num_rows and back.column_names == bt.column_names
+    assert back.column("instance_index").to_pylist()[-1] == 2
