@@ -530,7 +530,24 @@ def run_result_files() -> None:
         lines = op.read_text().splitlines()
     keep = [ln for ln in lines if not ln.startswith(("# timestamp", "# geometry_", "# sweep_"))]
     open(os.path.join(OUT, "e2e_c1_bump_steer.csv"), "w").write("\n".join(keep) + "\n")
-    json.dump({"metric_units": units, "case": "c1_dw_corner_bump_steer"},
+    # setup-reference pose of analyze_sweep (core/analysis.py:182-216) for a corner and an axle
+    from kinematics.core.analysis import analyze_sweep
+    analysis = {}
+    for case in ("c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll"):
+        g, sw = CASES[case]
+        sus = build_suspension(g)
+        res = analyze_sweep(sus, build_sweep(sw, sus))
+        ref = res.references["setup"]
+        analysis[case] = {
+            "metric_keys": res.metric_keys, "corner_metric_keys": res.corner_metric_keys,
+            "locations": res.locations, "steps": res.steps,
+            "sweep_parameters": [[p.point, p.axis, p.side] for p in res.sweep_parameters],
+            "setup_metrics": ref.metrics, "setup_corner_metrics": ref.corner_metrics,
+            "setup_positions": {k: list(v) for k, v in ref.positions.items()},
+            "last_frame_metrics": res.frames[-1].metrics,
+            "diagnostics": [[d.step, str(d.category.value)] for d in res.diagnostics],
+        }
+    json.dump({"metric_units": units, "case": "c1_dw_corner_bump_steer", "analysis": analysis},
               open(os.path.join(OUT, "result_files.json"), "w"), indent=1)
     print("result files:", len(units), "metric units,", len(keep), "csv lines")
 

@@ -435,3 +435,37 @@ def test_result_files_match_reference(tmp_path):
     back = pq.read_table(tmp_path / "batch.parquet")
     assert back.num_rows == bt.num_rows and back.column_names == bt.column_names
     assert back.column("instance_index").to_pylist()[-1] == 2
+
+
+@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll"])
+def test_analyze_sweep_matches_reference(case):
+    """analyze_sweep (reference core/analysis.py:219-316): frame / key structure, sweep parameters
+    and the solved setup-reference pose with its metric rows."""
+    from open_kinematics_b200.core.analysis import analyze_sweep
+    ref = json.load(open(os.path.join(GOLDEN, "result_files.json")))["analysis"][case]
+    meta, _ = load_golden(case)
+    sus, sweep = build_case(meta)
+    res = analyze_sweep(sus, sweep)
+    assert res.steps == ref["steps"] and res.locations == ref["locations"]
+    assert res.metric_keys == ref["metric_keys"] and res.corner_metric_keys == ref["corner_metric_keys"]
+    assert [[p.point, p.axis, p.side] for p in res.sweep_parameters] == ref["sweep_parameters"]
+    assert [[d.step, str(d.category.value)] for d in res.diagnostics] == ref["diagnostics"]
+    setup = res.references["setup"]
+    assert setup.label == "Setup"
+    for name, xyz in ref["setup_positions"].items():      # the reference lists its presentation points
+        if name in setup.positions:
+            assert np.abs(np.array(setup.positions[name]) - np.array(xyz)).max() <= 1e-4, name
+    assert len(set(ref["setup_positions"]) & set(setup.positions)) >= len(meta["output_points"])
+
+    def check_row(got, want, label):
+        assert list(got) == list(want), label
+        for key, value in want.items():
+            assert (got[key] is None) == (value is None), (label, key)
+            if value is not None:
+                assert abs(got[key] - value) <= 1e-4 * max(1.0, abs(value)), (label, key, got[key], value)
+
+    check_row(setup.metrics, ref["setup_metrics"], "setup")
+    assert list(setup.corner_metrics) == list(ref["setup_corner_metrics"])
+    for side, row in ref["setup_corner_metrics"].items():
+        check_row(setup.corner_metrics[side], row, side)
+    check_row(res.frames[-1].metrics, ref["last_frame_metrics"], "last frame")
