@@ -618,7 +618,9 @@ def compile_topology(
         "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
         "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)), "OKIN_H_OFF_LB": take(9 * NB),
         "OKIN_H_OFF_VEC": take((1 + NT) * N),
-        "OKIN_H_OFF_RED": take(64), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)), "OKIN_H_OFF_PPREV": take(N), "OKIN_H_OFF_PPREV2": take(N),
+        "OKIN_H_OFF_RED": take(32), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)),
+        # predictor history: two float32 vectors (stored two per double slot)
+        "OKIN_H_OFF_PPREV": take((N + 1) // 2), "OKIN_H_OFF_PPREV2": take((N + 1) // 2),
     }
     if off >= 65536:
         raise ValueError("Per-instance state exceeds the 16-bit shared-memory offset range")

@@ -498,7 +498,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   const int32_t* drow = okin_sec(pr, OKIN_S_DROW);
   const int ndrow = hdr[OKIN_H_NDROW], ngrow = hdr[OKIN_H_NGROW];
   OKIN_PHASE_BEGIN
-  double sq = 0.0, mx = 0.0;
+  double sq = 0.0;
   // Fast path: plain distance rows (most of every shipped topology).  r = sqrt(s + eps^2) - eps - L,
   // u = (p2 - p1)/sqrt(s + eps^2) is the whole gradient (dR/dp2 = u, dR/dp1 = -u).
   for (int slot = lane; slot < ndrow; slot += 32) {
@@ -510,8 +510,6 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
     const double inv = OKIN_RSQRT(s2);
     const double res = s2 * inv - OKIN_EPS - cst[oo & 0xffffu];
     r[OKIN_LDG(drow + 2 * ndrow + slot)] = res;
-    const double ar = fabs(res);
-    mx = (ar > mx || ar != ar) ? ar : mx;
     sq += res * res;
     if (with_grad) {
       double* u = rg + (oo >> 16);
@@ -542,8 +540,6 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
       res = okin_family_res(fam, p, c);
     }
     r[t] = res;
-    const double ar = fabs(res);
-    mx = (ar > mx || ar != ar) ? ar : mx;
     if (t < nls) sq += res * res;
     if (grad) {
       double* out = rg + OKIN_LDG(rec + OKIN_R_RG);
@@ -570,9 +566,18 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
     }
   }
   red[lane] = sq;
-  red[32 + lane] = mx;
   OKIN_PHASE_END
-  const double f2 = okin_red_sum(red), rmax = okin_red_max(red + 32);
+  const double f2 = okin_red_sum(red);
+  // max|r| in a second sweep over r[] so that the reduction scratch stays one value per lane
+  OKIN_PHASE_BEGIN
+  double mx = 0.0;
+  for (int t = lane; t < nrows; t += 32) {
+    const double ar = fabs(r[t]);
+    mx = (ar > mx || ar != ar) ? ar : mx;
+  }
+  red[lane] = mx;
+  OKIN_PHASE_END
+  const double rmax = okin_red_max(red);
   st.f2 = f2;
   st.rmax = rmax;
 }
@@ -860,18 +865,20 @@ OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, i
   const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* V = sm + hdr[OKIN_H_OFF_VEC] + n;
-  double* p1 = sm + hdr[OKIN_H_OFF_PPREV];
-  double* p2 = sm + hdr[OKIN_H_OFF_PPREV2];
+  // The history only shapes the starting point of the iteration, never the converged answer:
+  // single precision (1e-7 relative on mm-scale increments) is plenty and halves its footprint.
+  float* p1 = reinterpret_cast<float*>(sm + hdr[OKIN_H_OFF_PPREV]);
+  float* p2 = reinterpret_cast<float*>(sm + hdr[OKIN_H_OFF_PPREV2]);
   OKIN_PHASE_BEGIN
   for (int u = lane; u < n; u += 32) {
     double p = 0.0;
     for (int j = 0; j < nt; ++j) p = fma(V[j * n + u], dt[j], p);
-    const double a = p1[u], b = p2[u];
+    const double a = (double)p1[u], b = (double)p2[u];
     double step = p;
     if (order == 2) step = p + 0.5 * (p - a);
     if (order >= 3) step = (23.0 * p - 16.0 * a + 5.0 * b) * (1.0 / 12.0);
-    p2[u] = a;
-    p1[u] = p;
+    p2[u] = p1[u];
+    p1[u] = (float)p;
     pos[3 * OKIN_LDG(ep + u / 3) + u % 3] += step;
   }
   OKIN_PHASE_END

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Per-phase (source function) instruction and stall-sample shares of the sweep kernel.
 
-    python tools/ncu_phases.py sass.csv dis.txt n_states
+    python tools/ncu_phases.py sass.csv dis.txt n_states [kernel-section-substring]
 
 ``sass.csv``: ``ncu -i rep --page source --csv``; ``dis.txt``: ``nvdisasm -g -c`` of the cubin.
 Out-of-line device functions are separate .text sections in the disassembly and separate
@@ -15,6 +15,7 @@ from collections import defaultdict
 
 def main():
     sass, dis, states = sys.argv[1], sys.argv[2], float(sys.argv[3])
+    want = sys.argv[4] if len(sys.argv) > 4 else "okin_sweep_kernelILb0ELb0"
     core = open(__file__.replace("tools/ncu_phases.py", "open-kinematics_b200/csrc/okin_core.cuh")).read().split("\n")
     starts = []
     for i, line in enumerate(core, 1):
@@ -33,13 +34,17 @@ def main():
                 name = fn
         return name
 
-    locs, cur = [], None
+    locs, cur, active = [], None, False
     for raw in open(dis, errors="replace"):
+        m = re.match(r"\s*\.section\s+(\S+)", raw)
+        if m:   # one .text section per kernel instantiation: keep the profiled one
+            active = m.group(1).startswith(".text.") and want in m.group(1)
+            continue
         m = re.match(r'\s*//## File "([^"]+)", line (\d+)', raw)
         if m:
             cur = (m.group(1).split("/")[-1], int(m.group(2)))
             continue
-        if re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+\S", raw):
+        if active and re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+\S", raw):
             locs.append(cur)
     rows = list(csv.reader(open(sass)))
     agg = defaultdict(lambda: [0, 0, 0])
@@ -49,8 +54,8 @@ def main():
     hdr = rows[h]
     ci, si, ti = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
     data = [r for r in rows[h + 1:] if len(r) == len(hdr)]
-    # the dfma kernel precedes the sweep kernel in the cubin; align from the end
-    locs = locs[len(locs) - len(data):] if len(locs) >= len(data) else locs
+    if len(locs) != len(data):
+        print(f"warning: {len(locs)} disassembled instructions vs {len(data)} profiled rows", file=sys.stderr)
     for r, loc in zip(data, locs):
         n, s, t = int(r[ci]), int(r[si]), int(r[ti])
         a = agg[region(loc)]
