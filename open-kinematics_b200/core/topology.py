@@ -709,9 +709,7 @@ def compile_topology(
     isecs["OKIN_S_ROW_HOT"] = row_hot
     # Cold sections (setup, outputs requested per state, metrics, diagnostics) go last: the kernel
     # copies only the hot prefix of the blob to shared memory.
-    cold = ["OKIN_S_ROW", "OKIN_S_ROW_ORDER", "OKIN_S_IN_POINT", "OKIN_S_PAR_MODE", "OKIN_S_POINT_KIND",
-            "OKIN_S_DESIGN_PT", "OKIN_S_POINT_ELIM", "OKIN_S_POINT_DOP", "OKIN_S_MCORNER", "OKIN_S_MOP",
-            "OKIN_S_MAXLE", "OKIN_S_SHIM", "OKIN_S_SHIM_PTS", "OKIN_S_FREE_OUT", "OKIN_S_DGOP", "OKIN_S_ELIM_COL"]
+    cold = [k for k in isecs if D[k] >= D["OKIN_S_COLD0"]]
     isecs = {**{k: v for k, v in isecs.items() if k not in cold}, **{k: isecs[k] for k in cold}}
     hdr = np.zeros(D["OKIN_HDR_SIZE"], np.int32)
     chunks, cursor, n_hot = [], 0, None

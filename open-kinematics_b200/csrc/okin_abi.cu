@@ -77,15 +77,17 @@ __global__ void __launch_bounds__(OKIN_MAX_THREADS, 1)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, OkinSolverCfg cfg, okin_batch_io io, int n_iblob,
                   int table_doubles) {
-  extern __shared__ double okin_smem[];
-  int32_t* shdr = reinterpret_cast<int32_t*>(okin_smem);
+  // [section pointers][header][hot tables][one state slice per warp]
+  const int32_t** sec = reinterpret_cast<const int32_t**>(okin_smem);
+  int32_t* shdr = reinterpret_cast<int32_t*>(okin_smem + OKIN_S_COUNT);
   int32_t* tab = shdr + OKIN_HDR_SIZE;
   for (int i = threadIdx.x; i < OKIN_HDR_SIZE; i += blockDim.x) shdr[i] = hdr[i];
   const int n_hot = hdr[OKIN_H_NHOT];
   for (int i = threadIdx.x; i < n_hot; i += blockDim.x) tab[i] = ib[i];
+  for (int i = threadIdx.x; i < OKIN_S_COUNT; i += blockDim.x) okin_resolve_section(hdr, tab, ib, i, sec);
   __syncthreads();
   hdr = shdr;
-  OkinProgram pr{shdr, tab, fb, ib};
+  OkinProgram pr{shdr, tab, fb, ib, sec};
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   double* sm = okin_smem + table_doubles + (size_t)warp * hdr[OKIN_H_SMEM_DOUBLES];
@@ -124,10 +126,12 @@ __global__ void okin_continuity_kernel(const int32_t* __restrict__ hdr, const in
                                        long long n_instances, int n_steps, int stride,
                                        const double* __restrict__ positions, const int32_t* __restrict__ failed_step,
                                        double* diag, double* jumps) {
-  extern __shared__ double okin_smem[];
-  OkinProgram pr{hdr, ib, nullptr, ib};
+  const int32_t** sec = reinterpret_cast<const int32_t**>(okin_smem);
+  for (int i = threadIdx.x; i < OKIN_S_COUNT; i += blockDim.x) okin_resolve_section(hdr, ib, ib, i, sec);
+  __syncthreads();
+  OkinProgram pr{hdr, ib, nullptr, ib, sec};
   const int warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
-  double* scratch = okin_smem + (size_t)warp * (32 * stride + 64);
+  double* scratch = okin_smem + OKIN_S_COUNT + (size_t)warp * (32 * stride + 64);
   const size_t nout3 = 3 * (size_t)hdr[OKIN_H_NOUT], nd = hdr[OKIN_H_NDIAG], nf = hdr[OKIN_H_NF];
   for (long long i = (long long)blockIdx.x * warps_per_cta + warp; i < n_instances;
        i += (long long)gridDim.x * warps_per_cta) {
@@ -170,7 +174,8 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
     d.smem_optin = (int)prop.sharedMemPerBlockOptin;
     // CTA shape: W warps sharing one copy of the tables; pick the W that keeps the most warps resident
     // (shared memory, the 64K-register file at OKIN_REGS_PER_THREAD, 1 KB per-CTA reservation).
-    d.table_doubles = (int)((((size_t)t->hdr[OKIN_H_NHOT] + OKIN_HDR_SIZE) * sizeof(int32_t) + 7) / 8);
+    d.table_doubles =
+        OKIN_S_COUNT + (int)((((size_t)t->hdr[OKIN_H_NHOT] + OKIN_HDR_SIZE) * sizeof(int32_t) + 7) / 8);
     const size_t table_bytes = (size_t)d.table_doubles * 8;
     const size_t slice_bytes = (size_t)t->hdr[OKIN_H_SMEM_DOUBLES] * sizeof(double);
     const size_t sm_budget = prop.sharedMemPerMultiprocessor;
@@ -229,13 +234,15 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
     // continuity pass over the position rows the sweep kernel just wrote (same stream)
     const int stride = (n_steps - 1) | 1;   // odd: lanes walk their histories on different banks
     const size_t per_warp = ((size_t)32 * stride + 64) * sizeof(double);
+    const size_t fixed = OKIN_S_COUNT * sizeof(double);   // section pointer table
     int cw = 4;
-    while (cw > 1 && cw * per_warp > (size_t)d->smem_optin) cw >>= 1;
-    if (cw * per_warp > (size_t)d->smem_optin) return fail(OKIN_ERR_USAGE, "too many sweep steps for the continuity diagnostics");
+    while (cw > 1 && fixed + cw * per_warp > (size_t)d->smem_optin) cw >>= 1;
+    if (fixed + cw * per_warp > (size_t)d->smem_optin)
+      return fail(OKIN_ERR_USAGE, "too many sweep steps for the continuity diagnostics");
     OKIN_CUDA(cudaFuncSetAttribute(okin_continuity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(cw * per_warp)));
+                                   (int)(fixed + cw * per_warp)));
     const int cgrid = (int)std::min<int64_t>((n_instances + cw - 1) / cw, (int64_t)d->num_sms * 8);
-    okin_continuity_kernel<<<cgrid, cw * 32, cw * per_warp, stream>>>(
+    okin_continuity_kernel<<<cgrid, cw * 32, fixed + cw * per_warp, stream>>>(
         d->hdr, d->ib, (long long)n_instances, n_steps, stride, io.positions, io.failed_step, io.diagnostics,
         io.jumps);
     OKIN_CUDA(cudaGetLastError());
@@ -306,6 +313,14 @@ int okin_topology_create(const okin_topology_desc* desc, okin_topology** out) {
   }
   if (desc->hdr[OKIN_H_NHOT] < 0 || desc->hdr[OKIN_H_NHOT] > desc->n_iblob)
     return fail(OKIN_ERR_USAGE, "hot prefix out of range");
+  // The device code addresses sections below OKIN_S_COLD0 as shared memory: they must lie in the
+  // hot prefix, the others behind it.
+  for (int s = 0; s < OKIN_S_COUNT; ++s) {
+    const int64_t off = desc->hdr[OKIN_H_SEC0 + 2 * s], len = desc->hdr[OKIN_H_SEC0 + 2 * s + 1];
+    const bool in_hot = off + len <= desc->hdr[OKIN_H_NHOT];
+    if (s < OKIN_S_COLD0 ? !in_hot : (len > 0 && off < desc->hdr[OKIN_H_NHOT]))
+      return fail(OKIN_ERR_USAGE, "section on the wrong side of the hot prefix");
+  }
   if (desc->hdr[OKIN_H_NT] > OKIN_MAX_TARGETS) return fail(OKIN_ERR_USAGE, "too many targets");
   okin_topology* t = new okin_topology();
   t->hdr.assign(desc->hdr, desc->hdr + OKIN_HDR_SIZE);

@@ -44,6 +44,22 @@
 #define OKIN_LDG(p) (*(p))
 #endif
 
+// Address-space hint.  The per-instance state, the header and the hot tables live in the CTA's dynamic
+// shared memory, but they reach the (out-of-line) phase functions as generic pointers, for which the
+// compiler emits generic loads and 64-bit address arithmetic.  OKIN_SHARED re-derives a pointer from
+// the shared array symbol, which lets it prove the address space (LDS/STS, 32-bit addressing).  Only
+// for pointers that are in shared memory in the sweep kernel; identity in the lane emulation.
+#if defined(__CUDACC__) && !defined(OKIN_LANE_EMU)
+extern __shared__ double okin_smem[];
+#endif
+#if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
+#define OKIN_SHARED(p)                                                                  \
+  (reinterpret_cast<decltype(p)>(reinterpret_cast<char*>(okin_smem) +                   \
+                                 (reinterpret_cast<const char*>(p) - reinterpret_cast<const char*>(okin_smem))))
+#else
+#define OKIN_SHARED(p) (p)
+#endif
+
 // Unroll factor of the gather loops over a task's contributions (factor update, triangular solves,
 // assembly).  Not unrolled by default: the trip counts are 1-8 and data dependent, and the smaller
 // code measured 5 % faster than the compiler's own 4x unrolling (profiles/r01_g_*).
@@ -92,6 +108,8 @@ struct OkinProgram {
   const int32_t* ib;   // int32 blob: at least its hot prefix hdr[OKIN_H_NHOT] (shared memory in the kernel)
   const double* fb;    // double blob
   const int32_t* ibc;  // whole int32 blob (global memory); cold sections are read from here
+  const int32_t* const* sec;  // [OKIN_S_COUNT] start of every int32 section (hot: in ib, cold: in ibc),
+                              // resolved once per CTA by okin_resolve_sections
 };
 
 struct OkinSolverCfg {
@@ -105,9 +123,12 @@ struct OkinSolverCfg {
   int32_t use_predictor;  // continuation predictor order: 0 warm start only, 1..3 (Adams-Bashforth on the tangents)
 };
 
-OKIN_HD const int32_t* okin_sec(const OkinProgram& pr, int s) {
-  const int off = pr.hdr[OKIN_H_SEC0 + 2 * s];
-  return (off < pr.hdr[OKIN_H_NHOT] ? pr.ib : pr.ibc) + off;
+OKIN_HD const int32_t* okin_sec(const OkinProgram& pr, int s) { return OKIN_SHARED(pr.sec)[s]; }
+// Fills table[s] for section s: the hot prefix of the blob lives at ib, the rest at ibc.
+OKIN_HD void okin_resolve_section(const int32_t* hdr, const int32_t* ib, const int32_t* ibc, int s,
+                                  const int32_t** table) {
+  const int off = hdr[OKIN_H_SEC0 + 2 * s];
+  table[s] = (off < hdr[OKIN_H_NHOT] ? ib : ibc) + off;
 }
 OKIN_HD int okin_sec_len(const OkinProgram& pr, int s) { return pr.hdr[OKIN_H_SEC0 + 2 * s + 1]; }
 OKIN_HD const double* okin_fsec(const OkinProgram& pr, int s) { return pr.fb + pr.hdr[OKIN_H_FSEC0 + 2 * s]; }
@@ -159,8 +180,9 @@ OKIN_HD void okin_dop_eval(int op, double par, const double* a, const double* b,
 // active_only: only the ops referenced by solve rows (wheel centre, strut clamp).
 template <typename Dummy = void>
 OKIN_FN void okin_derived_update(const OkinProgram& pr, double* sm, bool active_only) {
-  const int32_t* dop = okin_sec(pr, OKIN_S_DOP);
-  const int32_t* lev = okin_sec(pr, OKIN_S_DOP_LEV);
+  sm = OKIN_SHARED(sm);
+  const int32_t* dop = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP));
+  const int32_t* lev = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP_LEV));
   const int nlev = okin_sec_len(pr, OKIN_S_DOP_LEV) - 1;
   double* pos = sm + pr.hdr[OKIN_H_OFF_POS];
   const double* par = sm + pr.hdr[OKIN_H_OFF_PAR];
@@ -186,11 +208,12 @@ OKIN_FN void okin_derived_update(const OkinProgram& pr, double* sm, bool active_
 // pushing it through the op chain (manager.py:271-324 does the same with dual numbers).
 template <typename Dummy = void>
 OKIN_FN void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
+  sm = OKIN_SHARED(sm);
   const int nad = pr.hdr[OKIN_H_NAD];
   if (nad == 0) return;
-  const int32_t* adj = okin_sec(pr, OKIN_S_ADJ);
-  const int32_t* chain = okin_sec(pr, OKIN_S_ADJ_CHAIN);
-  const int32_t* dop = okin_sec(pr, OKIN_S_DOP);
+  const int32_t* adj = OKIN_SHARED(okin_sec(pr, OKIN_S_ADJ));
+  const int32_t* chain = OKIN_SHARED(okin_sec(pr, OKIN_S_ADJ_CHAIN));
+  const int32_t* dop = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP));
   const double* pos = sm + pr.hdr[OKIN_H_OFF_POS];
   const double* par = sm + pr.hdr[OKIN_H_OFF_PAR];
   double* dblk = sm + pr.hdr[OKIN_H_OFF_DBLK];
@@ -240,7 +263,8 @@ OKIN_FN void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
 OKIN_FN void okin_shim_presolve(const OkinProgram& pr, double* sm, const double* params, int* invalid) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nshim = hdr[OKIN_H_NSHIM];
   if (nshim == 0) return;
   const int32_t* recs = okin_sec(pr, OKIN_S_SHIM);
@@ -379,7 +403,8 @@ OKIN_FN void okin_shim_presolve(const OkinProgram& pr, double* sm, const double*
 template <bool SHIM>
 OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints,
                         const double* __restrict__ params, int* invalid) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* cst = sm + hdr[OKIN_H_OFF_CST];
   double* par = sm + hdr[OKIN_H_OFF_PAR];
@@ -393,7 +418,7 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
   // Derived-op parameters.  A design projection reads the *authored* position of the derived
   // point (macpherson.py:199-204), which is what pos[] still holds at this moment.
   const int ndop = hdr[OKIN_H_NDOP];
-  const int32_t* dop = okin_sec(pr, OKIN_S_DOP);
+  const int32_t* dop = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP));
   const int32_t* par_mode = okin_sec(pr, OKIN_S_PAR_MODE);
   const double* par_val = okin_fsec(pr, OKIN_F_PAR_VAL);
   OKIN_PHASE_BEGIN
@@ -482,20 +507,21 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
 OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tval, bool with_grad, OkinState& st) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   okin_derived_update(pr, sm, true);
   if (with_grad) okin_derived_jacobians(pr, sm);
   const int nls = hdr[OKIN_H_NROW];
   const int nrows = nls + hdr[OKIN_H_NREP];
-  const int32_t* rows = okin_sec(pr, OKIN_S_ROW_HOT);
-  const int32_t* der = okin_sec(pr, OKIN_S_DER);
+  const int32_t* rows = OKIN_SHARED(okin_sec(pr, OKIN_S_ROW_HOT));
+  const int32_t* der = OKIN_SHARED(okin_sec(pr, OKIN_S_DER));
   const double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* cst = sm + hdr[OKIN_H_OFF_CST];
   const double* dblk = sm + hdr[OKIN_H_OFF_DBLK];
   double* r = sm + hdr[OKIN_H_OFF_R];
   double* rg = sm + hdr[OKIN_H_OFF_RG];
   double* red = sm + hdr[OKIN_H_OFF_RED];
-  const int32_t* drow = okin_sec(pr, OKIN_S_DROW);
+  const int32_t* drow = OKIN_SHARED(okin_sec(pr, OKIN_S_DROW));
   const int ndrow = hdr[OKIN_H_NDROW], ngrow = hdr[OKIN_H_NGROW];
   OKIN_PHASE_BEGIN
   double sq = 0.0;
@@ -587,14 +613,15 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
 OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_only) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nat = hdr[OKIN_H_NAT];
   const int nf = hdr[OKIN_H_NF];
-  const int32_t* aptr = okin_sec(pr, OKIN_S_ASM_PTR);
-  const int32_t* atask = okin_sec(pr, OKIN_S_ASM_TASK);
-  const int32_t* acon = okin_sec(pr, OKIN_S_ASM_CON);
-  const int32_t* gptr = okin_sec(pr, OKIN_S_G_PTR);
-  const int32_t* gcon = okin_sec(pr, OKIN_S_G_CON);
+  const int32_t* aptr = OKIN_SHARED(okin_sec(pr, OKIN_S_ASM_PTR));
+  const int32_t* atask = OKIN_SHARED(okin_sec(pr, OKIN_S_ASM_TASK));
+  const int32_t* acon = OKIN_SHARED(okin_sec(pr, OKIN_S_ASM_CON));
+  const int32_t* gptr = OKIN_SHARED(okin_sec(pr, OKIN_S_G_PTR));
+  const int32_t* gcon = OKIN_SHARED(okin_sec(pr, OKIN_S_G_CON));
   const double* rg = sm + hdr[OKIN_H_OFF_RG];
   const double* r = sm + hdr[OKIN_H_OFF_R];
   double* Lb = sm + hdr[OKIN_H_OFF_LB];
@@ -663,6 +690,7 @@ OKIN_HD bool okin_chol3(const double* d, double f[9]) {
 // {l00,l10,l11,l20,l21,l22, 1/l00,1/l11,1/l22} is written over it -- one level later, inside the
 // next level's update phase (which never reads diagonal blocks of finished columns).
 OKIN_HD void okin_write_diag_factor(double* sm, int doff, double* red, int lane) {
+  sm = OKIN_SHARED(sm);
   double f[9];
   const bool ok = okin_chol3(sm + doff, f);
   double* o = sm + doff;
@@ -672,17 +700,18 @@ OKIN_HD void okin_write_diag_factor(double* sm, int doff, double* red, int lane)
 
 template <typename Dummy = void>
 OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nlev = hdr[OKIN_H_NLEV];
-  const int32_t* lev_upd = okin_sec(pr, OKIN_S_LEV_UPD);
-  const int32_t* udst = okin_sec(pr, OKIN_S_UPD_DST);
-  const int32_t* uptr = okin_sec(pr, OKIN_S_UPD_PTR);
-  const int32_t* ucon = okin_sec(pr, OKIN_S_UPD_CON);
-  const int32_t* lev_scl = okin_sec(pr, OKIN_S_LEV_SCL);
-  const int32_t* scl = okin_sec(pr, OKIN_S_SCL);
-  const int32_t* lcp = okin_sec(pr, OKIN_S_LEV_COL_PTR);
-  const int32_t* lcol = okin_sec(pr, OKIN_S_LEV_COL);
-  const int32_t* doffs = okin_sec(pr, OKIN_S_DIAG_OFF);
+  const int32_t* lev_upd = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_UPD));
+  const int32_t* udst = OKIN_SHARED(okin_sec(pr, OKIN_S_UPD_DST));
+  const int32_t* uptr = OKIN_SHARED(okin_sec(pr, OKIN_S_UPD_PTR));
+  const int32_t* ucon = OKIN_SHARED(okin_sec(pr, OKIN_S_UPD_CON));
+  const int32_t* lev_scl = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_SCL));
+  const int32_t* scl = OKIN_SHARED(okin_sec(pr, OKIN_S_SCL));
+  const int32_t* lcp = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_COL_PTR));
+  const int32_t* lcol = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_COL));
+  const int32_t* doffs = OKIN_SHARED(okin_sec(pr, OKIN_S_DIAG_OFF));
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   red[lane] = 0.0;
@@ -698,7 +727,7 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
         double* dst = sm + OKIN_LDG(udst + t);
         double c0 = dst[0], c1 = dst[1], c2 = dst[2];
         OKIN_UNROLL_INNER
-      for (int q = b; q < e; ++q) {
+        for (int q = b; q < e; ++q) {
           const uint32_t w = (uint32_t)OKIN_LDG(ucon + q);
           const double* a = sm + (w >> 16);
           const double* B = sm + (w & 0xffffu);
@@ -738,17 +767,18 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
 // as an extra row).
 template <typename Dummy = void>
 OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, bool skip_forward) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nlev = hdr[OKIN_H_NLEV];
   const int n = 3 * hdr[OKIN_H_NF];
-  const int32_t* lcp = okin_sec(pr, OKIN_S_LEV_COL_PTR);
-  const int32_t* lcol = okin_sec(pr, OKIN_S_LEV_COL);
-  const int32_t* fptr = okin_sec(pr, OKIN_S_FW_PTR);
-  const int32_t* fcon = okin_sec(pr, OKIN_S_FW_CON);
-  const int32_t* bptr = okin_sec(pr, OKIN_S_BW_PTR);
-  const int32_t* bcon = okin_sec(pr, OKIN_S_BW_CON);
+  const int32_t* lcp = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_COL_PTR));
+  const int32_t* lcol = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_COL));
+  const int32_t* fptr = OKIN_SHARED(okin_sec(pr, OKIN_S_FW_PTR));
+  const int32_t* fcon = OKIN_SHARED(okin_sec(pr, OKIN_S_FW_CON));
+  const int32_t* bptr = OKIN_SHARED(okin_sec(pr, OKIN_S_BW_PTR));
+  const int32_t* bcon = OKIN_SHARED(okin_sec(pr, OKIN_S_BW_CON));
   const double* Lb = sm;
-  const int32_t* doffs = okin_sec(pr, OKIN_S_DIAG_OFF);
+  const int32_t* doffs = OKIN_SHARED(okin_sec(pr, OKIN_S_DIAG_OFF));
   double* vec = sm + hdr[OKIN_H_OFF_VEC] + first * n;
   for (int lv = 0; lv < (skip_forward ? 0 : nlev); ++lv) {  // L y = b
     const int cb = OKIN_LDG(lcp + lv), ce = OKIN_LDG(lcp + lv + 1);
@@ -803,9 +833,10 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
 // pos[free] += scale * vec[which]; returns max|vec[which]| (warp-uniform).
 template <typename Dummy = void>
 OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, double scale, bool save) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int n = 3 * hdr[OKIN_H_NF];
-  const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
+  const int32_t* ep = OKIN_SHARED(okin_sec(pr, OKIN_S_ELIM_POINT));
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* v = sm + hdr[OKIN_H_OFF_VEC] + which * n;
   double* red = sm + hdr[OKIN_H_OFF_RED];
@@ -826,9 +857,10 @@ OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, dou
 
 template <typename Dummy = void>
 OKIN_FN void okin_restore(const OkinProgram& pr, double* sm) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int n = 3 * hdr[OKIN_H_NF];
-  const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
+  const int32_t* ep = OKIN_SHARED(okin_sec(pr, OKIN_S_ELIM_POINT));
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* h = sm + hdr[OKIN_H_OFF_VEC];   // the step just applied (vec[0], scale 1)
   OKIN_PHASE_BEGIN
@@ -839,6 +871,7 @@ OKIN_FN void okin_restore(const OkinProgram& pr, double* sm) {
 // max|vec[which]| (warp-uniform).
 template <typename Dummy = void>
 OKIN_FN double okin_vec_max(const OkinProgram& pr, double* sm, int which) {
+  sm = OKIN_SHARED(sm);
   const int n = 3 * pr.hdr[OKIN_H_NF];
   const double* v = sm + pr.hdr[OKIN_H_OFF_VEC] + which * n;
   double* red = sm + pr.hdr[OKIN_H_OFF_RED];
@@ -859,10 +892,11 @@ OKIN_FN double okin_vec_max(const OkinProgram& pr, double* sm, int which) {
 // V_j are the tangents of the previous state; p_{k-1}, p_{k-2} are kept in shared memory.
 template <typename Dummy = void>
 OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, int order) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int n = 3 * hdr[OKIN_H_NF];
   const int nt = hdr[OKIN_H_NT];
-  const int32_t* ep = okin_sec(pr, OKIN_S_ELIM_POINT);
+  const int32_t* ep = OKIN_SHARED(okin_sec(pr, OKIN_S_ELIM_POINT));
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* V = sm + hdr[OKIN_H_OFF_VEC] + n;
   // The history only shapes the starting point of the iteration, never the converged answer:
@@ -889,11 +923,12 @@ OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, i
 // lstsq([J; pins], e_j) == (J^T J)^{-1} J^T e_j).  Uses the target rows of rg[].
 template <typename Dummy = void>
 OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nt = hdr[OKIN_H_NT];
   const int n = 3 * hdr[OKIN_H_NF];
-  const int32_t* sptr = okin_sec(pr, OKIN_S_TGT_SC_PTR);
-  const int32_t* sc = okin_sec(pr, OKIN_S_TGT_SC);
+  const int32_t* sptr = OKIN_SHARED(okin_sec(pr, OKIN_S_TGT_SC_PTR));
+  const int32_t* sc = OKIN_SHARED(okin_sec(pr, OKIN_S_TGT_SC));
   const double* rg = sm + hdr[OKIN_H_OFF_RG];
   double* vec = sm + hdr[OKIN_H_OFF_VEC] + n;
   OKIN_PHASE_BEGIN
@@ -919,6 +954,7 @@ OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
 template <typename Dummy = void>
 OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tval, const OkinSolverCfg& cfg,
                             OkinState& st, bool* converged, bool* tangents_ready) {
+  sm = OKIN_SHARED(sm);
   const int nt = pr.hdr[OKIN_H_NT];
   int nfev = 0;
   *tangents_ready = false;
@@ -1006,6 +1042,7 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
 // rest, derived points push their inputs' velocities through the op (sensitivity.py:118-141).
 // Derived inputs of derived points are supported one level deep (contact patch <- wheel centre).
 OKIN_HD void okin_point_vel_base(const OkinProgram& pr, const double* sm, int p, int j, double v[3]) {
+  sm = OKIN_SHARED(sm);
   v[0] = v[1] = v[2] = 0.0;
   if (p < 0) return;
   const int e = OKIN_LDG(okin_sec(pr, OKIN_S_POINT_ELIM) + p);
@@ -1015,7 +1052,8 @@ OKIN_HD void okin_point_vel_base(const OkinProgram& pr, const double* sm, int p,
 }
 OKIN_HD void okin_point_vel_op(const OkinProgram& pr, const double* sm, int d, const double* da, const double* db,
                                const double* dc, double v[3]) {
-  const int32_t* rec = okin_sec(pr, OKIN_S_DOP) + d * OKIN_DOP_STRIDE;
+  sm = OKIN_SHARED(sm);
+  const int32_t* rec = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP)) + d * OKIN_DOP_STRIDE;
   const int ia = OKIN_LDG(rec + 2), ib = OKIN_LDG(rec + 3), ic = OKIN_LDG(rec + 4);
   const double* pos = sm + pr.hdr[OKIN_H_OFF_POS];
   const double* par = sm + pr.hdr[OKIN_H_OFF_PAR];
@@ -1024,9 +1062,10 @@ OKIN_HD void okin_point_vel_op(const OkinProgram& pr, const double* sm, int d, c
                 pos + 3 * (ic < 0 ? ia : ic), da, db, dc, out, v);
 }
 OKIN_HD void okin_point_vel1(const OkinProgram& pr, const double* sm, int p, int j, double v[3]) {
+  sm = OKIN_SHARED(sm);
   const int d = p < 0 ? -1 : OKIN_LDG(okin_sec(pr, OKIN_S_POINT_DOP) + p);
   if (d < 0) { okin_point_vel_base(pr, sm, p, j, v); return; }
-  const int32_t* rec = okin_sec(pr, OKIN_S_DOP) + d * OKIN_DOP_STRIDE;
+  const int32_t* rec = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP)) + d * OKIN_DOP_STRIDE;
   double da[3], db[3], dc[3];
   okin_point_vel_base(pr, sm, OKIN_LDG(rec + 2), j, da);
   okin_point_vel_base(pr, sm, OKIN_LDG(rec + 3), j, db);
@@ -1034,9 +1073,10 @@ OKIN_HD void okin_point_vel1(const OkinProgram& pr, const double* sm, int p, int
   okin_point_vel_op(pr, sm, d, da, db, dc, v);
 }
 OKIN_HD void okin_point_vel(const OkinProgram& pr, const double* sm, int p, int j, double v[3]) {
+  sm = OKIN_SHARED(sm);
   const int d = p < 0 ? -1 : OKIN_LDG(okin_sec(pr, OKIN_S_POINT_DOP) + p);
   if (d < 0) { okin_point_vel_base(pr, sm, p, j, v); return; }
-  const int32_t* rec = okin_sec(pr, OKIN_S_DOP) + d * OKIN_DOP_STRIDE;
+  const int32_t* rec = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP)) + d * OKIN_DOP_STRIDE;
   double da[3], db[3], dc[3];
   okin_point_vel1(pr, sm, OKIN_LDG(rec + 2), j, da);
   okin_point_vel1(pr, sm, OKIN_LDG(rec + 3), j, db);
@@ -1047,7 +1087,8 @@ OKIN_HD void okin_point_vel(const OkinProgram& pr, const double* sm, int p, int 
 // One generic response on T in {double, OkinDual}; vel == nullptr for plain values.
 template <typename T>
 OKIN_HD T okin_response(const OkinProgram& pr, const double* sm, const int32_t* rec, int j) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
   const double* fc = okin_fsec(pr, OKIN_F_MCONST) + OKIN_LDG(rec + 12);
@@ -1101,7 +1142,8 @@ OKIN_HD T okin_response(const OkinProgram& pr, const double* sm, const int32_t* 
 
 // 19 corner state metrics of catalog.py:86-159 for one corner; one lane.
 OKIN_HD void okin_corner_metrics(const OkinProgram& pr, double* sm, const int32_t* rec, double* out, double* ctx) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
   const double* fc = okin_fsec(pr, OKIN_F_MCONST) + OKIN_LDG(rec + 18);
@@ -1226,7 +1268,8 @@ OKIN_HD void okin_corner_metrics(const OkinProgram& pr, double* sm, const int32_
 // All metric columns of one state into out[NM].
 template <typename Dummy = void>
 OKIN_FN void okin_metrics(const OkinProgram& pr, double* sm, double* out) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nmc = hdr[OKIN_H_NMC], nmop = hdr[OKIN_H_NMOP];
   const int32_t* corners = okin_sec(pr, OKIN_S_MCORNER);
   const int32_t* mops = okin_sec(pr, OKIN_S_MOP);
@@ -1322,7 +1365,8 @@ OKIN_HD double okin_stp(const double* o, const double* a, const double* b, const
 // filled by okin_continuity).  ok: the state was accepted; status: the instance status so far.
 template <typename Dummy = void>
 OKIN_FN void okin_diagnostics(const OkinProgram& pr, double* sm, double* row, bool ok, int status) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nd = hdr[OKIN_H_NDIAG], nop = hdr[OKIN_H_NDGOP];
   const double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
@@ -1407,7 +1451,7 @@ OKIN_FN void okin_diagnostics(const OkinProgram& pr, double* sm, double* row, bo
 template <typename Dummy = void>
 OKIN_HD void okin_continuity(const OkinProgram& pr, double* scratch, int stride, const double* positions,
                              int n_steps, int n_ok, double* diag, double* jumps) {
-  const int32_t* hdr = pr.hdr;
+  const int32_t* hdr = pr.hdr;   // global memory in the continuity kernel
   const int nf = hdr[OKIN_H_NF], nout3 = 3 * hdr[OKIN_H_NOUT], nd = hdr[OKIN_H_NDIAG];
   const int32_t* free_out = okin_sec(pr, OKIN_S_FREE_OUT);
   const int ntr = n_ok > 1 ? n_ok - 1 : 0;
@@ -1486,11 +1530,12 @@ OKIN_HD void okin_continuity(const OkinProgram& pr, double* scratch, int stride,
 // z = L^T x (lt) or x = L z (plain) with the block factor; returns |result|^2 (warp-uniform).
 template <typename Dummy = void>
 OKIN_FN double okin_factor_multiply(const OkinProgram& pr, double* sm, const double* src, double* dst, bool lt) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nf = hdr[OKIN_H_NF];
   const int32_t* ptr = okin_sec(pr, lt ? OKIN_S_BW_PTR : OKIN_S_FW_PTR);
   const int32_t* con = okin_sec(pr, lt ? OKIN_S_BW_CON : OKIN_S_FW_CON);
-  const int32_t* doffs = okin_sec(pr, OKIN_S_DIAG_OFF);
+  const int32_t* doffs = OKIN_SHARED(okin_sec(pr, OKIN_S_DIAG_OFF));
   const double* Lb = sm;
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
@@ -1526,6 +1571,7 @@ OKIN_FN double okin_factor_multiply(const OkinProgram& pr, double* sm, const dou
 // v *= s; returns nothing.  |v|^2 helper below.
 template <typename Dummy = void>
 OKIN_FN double okin_scale_norm2(const OkinProgram& pr, double* sm, double* v, double s) {
+  sm = OKIN_SHARED(sm);
   const int n = 3 * pr.hdr[OKIN_H_NF];
   double* red = sm + pr.hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
@@ -1551,7 +1597,8 @@ OKIN_FN double okin_scale_norm2(const OkinProgram& pr, double* sm, double* v, do
 #define OKIN_HEALTH_ITERS 24
 template <typename Dummy = void>
 OKIN_FN void okin_tangent_health(const OkinProgram& pr, double* sm, bool notpd, double* out2) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int n = 3 * hdr[OKIN_H_NF];
   double* x = sm + hdr[OKIN_H_OFF_RG];
   double* z = x + n;
@@ -1612,11 +1659,12 @@ template <bool FULL, bool SHIM>
 OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints,
                         const double* __restrict__ params, const double* __restrict__ tvals, int n_steps,
                         const OkinSolverCfg& cfg, const OkinOutputs& out) {
-  const int32_t* hdr = pr.hdr;
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nt = hdr[OKIN_H_NT];
   const int n = 3 * hdr[OKIN_H_NF];
   const int nout = hdr[OKIN_H_NOUT];
-  const int32_t* out_point = okin_sec(pr, OKIN_S_OUT_POINT);
+  const int32_t* out_point = OKIN_SHARED(okin_sec(pr, OKIN_S_OUT_POINT));
   const int32_t* ecol = okin_sec(pr, OKIN_S_ELIM_COL);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* vec = sm + hdr[OKIN_H_OFF_VEC];

@@ -135,13 +135,11 @@ enum okin_hdr_slot {
 
 // int32 sections
 enum okin_isec {
-  OKIN_S_POINT_KIND = 0, // [P]
-  OKIN_S_IN_POINT,       // [NIN] input slot -> point
-  OKIN_S_DOP,            // [NDOP][OKIN_DOP_STRIDE]
-  OKIN_S_PAR_MODE,       // [NPAR]
+  // hot sections: read inside the iteration; the sweep kernel keeps them in shared memory and the
+  // device code addresses them as shared (OKIN_SHARED)
+  OKIN_S_DOP = 0,            // [NDOP][OKIN_DOP_STRIDE]
   OKIN_S_ADJ,            // [NAD][OKIN_ADJ_STRIDE]
   OKIN_S_ADJ_CHAIN,      // derived-op indices, referenced by ADJ
-  OKIN_S_ROW,            // [NROW+NREP][OKIN_ROW_STRIDE]
   OKIN_S_DER,            // [..][OKIN_DER_STRIDE]
   OKIN_S_ASM_PTR,        // [NAT+1] contribution ranges per assembly task (one task per 3x3 block)
   OKIN_S_ASM_TASK,       // [NAT] block id | OKIN_ASM_DIAG flag, heaviest task first
@@ -161,26 +159,33 @@ enum okin_isec {
   OKIN_S_BW_PTR,         // [NF+1]
   OKIN_S_BW_CON,         // (block offset << 16) | (3*I)
   OKIN_S_ELIM_POINT,     // [NF] elimination position -> point index
-  OKIN_S_ELIM_COL,       // [NF] elimination position -> reference column block (sorted free-point order)
   OKIN_S_TGT_SC_PTR,     // [NT+1]
   OKIN_S_TGT_SC,         // (rg index << 16) | unknown index (elimination order)
   OKIN_S_OUT_POINT,      // [NOUT]
-  OKIN_S_ROW_ORDER,      // [NROW+NREP] evaluation order (rows grouped by family)
   OKIN_S_DOP_LEV,        // [n_derived_levels+1] ranges of DOP evaluated in one parallel phase
+  OKIN_S_DROW,           // [3][NDROW] = {p0 | p1 << 16}, {cst_off | rg_off << 16}, {row}: plain distance rows
+  OKIN_S_DIAG_OFF,       // [NF] shared-memory offset of the diagonal block of elimination column j
+  OKIN_S_ROW_HOT,        // [NGROW][OKIN_ROW_STRIDE] records of the generic-path rows in evaluation order
+                         // (grouped by family), each carrying its row index in OKIN_R_ROWID
+  // cold sections (index >= OKIN_S_COLD0): set-up rules, outputs requested per state, metrics,
+  // diagnostics, shims; they stay in global memory
+  OKIN_S_COLD0,
+  OKIN_S_ROW = OKIN_S_COLD0,            // [NROW+NREP][OKIN_ROW_STRIDE]
+  OKIN_S_ROW_ORDER,      // [NROW+NREP] evaluation order (rows grouped by family)
+  OKIN_S_IN_POINT,       // [NIN] input slot -> point
+  OKIN_S_PAR_MODE,       // [NPAR]
+  OKIN_S_POINT_KIND, // [P]
+  OKIN_S_DESIGN_PT,      // [NDSN] points whose design position is kept for the metrics
   OKIN_S_POINT_ELIM,     // [P] elimination position of a free point, else -1
   OKIN_S_POINT_DOP,      // [P] derived-op index of a derived point, else -1
-  OKIN_S_DESIGN_PT,      // [NDSN] points whose design position is kept for the metrics
   OKIN_S_MCORNER,        // [NMC][OKIN_MCORNER_STRIDE]
   OKIN_S_MOP,            // [NMOP][OKIN_MOP_STRIDE]
   OKIN_S_MAXLE,          // [NMAXLE][OKIN_MAXLE_STRIDE]
   OKIN_S_SHIM,           // [NSHIM][OKIN_SHIM_STRIDE]
   OKIN_S_SHIM_PTS,       // point lists referenced by SHIM (upright attachments, rocker group)
-  OKIN_S_DROW,           // [3][NDROW] = {p0 | p1 << 16}, {cst_off | rg_off << 16}, {row}: plain distance rows
-  OKIN_S_DIAG_OFF,       // [NF] shared-memory offset of the diagonal block of elimination column j
   OKIN_S_FREE_OUT,       // [NF] output slot of free point k (reference column order), -1 = not exported
   OKIN_S_DGOP,           // [NDGOP][OKIN_DGOP_STRIDE] topology diagnostic ops
-  OKIN_S_ROW_HOT,        // [NGROW][OKIN_ROW_STRIDE] records of the generic-path rows in evaluation order
-                         // (grouped by family), each carrying its row index in OKIN_R_ROWID
+  OKIN_S_ELIM_COL,       // [NF] elimination position -> reference column block (sorted free-point order)
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000

@@ -11,7 +11,9 @@
 extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const double* fb, long n_instances,
                               int n_steps, const okin_solver_cfg* c, const okin_batch_io* io) {
   if (hdr[OKIN_H_MAGIC] != OKIN_MAGIC) return -1;
-  OkinProgram pr{hdr, ib, fb, ib};
+  const int32_t* sec[OKIN_S_COUNT];
+  for (int s = 0; s < OKIN_S_COUNT; ++s) okin_resolve_section(hdr, ib, ib, s, sec);
+  OkinProgram pr{hdr, ib, fb, ib, sec};
   OkinSolverCfg cfg{c->step_tol, c->coarse_tol, c->fine_tol, c->residual_tol, c->mu_init, c->max_iter,
                     c->use_predictor};
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
