@@ -621,6 +621,7 @@ def compile_topology(
         "OKIN_H_OFF_RED": take(32), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)),
         # predictor history: two float32 vectors (stored two per double slot)
         "OKIN_H_OFF_PPREV": take((N + 1) // 2), "OKIN_H_OFF_PPREV2": take((N + 1) // 2),
+        "OKIN_H_OFF_TGT": take(2 * D["OKIN_MAX_TARGETS"]),
     }
     if off >= 65536:
         raise ValueError("Per-instance state exceeds the 16-bit shared-memory offset range")

@@ -1685,24 +1685,35 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   OkinState st;
   st.f2 = 0.0; st.rmax = 0.0; st.mu = 0.0; st.notpd = 0;
   int status = invalid ? OKIN_STATUS_INVALID_GEOMETRY : OKIN_STATUS_OK, failed = invalid ? 0 : -1;
-  double tcur[OKIN_MAX_TARGETS], tprev[OKIN_MAX_TARGETS];
-  for (int j = 0; j < OKIN_MAX_TARGETS; ++j) { tcur[j] = 0.0; tprev[j] = 0.0; }
+  // Target values of the current step, their increments and the previous increments live in shared
+  // memory (runtime-indexed per-thread arrays would be local memory).
+  double* tcur = sm + hdr[OKIN_H_OFF_TGT];
+  double* dt = tcur + OKIN_MAX_TARGETS;
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  for (int j = lane; j < 2 * OKIN_MAX_TARGETS; j += 32) tcur[j] = 0.0;
+  OKIN_PHASE_END
   bool have_tangent = false;
   int history = 0;
-  double dtprev[OKIN_MAX_TARGETS];
-  for (int j = 0; j < OKIN_MAX_TARGETS; ++j) dtprev[j] = 0.0;
 
   for (int s = 0; s < n_steps; ++s) {
     if (status == OKIN_STATUS_OK) {
-      for (int j = 0; j < nt; ++j) { tprev[j] = tcur[j]; tcur[j] = OKIN_LDG(tvals + j * n_steps + s); }
-      if (cfg.use_predictor && have_tangent) {
-        double dt[OKIN_MAX_TARGETS];
-        bool same = true;
-        for (int j = 0; j < OKIN_MAX_TARGETS; ++j) {
-          dt[j] = tcur[j] - tprev[j];
-          if (fabs(dt[j] - dtprev[j]) > 1e-9 * (fabs(dt[j]) + fabs(dtprev[j]))) same = false;
-          dtprev[j] = dt[j];
+      const bool predict = cfg.use_predictor && have_tangent;
+      OKIN_PHASE_BEGIN
+      double changed = 0.0;
+      if (lane < nt) {
+        const double cur = OKIN_LDG(tvals + lane * n_steps + s);
+        const double d = cur - tcur[lane], dprev = dt[lane];
+        tcur[lane] = cur;
+        if (predict) {
+          if (fabs(d - dprev) > 1e-9 * (fabs(d) + fabs(dprev))) changed = 1.0;
+          dt[lane] = d;
         }
+      }
+      red[lane] = changed;
+      OKIN_PHASE_END
+      if (predict) {
+        const bool same = okin_red_sum(red) == 0.0;
         history = same ? history + 1 : 1;   // consecutive predictor steps with the same increments
         const int order = history < cfg.use_predictor ? history : cfg.use_predictor;
         okin_predict(pr, sm, dt, order);

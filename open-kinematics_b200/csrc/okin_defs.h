@@ -123,6 +123,7 @@ enum okin_hdr_slot {
   OKIN_H_NDROW,    // distance rows on the fast evaluation path
   OKIN_H_NGROW,    // rows on the generic evaluation path (ROW_ORDER entries)
   OKIN_H_OFF_PPREV2,  // second predictor-history vector
+  OKIN_H_OFF_TGT,  // [2][OKIN_MAX_TARGETS] target values of the current step and their last increments
   OKIN_H_NHOT,     // int32 words of the hot prefix of the int blob (sections used inside the
                    // iteration; the kernel keeps them in shared memory, the rest stays in global memory)
   OKIN_H_NDIAG,    // diagnostic columns per state (OKIN_DIAG_BASE + topology columns), 0 = no program
