@@ -384,6 +384,11 @@ def run_cuda(args) -> None:
             executed = json.load(open(os.path.join(ROOT, "profiles", "fp64_flops.json")))["executed_fp64_flops_per_state"]
         except (OSError, KeyError):
             pass
+        smem_pipe = None
+        try:
+            smem_pipe = json.load(open(os.path.join(ROOT, "profiles", "smem_pipe.json")))
+        except OSError:
+            pass
         geo = topo.launch_geometry(n_inst, local)
         base = cpu_baseline(sample_instances=args.cpu_sample, processes=1)
         line = {
@@ -408,6 +413,8 @@ def run_cuda(args) -> None:
                 "peak_source": "okin_fp64_peak DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic_flops_per_state": flops_state, "kernel_ms": k_ms,
                 "executed_flops_per_state_ncu": executed,
+                # the unit ncu shows closest to its peak is the shared-memory data pipe, not FP64
+                "shared_memory_pipe_ncu": smem_pipe,
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                         "algorithmic_bytes_per_state": alg_bytes_state,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
