@@ -469,3 +469,88 @@ def test_analyze_sweep_matches_reference(case):
     for side, row in ref["setup_corner_metrics"].items():
         check_row(setup.corner_metrics[side], row, side)
     check_row(res.frames[-1].metrics, ref["last_frame_metrics"], "last frame")
+
+
+def test_c2_macpherson_batch_properties():
+    """BASELINE config 2 at its full size: 1e5 hardpoint-perturbed MacPherson corners, coordinated
+    bump + steer sweep.  Size-independent properties: every accepted state keeps its own link
+    lengths and keeps the strut bottom on the ball-joint -> strut-top line at its clamp offset; a
+    random subsample matches the oracle (SciPy LM, tight) on the same inputs."""
+    from oracle.solve import solve_sweep as oracle_sweep
+    meta, _ = load_golden("c2_macpherson_bump_steer")
+    sus, sweep = build_case(meta)
+    prog, values = _program(sus, sweep)
+    rng = np.random.default_rng(2)
+    nominal = _nominal(sus, prog)[0].reshape(-1, 3)
+    n = 100000
+    hp = nominal[None] + rng.normal(0.0, 0.5, size=(n,) + nominal.shape)
+    from open_kinematics_b200.core.enums import PointID as P
+    i_lbj, i_top, i_sb = (prog.in_keys.index(k) for k in (P.LOWER_WISHBONE_OUTBOARD, P.STRUT_TOP, P.STRUT_BOTTOM))
+    axis0 = nominal[i_top] - nominal[i_lbj]
+    frac = float((nominal[i_sb] - nominal[i_lbj]) @ axis0 / (axis0 @ axis0))
+    hp[:, i_sb] = hp[:, i_lbj] + frac * (hp[:, i_top] - hp[:, i_lbj])      # validator (SURVEY App. F)
+    out = gpu_solve(prog, hp.reshape(n, -1), values)
+    ok = out["status"] == 0
+    assert ok.mean() > 0.999
+    pos = out["positions"][ok]
+    from open_kinematics_b200.core.constraints import DistanceConstraint
+    for c in sus.constraints():
+        if isinstance(c, DistanceConstraint) and c.p1 in prog.in_keys and c.p2 in prog.in_keys:
+            ia, ib = prog.in_keys.index(c.p1), prog.in_keys.index(c.p2)
+            design = np.linalg.norm(hp[ok][:, ia] - hp[ok][:, ib], axis=1)
+            length = np.linalg.norm(pos[:, :, prog.out_keys.index(c.p1)] - pos[:, :, prog.out_keys.index(c.p2)], axis=2)
+            assert np.abs(length - design[:, None]).max() < 1e-4
+    lbj, top, sb = (pos[:, :, prog.out_keys.index(k)] for k in (P.LOWER_WISHBONE_OUTBOARD, P.STRUT_TOP, P.STRUT_BOTTOM))
+    u = (top - lbj) / np.linalg.norm(top - lbj, axis=2, keepdims=True)
+    off_line = (sb - lbj) - np.sum((sb - lbj) * u, axis=2, keepdims=True) * u
+    assert np.abs(off_line).max() < 1e-4
+    clamp = np.sum((sb - lbj) * u, axis=2)
+    assert np.abs(clamp - clamp[:, :1]).max() < 1e-4
+    problem, _ = oracle_problem(sus, sweep)
+    for i in rng.choice(np.flatnonzero(ok), 3, replace=False):
+        inst = {k: hp[i, j] for j, k in enumerate(prog.in_keys)}
+        ref = oracle_sweep(problem, inst, values, ftol=1e-15, xtol=1e-15, gtol=1e-15)
+        order = [prog.out_keys.index(k) for k in ref["keys"]]
+        assert np.abs(out["positions"][i][:, order] - ref["positions"]).max() <= POS_TOL_MM
+
+
+def test_c5_doe_grid_metrics_consistency():
+    """BASELINE config 5 in small: full-factorial grid over 6 hardpoint coordinates of the C3 axle
+    (3^6 instances) with metrics on.  Derivative metrics, obtained on the device from the tangent
+    solves, must agree with central differences of the state metrics along the sweep."""
+    from open_kinematics_b200.core.sweep import BatchSolver
+    meta, _ = load_golden("c3_rocker_ubar_coilover_roll")
+    sus, sweep = build_case(meta)
+    solver = BatchSolver(sus, sweep)
+    try:
+        nominal = solver.nominal_hardpoints()
+        rng = np.random.default_rng(5)
+        coords = rng.choice(np.flatnonzero(np.abs(nominal) > 1.0), 6, replace=False)
+        levels = np.array(np.meshgrid(*[[-1.0, 0.0, 1.0]] * 6, indexing="ij")).reshape(6, -1).T
+        hp = np.repeat(nominal[None, :], len(levels), axis=0)
+        hp[:, coords] += levels
+        res = solver.solve(hp, want_metrics=True)
+    finally:
+        solver.close()
+    ok = res.status == 0
+    assert ok.mean() > 0.95
+    names = res.metric_names
+    m = res.metrics[ok]
+    col = {n: i for i, n in enumerate(names)}
+    checked = 0
+    for side in ("left", "right"):
+        travel = m[:, :, col[f"wheel_travel_{side}"]]
+        for response in ("camber", "roadwheel_angle", "caster", "kpi", "half_track"):
+            value = m[:, :, col[f"{response}_{side}"]]
+            deriv = m[:, :, col[f"deriv_{response}_wrt_hub_z_{side}"]]
+            # Central difference of the response against the own hub's travel along the roll sweep.
+            # The other hub moves too, but it reaches this corner only through the U-bar arm, which
+            # does not load the wheel carrier kinematically: the cross term is below the tolerance.
+            fd = (value[:, 2:] - value[:, :-2]) / (travel[:, 2:] - travel[:, :-2])
+            err = np.abs(fd - deriv[:, 1:-1])
+            scale = np.maximum(np.abs(deriv[:, 1:-1]), 1e-3)
+            if response in ("camber", "roadwheel_angle", "half_track"):   # O(h^2) difference error: 2 %
+                assert np.nanmedian(err / scale) < 0.02, (response, side, np.nanmedian(err / scale))
+                checked += 1
+    assert checked == 6
+    assert np.isfinite(m[:, :, col["roll_center_z"]]).mean() > 0.9
