@@ -18,7 +18,14 @@
 //                        (points/derived/manager.py:186-197, :271-324), hand-written JVPs
 //   okin_solve_step   <- least_squares(method="lm") call (solver.py:124-169, :717-724)
 //   okin_sweep        <- solve_suspension_sweep loop (solver.py:716-774)
-//   okin_tangents     <- compute_state_tangents (sensitivity.py:57-143) via the Cholesky factor
+//   tangent columns   <- compute_state_tangents (sensitivity.py:57-143): right-hand sides carried through
+//                        the Cholesky factorisation (okin_tangent_rhs, okin_factor, okin_solve),
+//                        okin_point_vel for derived points, okin_tangent_health for rank / sigma_min / cond
+//   okin_shim_presolve <- solve_camber_shim_assembly + application (suspensions/config/shims.py:284-501,
+//                        corner/double_wishbone.py:501-571)
+//   okin_metrics      <- Suspension.compute_state_metrics (metrics/*.py; kernels in okin_metrics.cuh)
+//   okin_diagnostics, okin_continuity <- diagnose_sweep (diagnostics.py:118-226) and the U-bar checks
+//                        (axle/mechanisms.py:432-549)
 #pragma once
 
 #include "okin_defs.h"
@@ -668,7 +675,7 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
 
 // ---------------------------------------------------------------------------------------
 // 3x3-block sparse Cholesky, left-looking, level-scheduled over the elimination tree.
-// Dfac[j] = {l00,l10,l11,l20,l21,l22, 1/l00, 1/l11, 1/l22}.
+// A finished column's diagonal block holds its factor {l00,l10,l11,l20,l21,l22, 1/l00, 1/l11, 1/l22}.
 // ---------------------------------------------------------------------------------------
 OKIN_HD bool okin_chol3(const double* d, double f[9]) {
   // d: 3x3 row-major block, lower part valid.

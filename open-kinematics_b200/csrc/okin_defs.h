@@ -107,8 +107,7 @@ enum okin_hdr_slot {
   OKIN_H_TROW0,    // first target row
   // shared-memory layout (offsets in doubles from the instance's base)
   OKIN_H_OFF_POS, OKIN_H_OFF_CST, OKIN_H_OFF_R, OKIN_H_OFF_RG, OKIN_H_OFF_DBLK, OKIN_H_OFF_LB,
-  OKIN_H_OFF_DFAC /* unused: diagonal factors live in their diagonal blocks */, OKIN_H_OFF_VEC,
-  OKIN_H_OFF_XSAVE /* unused: a rejected step is undone by subtracting it */, OKIN_H_OFF_RED, OKIN_H_OFF_PAR,
+  OKIN_H_OFF_VEC, OKIN_H_OFF_RED, OKIN_H_OFF_PAR,
   OKIN_H_OFF_PPREV,
   OKIN_H_SMEM_DOUBLES, // shared-memory doubles per instance
   // metric program (csrc/okin_metrics.cuh)
