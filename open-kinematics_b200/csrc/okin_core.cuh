@@ -960,7 +960,9 @@ OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
 OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tval, const OkinSolverCfg& cfg,
-                            OkinState& st, bool* converged, bool* tangents_ready) {
+                            OkinState& st, bool* converged, bool* tangents_ready, bool relinearise,
+                            bool* gradients_at_solution) {
+  *gradients_at_solution = false;
   sm = OKIN_SHARED(sm);
   const int nt = pr.hdr[OKIN_H_NT];
   int nfev = 0;
@@ -989,10 +991,15 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
     }
     const double f2_old = st.f2;
     if (st.mu == 0.0 && hmax <= cfg.coarse_tol) {
-      okin_eval_rows(pr, sm, tval, false, st);   // residuals at the new point (also the reported max|r|)
+      // Residuals at the new point (also the reported max|r|).  When the caller will relinearise at
+      // the solution anyway (exported tangents / metrics) and this step already ends the iteration,
+      // the row gradients are evaluated in the same pass.
+      const bool last = hmax <= cfg.fine_tol;
+      okin_eval_rows(pr, sm, tval, relinearise && last, st);
       ++nfev;
       *tangents_ready = true;                    // linearised within hmax of the solution
-      if (hmax <= cfg.fine_tol) {                // error left ~ k hmax^2: done without verification
+      if (last) {                                // error left ~ k hmax^2: done without verification
+        *gradients_at_solution = relinearise;
         *converged = true;
         break;
       }
@@ -1726,7 +1733,9 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
         okin_predict(pr, sm, dt, order);
       }
       bool conv = false, tangents_ready = false;
-      const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready);
+      const bool relinearise = o_tangents || o_velocities || o_health || o_metrics;
+      bool at_solution = false;
+      const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready, relinearise, &at_solution);
       const bool valid = st.rmax == st.rmax;
       if (!conv || !valid) {
         status = valid ? OKIN_STATUS_NOT_CONVERGED : OKIN_STATUS_INVALID_GEOMETRY;
@@ -1742,13 +1751,15 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
       if (status == OKIN_STATUS_OK) {
-        if (o_tangents || o_velocities || o_health || o_metrics || !tangents_ready) {
+        if (relinearise || !tangents_ready) {
           // Exported tangents are taken at the solution itself: relinearise there.  (For the
           // predictor alone the factor of the last Gauss-Newton point, <= coarse_tol away, is
           // enough and was solved together with the chord step.)
-          const double rmax = st.rmax;
-          okin_eval_rows(pr, sm, tcur, true, st);
-          st.rmax = rmax;
+          if (!at_solution) {
+            const double rmax = st.rmax;
+            okin_eval_rows(pr, sm, tcur, true, st);
+            st.rmax = rmax;
+          }
           okin_assemble(pr, sm, 0.0, false);
           okin_tangent_rhs(pr, sm);
           okin_factor(pr, sm, st);
