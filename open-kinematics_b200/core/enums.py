@@ -14,15 +14,24 @@ class Axis(IntEnum):
     Z = 2
 
 
-class TargetPositionMode(StrEnum):
-    RELATIVE = "relative"
-    ABSOLUTE = "absolute"
+def _schema_enum(name: str, *values: str) -> type:
+    """String enumeration of one schema keyword set: member ``FOO_BAR`` has the YAML value ``foo_bar``."""
+    return StrEnum(name, {value.upper(): value for value in values})
 
 
-class Units(StrEnum):
-    MILLIMETERS = "millimeters"
-    DEGREES = "degrees"
-
+# Keyword sets of the geometry / sweep schema (reference enums.py:13-30, :84-170).
+TargetPositionMode = _schema_enum("TargetPositionMode", "relative", "absolute")
+Units = _schema_enum("Units", "millimeters", "degrees")
+ShimType = _schema_enum("ShimType", "outboard_camber")
+SuspensionType = _schema_enum("SuspensionType", "double_wishbone", "macpherson")
+Scope = _schema_enum("Scope", "corner", "axle")
+AxlePosition = _schema_enum("AxlePosition", "front", "rear")
+ActuationType = _schema_enum("ActuationType", "direct", "pushrod_rocker")
+MountBody = _schema_enum("MountBody", "lower_wishbone", "upright")
+CornerSpringType = _schema_enum("CornerSpringType", "none", "coilover", "torsion_bar")
+ArbType = _schema_enum("ArbType", "none", "u_bar", "t_bar")
+HeaveLinkType = _schema_enum("HeaveLinkType", "none", "rocker_to_rocker")
+SteeringType = _schema_enum("SteeringType", "none", "rack")
 
 _POINT_NAMES = """
 NOT_ASSIGNED
@@ -44,52 +53,3 @@ PointID = IntEnum("PointID", {name: i for i, name in enumerate(_POINT_NAMES)})
 PointID.__doc__ = "Identifiers for authored and derived suspension points."
 
 
-class ShimType(StrEnum):
-    OUTBOARD_CAMBER = "outboard_camber"
-
-
-class SuspensionType(StrEnum):
-    DOUBLE_WISHBONE = "double_wishbone"
-    MACPHERSON = "macpherson"
-
-
-class Scope(StrEnum):
-    CORNER = "corner"
-    AXLE = "axle"
-
-
-class AxlePosition(StrEnum):
-    FRONT = "front"
-    REAR = "rear"
-
-
-class ActuationType(StrEnum):
-    DIRECT = "direct"
-    PUSHROD_ROCKER = "pushrod_rocker"
-
-
-class MountBody(StrEnum):
-    LOWER_WISHBONE = "lower_wishbone"
-    UPRIGHT = "upright"
-
-
-class CornerSpringType(StrEnum):
-    NONE = "none"
-    COILOVER = "coilover"
-    TORSION_BAR = "torsion_bar"
-
-
-class ArbType(StrEnum):
-    NONE = "none"
-    U_BAR = "u_bar"
-    T_BAR = "t_bar"
-
-
-class HeaveLinkType(StrEnum):
-    NONE = "none"
-    ROCKER_TO_ROCKER = "rocker_to_rocker"
-
-
-class SteeringType(StrEnum):
-    NONE = "none"
-    RACK = "rack"
