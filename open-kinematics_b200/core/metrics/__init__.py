@@ -1,0 +1,1 @@
+"""Row containers for the metric columns the device computes."""

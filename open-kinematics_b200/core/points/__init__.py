@@ -1,0 +1,1 @@
+"""Point bookkeeping of the host mirror."""

@@ -1,0 +1,1 @@
+"""Declarative derived points (compiled to device ops by core/topology.py)."""

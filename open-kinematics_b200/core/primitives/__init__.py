@@ -1,0 +1,1 @@
+"""Value types shared by the host mirror: points, directions, point keys, constants."""

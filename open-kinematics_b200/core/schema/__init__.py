@@ -1,0 +1,1 @@
+"""Configuration records parsed from the geometry mapping."""

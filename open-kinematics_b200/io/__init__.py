@@ -1,0 +1,1 @@
+"""Result tables of solved sweeps (wide-form files, batch Arrow sink)."""
