@@ -554,3 +554,36 @@ def test_c5_doe_grid_metrics_consistency():
                 checked += 1
     assert checked == 6
     assert np.isfinite(m[:, :, col["roll_center_z"]]).mean() > 0.9
+
+
+def test_optional_outputs_are_independent():
+    """Every optional output can be requested on its own (the host path allocates device scratch
+    for what the kernels need but the caller did not ask for), long sweeps included."""
+    from open_kinematics_b200 import _lib
+    from open_kinematics_b200.core.topology import compile_suspension
+    meta, arr = load_golden("c4_tbar_heave_shim_bump")      # 31 steps, shimmed axle
+    sus, sweep = build_case(meta)
+    prog = compile_suspension(sus, sweep)
+    hp = np.repeat(_nominal(sus, prog), 5, axis=0)
+    sv = arr["sweep_values"]
+    values = np.concatenate([sv, sv[:, ::-1], sv, sv[:, ::-1]], axis=1)   # 124 steps: up, down, up, down
+    topo = _lib.DeviceTopology(prog)
+    try:
+        full = topo.solve_batch(hp, values, want_metrics=True, want_velocities=True, want_health=True,
+                                want_diagnostics=True, want_tangents=True, want_design=True)
+        assert (full["status"] == 0).all()
+        only_diag = topo.solve_batch(hp, values, want_positions=False, want_diagnostics=True)
+        assert only_diag["positions"] is None
+        # (a different set of outputs takes a different code path: equal to rounding, not bit for bit)
+        assert np.allclose(only_diag["diagnostics"], full["diagnostics"], rtol=0, atol=1e-9, equal_nan=True)
+        assert np.allclose(only_diag["jumps"], full["jumps"], rtol=0, atol=1e-9)
+        only_metrics = topo.solve_batch(hp, values, want_positions=False, want_metrics=True)
+        assert np.allclose(only_metrics["metrics"], full["metrics"], rtol=1e-9, atol=1e-9, equal_nan=True)
+        lean = topo.solve_batch(hp, values)
+        assert np.abs(lean["positions"] - full["positions"]).max() <= 1e-9
+        # the sweep retraces itself: same states on the way back, no jump flags
+        n = sv.shape[1]
+        assert np.abs(full["positions"][:, :n] - full["positions"][:, 2 * n - 1:n - 1:-1]).max() <= 1e-7
+        assert (full["diagnostics"][:, :, 0] == 0).all()
+    finally:
+        topo.close()
