@@ -693,9 +693,8 @@ OKIN_HD bool okin_chol3(const double* d, double f[9]) {
   return d00 > 0.0 && t11 > 0.0 && t22 > 0.0;
 }
 
-// After a column's rows are scaled its diagonal block is dead, so the diagonal factor
-// {l00,l10,l11,l20,l21,l22, 1/l00,1/l11,1/l22} is written over it -- one level later, inside the
-// next level's update phase (which never reads diagonal blocks of finished columns).
+// Once a column's diagonal block has received its updates nothing reads its raw entries again, so the
+// factor {l00,l10,l11,l20,l21,l22, 1/l00,1/l11,1/l22} is written over it.
 OKIN_HD void okin_write_diag_factor(double* sm, int doff, double* red, int lane) {
   sm = OKIN_SHARED(sm);
   double f[9];
@@ -723,10 +722,9 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
   OKIN_PHASE_BEGIN
   red[lane] = 0.0;
   OKIN_PHASE_END
-  for (int lv = 0; lv <= nlev; ++lv) {
-    const int ub = lv < nlev ? OKIN_LDG(lev_upd + lv) : 0, ue = lv < nlev ? OKIN_LDG(lev_upd + lv + 1) : 0;
-    const int wb = lv > 0 ? OKIN_LDG(lcp + lv - 1) : 0, we = lv > 0 ? OKIN_LDG(lcp + lv) : 0;
-    if (ue > ub || we > wb) {
+  for (int lv = 0; lv < nlev; ++lv) {
+    const int ub = OKIN_LDG(lev_upd + lv), ue = OKIN_LDG(lev_upd + lv + 1);
+    if (ue > ub) {
       OKIN_PHASE_BEGIN
       // left-looking update of one block row (or of the carried right-hand side)
       for (int t = ub + lane; t < ue; t += 32) {
@@ -745,20 +743,21 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
         }
         dst[0] = c0; dst[1] = c1; dst[2] = c2;
       }
-      // diagonal factors of the previous level, taken by the highest lanes
-      for (int c = wb + (31 - lane); c < we; c += 32)
-        okin_write_diag_factor(sm, OKIN_LDG(doffs + OKIN_LDG(lcol + c)), red, lane);
       OKIN_PHASE_END
     }
-    if (lv == nlev) break;
+    // The level's diagonal blocks are final: factor each once, in place (one lane per column), so that
+    // the scale tasks below and the triangular solves later read the factor instead of recomputing it.
+    const int wb = OKIN_LDG(lcp + lv), we = OKIN_LDG(lcp + lv + 1);
+    OKIN_PHASE_BEGIN
+    for (int c = wb + lane; c < we; c += 32)
+      okin_write_diag_factor(sm, OKIN_LDG(doffs + OKIN_LDG(lcol + c)), red, lane);
+    OKIN_PHASE_END
     const int sb = OKIN_LDG(lev_scl + lv), se = OKIN_LDG(lev_scl + lv + 1);
     OKIN_PHASE_BEGIN
     for (int t = sb + lane; t < se; t += 32) {
       const uint32_t w = (uint32_t)OKIN_LDG(scl + t);
-      const int doff = (int)(w & 0xffffu), roff = (int)(w >> 16);
-      double f[9];
-      okin_chol3(sm + doff, f);
-      double* b = sm + roff;
+      const double* f = sm + (w & 0xffffu);
+      double* b = sm + (w >> 16);
       const double x0 = b[0] * f[6];
       const double x1 = (b[1] - x0 * f[1]) * f[7];
       const double x2 = (b[2] - x0 * f[3] - x1 * f[4]) * f[8];
