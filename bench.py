@@ -258,7 +258,7 @@ def run_cuda(args) -> None:
     local_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
 
     sus, sweep = workload_case()
-    solver = BatchSolver(sus, sweep)
+    solver = BatchSolver(sus, sweep, tune_layout=True)     # bank-conflict-aware block placement (compile time)
     prog, topo = solver.program, solver.topology
     n_inst, S = args.instances, N_STEPS_SWEEP
     nin3, nout3, nt, n = 3 * prog.n_in, 3 * prog.n_out, len(prog.target_points), prog.n_unknowns
@@ -403,7 +403,7 @@ def run_cuda(args) -> None:
                 "n_unknowns": n, "n_rows": prog.stats["n_rows"], "ok_fraction": ok_frac,
                 "mean_nfev_per_state": mean_iters, "outputs": "positions(all points)+nfev+max_residual+status",
                 "l2_policy": f"inputs+outputs per launch {n_inst * (nin3 * 8 + S * nout3 * 8) / 1e9:.2f} GB >> 126 MB L2",
-                "launch": geo, "numa_local_cpus": local_cpus, "e2e_instances_per_gpu": e2e_inst, "e2e_ok_fraction": e2e_ok,
+                "launch": geo, "layout_tuning": prog.stats.get("layout_tuning"), "numa_local_cpus": local_cpus, "e2e_instances_per_gpu": e2e_inst, "e2e_ok_fraction": e2e_ok,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_inst * nin3 * 8 + nt * S * 8),
                     "d2h_bytes_per_step": int(e2e_inst * bytes_per_inst_out)},

@@ -77,7 +77,10 @@ class BatchSolver:
     the device from that instance's hardpoints (reference recomputes them in
     ``Suspension.constraints()``, core/sweep.py:58-63)."""
 
-    def __init__(self, suspension, sweep_config: SweepConfig, output_points=None):
+    def __init__(self, suspension, sweep_config: SweepConfig, output_points=None, tune_layout: bool = False):
+        """``tune_layout``: spend a few seconds at compile time placing the factor blocks so that the
+        kernel's shared-memory accesses hit fewer bank conflicts (core/layout_tuning.py); worth it for
+        large batches, results are unchanged."""
         validate_sweep_controls(sweep_config, suspension.actuator_dofs())
         self.suspension = suspension
         self.heads, self.values = sweep_target_values(sweep_config)
@@ -92,6 +95,7 @@ class BatchSolver:
             if suspension.config is not None else None,
             shims=shim_records(suspension),
             diagnostics=lambda pidx, design_pts: build_diagnostic_program(suspension, pidx, design_pts),
+            tune_layout=tune_layout,
         )
         self.topology = _lib.DeviceTopology(self.program)
 

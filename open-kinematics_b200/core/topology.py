@@ -290,6 +290,7 @@ def compile_topology(
     metrics=None,
     shims=None,
     diagnostics=None,
+    tune_layout: bool = False,
 ) -> TopologyProgram:
     """Compile one topology.
 
@@ -627,9 +628,54 @@ def compile_topology(
         raise ValueError("Per-instance state exceeds the 16-bit shared-memory offset range")
     base = {LB: layout["OKIN_H_OFF_LB"], VEC: layout["OKIN_H_OFF_VEC"]}
 
+    # ---- optional: bank-conflict-aware placement of the factor blocks (core/layout_tuning.py) ------
+    slot = list(range(NB))
+    tuning = None
+    if tune_layout and NB > 1:
+        from .layout_tuning import AccessTrace, tune_block_slots
+        trace = AccessTrace(base[LB])
+
+        def ref(r):
+            return ("LB", r[1]) if r[0] == LB else ("ABS", base[VEC] + r[1])
+
+        for lv in range(NLEV):
+            for r0 in range(lev_upd[lv], lev_upd[lv + 1], 32):          # update rounds
+                ts = range(r0, min(r0 + 32, lev_upd[lv + 1]))
+                lanes = [t - r0 for t in ts]
+                trace.access(lanes, [ref(upd_dst[t]) for t in ts], (0, 1, 2))          # load c0..c2
+                for q in range(max(upd_ptr[t + 1] - upd_ptr[t] for t in ts)):
+                    act = [t for t in ts if upd_ptr[t + 1] - upd_ptr[t] > q]
+                    la = [t - r0 for t in act]
+                    trace.access(la, [ref(upd_con[upd_ptr[t] + q][0]) for t in act], (0, 1, 2))
+                    trace.access(la, [ref(upd_con[upd_ptr[t] + q][1]) for t in act], range(9))
+                trace.access(lanes, [ref(upd_dst[t]) for t in ts], (0, 1, 2))          # store
+            for r0 in range(lev_scl[lv], lev_scl[lv + 1], 32):          # scale rounds
+                ts = range(r0, min(r0 + 32, lev_scl[lv + 1]))
+                lanes = [t - r0 for t in ts]
+                trace.access(lanes, [ref(scl[t][0]) for t in ts], (1, 3, 4, 6, 7, 8))
+                trace.access(lanes, [ref(scl[t][1]) for t in ts], (0, 1, 2, 0, 1, 2))   # load + store
+        nrhs = 1 + len(targets)
+        for lv in range(NLEV):                                        # backward solve, all right-hand sides
+            tasks = [(j, r) for j in lev_cols[lv] for r in range(nrhs)]
+            for r0 in range(0, len(tasks), 32):
+                ts = tasks[r0:r0 + 32]
+                for q in range(max((bw_ptr[j + 1] - bw_ptr[j] for j, _ in ts), default=0)):
+                    act = [(n, j) for n, (j, _) in enumerate(ts) if bw_ptr[j + 1] - bw_ptr[j] > q]
+                    trace.access([n for n, _ in act], [ref(bw_con[bw_ptr[j] + q][0]) for _, j in act], range(9))
+                trace.access(list(range(len(ts))), [("LB", boff(j, j)) for j, _ in ts], (1, 3, 4, 6, 7, 8))
+        for r0 in range(0, NAT, 32):                                  # assembly: block stores
+            ts = range(r0, min(r0 + 32, NAT))
+            trace.access([t - r0 for t in ts], [("LB", 9 * (asm_task[t] & 0xFFFF)) for t in ts], range(9))
+        tuned, before, after, ideal = tune_block_slots(trace, NB)
+        slot = [int(v) for v in tuned]
+        tuning = {"wavefronts_before": before, "wavefronts_after": after, "wavefronts_ideal": ideal}
+
     def sm(ref) -> int:
+        if ref[0] == LB:
+            return base[LB] + 9 * slot[ref[1] // 9] + ref[1] % 9
         return base[ref[0]] + ref[1]
 
+    asm_task = [(t & ~0xFFFF) | slot[t & 0xFFFF] for t in asm_task]
     diag_off = [sm((LB, boff(j, j))) for j in range(NF)]
     upd_dst = [sm(d) for d in upd_dst]
     upd_con = [(sm(a) << 16) | sm(b) for a, b in upd_con]
@@ -762,6 +808,7 @@ def compile_topology(
         "asm_fma": 9 * len(asm_con), "g_fma": 3 * len(g_con), "update_fma": 9 * len(upd_con),
         "scale_tasks": len(scl) + NF, "solve_fma": 9 * (len(fw_con) + len(bw_con)) + 12 * NF,
         "smem_doubles": off, "iblob_words": int(iblob.size), "dense_lu_flops": dense_flops,
+        "layout_tuning": tuning,
     }
     return TopologyProgram(
         hdr=hdr, iblob=iblob, fblob=fblob, point_keys=point_keys, free_order=free_order, in_keys=in_keys,
@@ -775,7 +822,7 @@ def compile_topology(
 
 
 def compile_suspension(suspension, sweep_config, output_points=None, design_rules: bool = True,
-                       with_metrics: bool = True) -> TopologyProgram:
+                       with_metrics: bool = True, tune_layout: bool = False) -> TopologyProgram:
     """Compile a built suspension + sweep (first-step targets define the target rows)."""
     from .diagnostics_program import build_diagnostic_program
     from .metrics_program import build_metric_program
@@ -790,4 +837,5 @@ def compile_suspension(suspension, sweep_config, output_points=None, design_rule
         output_points=output_points, design_rules=design_rules, metrics=metrics,
         shims=shim_records(suspension) if design_rules else None,
         diagnostics=lambda pidx, design_pts: build_diagnostic_program(suspension, pidx, design_pts),
+        tune_layout=tune_layout,
     )

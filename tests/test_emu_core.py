@@ -224,3 +224,24 @@ def test_generic_family_mechanism_matches_reference(emu_device):
     (three-point angle, equal distance, vectors perpendicular, fixed axis, point on plane, coplanar)."""
     import test_gpu_parity as G
     G.test_generic_family_mechanism_matches_reference()
+
+
+@pytest.mark.parametrize("case", ["c3_rocker_ubar_coilover_roll", "c2_macpherson_bump_steer"])
+def test_tuned_block_placement_keeps_the_answer(case):
+    """Bank-conflict-aware placement of the factor blocks (core/layout_tuning.py) only permutes
+    storage: fewer modelled wavefronts, same positions and tangents."""
+    from open_kinematics_b200.core.topology import compile_suspension
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    plain = compile_suspension(sus, sweep)
+    tuned = compile_suspension(sus, sweep, tune_layout=True)
+    info = tuned.stats["layout_tuning"]
+    assert info["wavefronts_ideal"] <= info["wavefronts_after"] <= info["wavefronts_before"]
+    assert plain.stats["layout_tuning"] is None
+    a = emu_solve(plain, _nominal(sus, plain), arr["sweep_values"])
+    b = emu_solve(tuned, _nominal(sus, tuned), arr["sweep_values"])
+    assert (b["status"] == 0).all()
+    assert np.abs(a["positions"] - b["positions"]).max() <= 1e-9
+    assert np.abs(a["tangents"] - b["tangents"]).max() <= 1e-9
+    order = [tuned.out_keys.index(key_from_name(n)) for n in meta["point_keys"]]
+    assert np.abs(b["positions"][0][:, order] - arr["positions_tight"]).max() <= POS_TOL_MM
