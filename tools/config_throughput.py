@@ -101,6 +101,8 @@ def main():
     run("c1_dw_corner_bump36", *build_case(meta), n, 0.5)
     meta, _ = load_golden("c2_macpherson_bump_steer")
     run("c2_macpherson_bump_steer41", *build_case(meta), n, 0.5)
+    if os.environ.get("OKIN_CORNERS_ONLY"):
+        return
     meta, _ = load_golden("c4_tbar_heave_shim_bump")
     sus, _ = build_case(meta)
     run("c4_tbar_heave_shim_bump101_mc", sus, build_sweep(axle_sweep(101, 50.0, False), sus), n // 2, 0.25, shim_mc=True)
