@@ -494,6 +494,54 @@ def compile_topology(
     def boff(i, j) -> int:
         return 9 * block_id[(i, j)]
 
+    # ---- optional: conflict-aware order of the row-gradient vectors (core/layout_tuning.py) --------
+    rg_tuning = None
+    if tune_layout:
+        from .layout_tuning import UnitTrace, tune_unit_order
+        units = [r for r in rows if r in ls_rows]               # rows that own gradient storage
+        unit_of = {id(r): u for u, r in enumerate(units)}
+        sizes = [3 if r.fast else 3 * len(r.eff) for r in units]
+
+        def gref(r, e):                                          # (unit, offset) of d row / d block e
+            return unit_of[id(r)], 0 if r.fast else 3 * e
+
+        pattern: dict = {}
+        for r in ls_rows:
+            for ea, ca in enumerate(r.eff):
+                for eb, cb in enumerate(r.eff):
+                    pa, pb = pos_of[ca], pos_of[cb]
+                    if pa < pb or (pa == pb and ea != eb):
+                        continue
+                    pattern.setdefault((pa, pb), []).append((gref(r, ea), gref(r, eb)))
+        order_tasks = sorted(block_id.items(), key=lambda kv: (-len(pattern.get(kv[0], [])), kv[1]))
+        rg_base = 3 * P + max(ncst, 1) + len(rows)
+        trace = UnitTrace(rg_base, sizes)
+        for r0 in range(0, len(order_tasks), 32):               # assembly: gradient pairs of every block
+            ts = [pattern.get(k, []) for k, _ in order_tasks[r0:r0 + 32]]
+            for q in range(max(len(c) for c in ts)):
+                act = [(n, c[q]) for n, c in enumerate(ts) if len(c) > q]
+                trace.access([n for n, _ in act], [c[0] for _, c in act], (0, 1, 2))
+                trace.access([n for n, _ in act], [c[1] for _, c in act], (0, 1, 2))
+        per_col: dict = {}
+        for r in ls_rows:
+            for e, cblk in enumerate(r.eff):
+                per_col.setdefault(pos_of[cblk], []).append(gref(r, e))
+        cols = [per_col.get(j, []) for j in range(NF)]
+        for r0 in range(0, NF, 32):                              # g = J^T r, one lane per block column
+            ts = cols[r0:r0 + 32]
+            for q in range(max(len(c) for c in ts)):
+                act = [(n, c[q]) for n, c in enumerate(ts) if len(c) > q]
+                trace.access([n for n, _ in act], [c for _, c in act], (0, 1, 2))
+        fast = [r for r in rows if r.fast]
+        for r0 in range(0, len(fast), 32):                       # fast distance rows store u
+            trace.access(list(range(len(fast[r0:r0 + 32]))), [gref(r, 0) for r in fast[r0:r0 + 32]], (0, 1, 2))
+        rg_order, before, after, ideal = tune_unit_order(trace)
+        start = trace.offsets(rg_order)
+        first = min(r.rg_off for r in units)
+        for u, r in enumerate(units):
+            r.rg_off = first + int(start[u])
+        rg_tuning = {"wavefronts_before": before, "wavefronts_after": after, "wavefronts_ideal": ideal}
+
     # ---- assembly gather lists (A = J^T J), one task per 3x3 block ----------------
     # contribution = (rg offset of the row's gradient w.r.t. the block-row point) << 16 |
     #                (rg offset of its gradient w.r.t. the block-column point)
@@ -668,7 +716,8 @@ def compile_topology(
             trace.access([t - r0 for t in ts], [("LB", 9 * (asm_task[t] & 0xFFFF)) for t in ts], range(9))
         tuned, before, after, ideal = tune_block_slots(trace, NB)
         slot = [int(v) for v in tuned]
-        tuning = {"wavefronts_before": before, "wavefronts_after": after, "wavefronts_ideal": ideal}
+        tuning = {"wavefronts_before": before, "wavefronts_after": after, "wavefronts_ideal": ideal,
+                  "row_gradients": rg_tuning}
 
     def sm(ref) -> int:
         if ref[0] == LB:
