@@ -57,3 +57,32 @@ def test_family_codes_agree_between_header_generator_and_compiler():
         assert FAMILY_CODE[fam.name] == code
     committed = open(os.path.join(ROOT, "open-kinematics_b200", "csrc", "okin_gen_constraints.cuh")).read()
     assert committed == gen.generate(), "csrc/okin_gen_constraints.cuh is stale: run tools/generate_jacobians.py"
+
+
+def test_bank_conflict_model_on_known_patterns():
+    import numpy as np
+    """core/layout_tuning.py: wavefronts of 64-bit shared-memory accesses, half-warp at a time,
+    16 bank pairs."""
+    from open_kinematics_b200.core.layout_tuning import AccessTrace, UnitTrace, tune_block_slots, tune_unit_order
+
+    def count(addresses):
+        trace = AccessTrace(lb_base=0)
+        trace.access(list(range(len(addresses))), [("ABS", a) for a in addresses])
+        trace.freeze()
+        return trace.wavefronts(np.arange(1)), trace.ideal()
+
+    assert count(list(range(32))) == (2, 2)                 # consecutive doubles: one wavefront per half-warp
+    assert count([7] * 32) == (2, 2)                        # broadcast
+    assert count([16 * i for i in range(16)]) == (16, 1)    # same bank pair, 16 different doubles
+    assert count([9 * i for i in range(16)]) == (1, 1)      # stride of a 3x3 block: conflict-free
+    assert count([3 * i for i in range(16)]) == (1, 1)      # stride of a 3-vector
+    assert count([8 * i for i in range(16)]) == (8, 1)      # stride 8: two bank pairs only
+    # two blocks whose rows collide until one is moved
+    trace = AccessTrace(lb_base=0)
+    trace.access([0, 1], [("LB", 0), ("LB", 9 * 16)], (0, 1, 2))
+    slot, before, after, ideal = tune_block_slots(trace, 17, iterations=200)
+    assert (before, after, ideal) == (6, 3, 3) and sorted(slot) == list(range(17))
+    units = UnitTrace(base=0, sizes=[3, 13, 3])
+    units.access([0, 1], [(0, 0), (2, 0)], (0, 1, 2))      # units 0 and 2 start 16 doubles apart
+    order, before, after, ideal = tune_unit_order(units, iterations=50)
+    assert (before, after, ideal) == (6, 3, 3)
