@@ -870,6 +870,13 @@ def compile_topology(
     )
 
 
+def structure_point_index(suspension) -> dict:
+    """``{point key: index}`` of a suspension's points in the compiled topology (sorted keys), without
+    compiling anything."""
+    state, _ = suspension.structure()
+    return {k: i for i, k in enumerate(sorted(state.positions.keys()))}
+
+
 def compile_suspension(suspension, sweep_config, output_points=None, design_rules: bool = True,
                        with_metrics: bool = True, tune_layout: bool = False) -> TopologyProgram:
     """Compile a built suspension + sweep (first-step targets define the target rows)."""

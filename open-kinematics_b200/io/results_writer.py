@@ -26,28 +26,7 @@ FORMAT_VERSION = "3"
 METADATA_KEY = b"kinematics_meta"
 STANDARD_COLUMNS = ("step_index", "solver_converged", "solver_max_residual", "solver_nfev")
 
-_DEG = {"camber", "caster", "kpi", "roadwheel_angle", "svsa_angle", "roll", "rocker_angle", "torsion_bar_twist",
-        "arb_arm_angle", "arb_twist", "t_bar_heave_angle"}
-_PERCENT = {"anti_dive", "anti_lift", "anti_squat"}
-_SIDES = ("_left", "_right")
-
-
-def metric_unit(name: str) -> str:
-    """Unit symbol of a flat metric column (reference metrics/registry.py specs, metrics/units.py):
-    angles in deg, anti-geometry in %, everything else in mm; ``deriv_<response>_wrt_<driver>`` is the
-    quotient of its response and driver units (drivers are displacements in mm)."""
-    key = name
-    for side in _SIDES:
-        if key.endswith(side):
-            key = key[:-len(side)]
-    if key.startswith("deriv_") and "_wrt_" in key:
-        response = key[len("deriv_"):key.index("_wrt_")]
-        return f"{metric_unit(response)}/mm"
-    if key in _DEG:
-        return "deg"
-    if key in _PERCENT:
-        return "%"
-    return "mm"
+from ..core.metrics.registry import metric_unit  # noqa: E402,F401  (re-exported)
 
 
 def point_key_name(key) -> str:

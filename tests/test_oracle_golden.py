@@ -93,3 +93,26 @@ def test_oracle_failure_flags():
         problem, values = oracle_problem(sus, sweep)
         out = solve_sweep(problem, authored_positions(sus), values)
         assert (out["status"], out["failed_step"]) == (rec["status"], rec["failed_step"]), label
+
+
+def test_metric_registry_columns_and_units_match_reference():
+    """Host-only mirror of flat_specs_for_suspension (reference core/metrics/registry.py:201-215): the
+    flat columns of every golden case, in export order, with the reference's unit symbols; and
+    flatten_positions (core/export.py)."""
+    import numpy as np
+    from helpers import SWEEP_CASES, build_case, load_golden
+    from open_kinematics_b200.core.export import flatten_positions
+    from open_kinematics_b200.core.metrics.registry import flat_specs_for_suspension
+    units = json.load(open(os.path.join(GOLDEN, "result_files.json")))["metric_units"]
+    for case in SWEEP_CASES:
+        meta, arr = load_golden(case)
+        sus, sweep = build_case(meta)
+        specs = flat_specs_for_suspension(sus, [dim[0] for dim in sweep.target_sweeps])
+        assert list(specs) == meta["metric_names"], case
+        for name, spec in specs.items():
+            assert spec.unit == units[name], (case, name)
+    meta, arr = load_golden("c1_dw_corner_bump")
+    sus, _ = build_case(meta)
+    flat = flatten_positions(sus.authored_state().positions, sus.output_points())
+    assert list(flat) == [k.name.lower() for k in sus.output_points() if k in sus.authored_state().positions]
+    assert all(isinstance(v, tuple) and len(v) == 3 for v in flat.values())
