@@ -113,7 +113,21 @@ def tangents_vs_resolved_states():
             assert np.abs(fd - field.velocity(key)).max() <= 2e-3   # O(h^2) with 4 mm steps
 
 
-BODIES = [t_bar_invariants, macpherson_invariants, rocker_axle_invariants, tangents_vs_resolved_states]
+def known_metric_values_at_design():
+    """Hand-checked values of the reference's test geometry at its design pose (reference
+    tests/test_metrics.py:321-400): camber -1.909 deg (top tilted inward), caster +4.764 deg (top tilted
+    rearward), roadwheel angle 0; all at the reference's tolerance of 1e-3."""
+    meta, _ = load_golden("c1_dw_corner_bump")
+    sus, _ = build_case(meta)
+    row = sus.compute_state_metrics(sus.initial_state())
+    assert abs(row["camber"] + 1.909) <= 1e-3 and row["camber"] < 0
+    assert abs(row["caster"] - 4.764) <= 1e-3 and row["caster"] > 0
+    assert abs(row["roadwheel_angle"]) <= 1e-3
+    assert abs(row["wheel_travel"]) <= 1e-6
+    assert not any(key.startswith("deriv_") for key in row)      # no tangents given: no derivative columns
+
+
+BODIES = [known_metric_values_at_design, t_bar_invariants, macpherson_invariants, rocker_axle_invariants, tangents_vs_resolved_states]
 
 
 @pytest.mark.parametrize("body", BODIES, ids=lambda f: f.__name__)
