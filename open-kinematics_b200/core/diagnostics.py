@@ -17,7 +17,6 @@ from math import acos, degrees
 import numpy as np
 
 from .primitives.constants import SOLVE_ACCEPT_RESIDUAL
-from .topology import D
 
 CONTINUITY_ABS_FLOOR_MM: float = 5.0
 CONTINUITY_MEDIAN_FACTOR: float = 4.0

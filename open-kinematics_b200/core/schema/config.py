@@ -10,7 +10,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ..enums import ArbType, AxlePosition, HeaveLinkType, SteeringType
+from ..enums import AxlePosition, SteeringType
 from ..primitives.constants import EPS_GEOMETRIC, MM_PER_INCH
 from ..primitives.geometry import Direction3, Point3
 

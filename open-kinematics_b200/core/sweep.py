@@ -10,9 +10,9 @@ import numpy as np
 from .. import _lib
 from .metrics.main import rows_from_columns
 from .points.derived.manager import DerivedPointsManager
-from .sensitivity import (STATE_MATCH_TOL_MM, TangentField, TangentSolveInfo, fields_from_velocities,
+from .sensitivity import (STATE_MATCH_TOL_MM, TangentField, TangentSolveInfo, fields_from_velocities,  # noqa: F401
                           measured_targets, solve_info_from_health)
-from .solver import (SolverConfig, SolverInfo, convert_targets_to_absolute, solve_suspension_sweep,
+from .solver import (SolverConfig, SolverInfo, convert_targets_to_absolute, solve_suspension_sweep,  # noqa: F401
                      sweep_target_values)
 from .targeting import SweepConfig, validate_sweep_controls
 from .topology import TopologyProgram, compile_topology

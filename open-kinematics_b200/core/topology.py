@@ -33,7 +33,7 @@ from .constraints import (
 )
 from .enums import TargetPositionMode
 from .points.derived.manager import DerivedPointsManager, DerivedPointsSpec
-from .targeting import PointTarget, resolve_target
+from .targeting import resolve_target
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc")
 
