@@ -57,3 +57,27 @@ def test_bench_rank_protocol_world_size_2_gloo(tmp_path):
     assert rows[0][2] != rows[1][2]                      # different perturbation streams
     for r in rows:                                       # every rank sees the max over ranks
         assert r[3] == 20.0 and r[4] == 40.0
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The bench lines committed under profiles/ carry every key of the bench contract (so a change
+    to bench.py that drops one shows up here, without a GPU)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("r01_bench_1gpu.json", "r01_bench_8gpu.json"):
+        line = json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                    "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks",
+                    "roofline", "cpu_baseline"):
+            assert key in line, (name, key)
+        assert line["dtype"] == "f64" and line["scaling"] == "weak" and line["vs_baseline"] is None
+        assert line["higher_is_better"] is True and line["warmup"] >= 3 and "workload" in line["config"]
+        assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+        assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+        assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+        assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+        assert abs(line["value"] - line["n_gpus"] * line["config"]["instances_per_gpu"] * line["config"]["sweep_steps"]
+                   / (line["ms_per_step"] * 1e-3)) <= 1e-6 * line["value"]
+    ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_reference_arm.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "port"
