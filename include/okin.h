@@ -57,8 +57,15 @@
  *   jumps_out       [n_instances][n_steps][n_unknowns/3]  row 0: continuity threshold of each free point
  *                                                    (reference column order); row s>0: displacement into
  *                                                    step s where it exceeded the threshold, else 0
+ *   instance_targets [n_instances][n_targets][n_steps] per-instance sweep tables (Monte Carlo over the sweep
+ *                                                    itself); when given it replaces the
+ *                                                    shared target_values
  *   status_out      [n_instances]                    OKIN_STATUS_*
  *   failed_step_out [n_instances]                    -1 or the first failed step
+ *   worst_row_out   [n_instances]                    device row owning max|r| at the failed step, -1 when the
+ *                                                    sweep did not fail; the host maps it to the reference's
+ *                                                    "Worst residual row" text (describe_worst_residual,
+ *                                                    solver.py:640-651) through TopologyProgram.row_source
  * The buffers of one call travel in an okin_batch_io; every output pointer except status /
  * failed_step may be NULL (not wanted).
  */
@@ -133,6 +140,8 @@ typedef struct okin_batch_io {
   double* design;
   double* diagnostics;
   double* jumps;
+  const double* instance_targets; /* optional [n_instances][n_targets][n_steps]; replaces target_values */
+  int32_t* worst_row;             /* optional [n_instances] */
 } okin_batch_io;
 
 int okin_device_count(int* out);
@@ -141,8 +150,9 @@ int okin_topology_create(const okin_topology_desc* desc, okin_topology** out);
 int okin_topology_destroy(okin_topology* topo);
 int okin_topology_get_info(const okin_topology* topo, okin_topology_info* out);
 
-/* Host buffers; instance range sharded evenly over device_ids (NULL / 0 => device 0).  Returns
- * after every output has landed in the caller's buffers. */
+/* Host buffers; instance range sharded evenly over device_ids (NULL / 0 => device 0), one host
+ * thread per device.  Returns after every output has landed in the caller's buffers (also on
+ * error: no copy is left in flight). */
 int okin_solve_batch(okin_topology* topo, const okin_solver_cfg* cfg, int64_t n_instances, int32_t n_steps,
                      const okin_batch_io* io, const int32_t* device_ids, int32_t n_devices);
 
@@ -150,6 +160,13 @@ int okin_solve_batch(okin_topology* topo, const okin_solver_cfg* cfg, int64_t n_
  * without synchronising. */
 int okin_solve_batch_device(okin_topology* topo, const okin_solver_cfg* cfg, int32_t device, void* stream,
                             int64_t n_instances, int32_t n_steps, const okin_batch_io* d_io);
+
+/* Page-locked host memory for the buffers of okin_solve_batch (copies from / to pageable memory are
+ * staged by the driver and block; with these the H2D / kernel / D2H pipeline overlaps).  The pages are
+ * placed on the NUMA node next to `device` when the box exposes it (device < 0: no preference).
+ * Replaces nothing in the reference (its arrays are NumPy allocations, solver.py:187-214). */
+int okin_host_alloc(int64_t bytes, int32_t device, void** out);
+int okin_host_free(void* ptr);
 
 /* Instance range [begin, begin+count) that shard k of n_shards owns: [k*N/G, (k+1)*N/G).  The
  * same rule splits a host batch over device_ids and a torchrun job over ranks. */

@@ -41,10 +41,14 @@ class SolverCfg(ctypes.Structure):
 class BatchIO(ctypes.Structure):
     """``okin_batch_io``: the buffers of one batch call (host or device addresses)."""
 
-    INPUTS = ("hardpoints", "params", "target_values")
+    INPUTS = ("hardpoints", "params", "target_values", "instance_targets")
     OUTPUTS = ("status", "failed_step", "positions", "iters", "max_residual", "tangents", "velocities",
-               "tangent_health", "metrics", "design", "diagnostics", "jumps")
-    _fields_ = [(n, ctypes.c_void_p) for n in INPUTS + OUTPUTS]
+               "tangent_health", "metrics", "design", "diagnostics", "jumps", "worst_row")
+    # field order of the C struct (include/okin.h)
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "hardpoints", "params", "target_values", "status", "failed_step", "positions", "iters", "max_residual",
+        "tangents", "velocities", "tangent_health", "metrics", "design", "diagnostics", "jumps",
+        "instance_targets", "worst_row")]
 
     @classmethod
     def of(cls, **buffers) -> "BatchIO":
@@ -83,6 +87,8 @@ SIGNATURES = {
     "okin_launch_geometry": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_i32p]),
     "okin_fp64_peak": (ctypes.c_int, [ctypes.c_int32, c_f64p]),
+    "okin_host_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
+    "okin_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "okin_last_error": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32]),
 }
 
@@ -156,6 +162,23 @@ def shard_range(n_instances: int, shard: int, n_shards: int) -> tuple:
     return begin.value, count.value
 
 
+def pinned_empty(shape, dtype=np.float64, device: int = 0) -> np.ndarray:
+    """Uninitialised array in page-locked host memory (``okin_host_alloc``), placed next to
+    ``device``.  Buffers like this keep the H2D / kernel / D2H pipeline of ``okin_solve_batch``
+    overlapped; allocate once and reuse (``solve_batch(out=...)``), page-locking is slow."""
+    import weakref
+    shape = tuple(int(d) for d in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes == 0:
+        return np.empty(shape, dtype)
+    ptr = ctypes.c_void_p()
+    check(load().okin_host_alloc(nbytes, device, ctypes.byref(ptr)), "okin_host_alloc")
+    raw = np.ctypeslib.as_array((ctypes.c_char * nbytes).from_address(ptr.value))
+    weakref.finalize(raw, load().okin_host_free, ptr.value)   # views keep ``raw`` alive through .base
+    return raw.view(dtype).reshape(shape)
+
+
 def default_cfg(**overrides) -> SolverCfg:
     cfg = SolverCfg()
     check(load().okin_default_cfg(ctypes.byref(cfg)), "okin_default_cfg")
@@ -206,8 +229,13 @@ class DeviceTopology:
     def solve_batch(self, hardpoints: np.ndarray, target_values: np.ndarray, cfg: SolverCfg | None = None,
                     devices=None, want_positions=True, want_tangents=False, want_metrics=False,
                     want_design=False, params: np.ndarray | None = None, want_velocities=False,
-                    want_health=False, want_diagnostics=False) -> dict:
-        """hardpoints [n_inst, n_in*3]; target_values [n_targets, n_steps]."""
+                    want_health=False, want_diagnostics=False, instance_targets: np.ndarray | None = None,
+                    want_worst_row=False, out: dict | None = None, pinned: bool = False) -> dict:
+        """hardpoints [n_inst, n_in*3]; target_values [n_targets, n_steps];
+        instance_targets optional [n_inst, n_targets, n_steps] (replaces target_values).
+        ``out``: a dict returned by an earlier call; arrays of matching shape are overwritten instead
+        of allocated (the way to reuse page-locked buffers).  ``pinned``: allocate what is missing in
+        page-locked memory next to the first device."""
         require_device()
         prog = self.program
         hp = np.ascontiguousarray(hardpoints, dtype=np.float64)
@@ -225,28 +253,44 @@ class DeviceTopology:
                 raise ValueError(f"params must have shape ({n_inst}, {len(prog.param_names)}), got {par.shape}")
             if par.shape[1] == 0:
                 par = None
+        itv = None
+        if instance_targets is not None:
+            itv = np.ascontiguousarray(instance_targets, dtype=np.float64)
+            if itv.shape != (n_inst, nt, n_steps):
+                raise ValueError(f"instance_targets must have shape ({n_inst}, {nt}, {n_steps}), got {itv.shape}")
         cfg = cfg or default_cfg()
+        dev = np.ascontiguousarray(devices if devices is not None else [0], dtype=np.int32)
+        prev = out or {}
+
+        def buf(name, want, shape, dtype=np.float64):
+            if not want:
+                return None
+            old = prev.get(name)
+            if isinstance(old, np.ndarray) and old.shape == tuple(shape) and old.dtype == np.dtype(dtype) \
+                    and old.flags.c_contiguous and old.flags.writeable:
+                return old
+            return pinned_empty(shape, dtype, int(dev[0])) if pinned else np.empty(shape, dtype)
+
         out = {
-            "positions": np.empty((n_inst, n_steps, prog.n_out, 3)) if want_positions else None,
-            "status": np.empty(n_inst, np.int32),
-            "failed_step": np.empty(n_inst, np.int32),
-            "iters": np.empty((n_inst, n_steps), np.int32),
-            "max_residual": np.empty((n_inst, n_steps)),
-            "tangents": np.empty((n_inst, n_steps, nt, prog.n_unknowns)) if want_tangents else None,
-            "velocities": np.empty((n_inst, n_steps, nt, prog.n_out, 3)) if want_velocities else None,
-            "tangent_health": np.empty((n_inst, n_steps, 2)) if want_health else None,
-            "metrics": np.empty((n_inst, n_steps, len(prog.metric_names))) if want_metrics else None,
-            "design": np.empty((n_inst, prog.n_out, 3)) if want_design else None,
-            "diagnostics": np.empty((n_inst, n_steps, len(prog.diagnostic_names))) if want_diagnostics else None,
-            "jumps": np.empty((n_inst, n_steps, prog.n_unknowns // 3)) if want_diagnostics else None,
+            "positions": buf("positions", want_positions, (n_inst, n_steps, prog.n_out, 3)),
+            "status": buf("status", True, (n_inst,), np.int32),
+            "failed_step": buf("failed_step", True, (n_inst,), np.int32),
+            "iters": buf("iters", True, (n_inst, n_steps), np.int32),
+            "max_residual": buf("max_residual", True, (n_inst, n_steps)),
+            "tangents": buf("tangents", want_tangents, (n_inst, n_steps, nt, prog.n_unknowns)),
+            "velocities": buf("velocities", want_velocities, (n_inst, n_steps, nt, prog.n_out, 3)),
+            "tangent_health": buf("tangent_health", want_health, (n_inst, n_steps, 2)),
+            "metrics": buf("metrics", want_metrics, (n_inst, n_steps, len(prog.metric_names))),
+            "design": buf("design", want_design, (n_inst, prog.n_out, 3)),
+            "diagnostics": buf("diagnostics", want_diagnostics, (n_inst, n_steps, len(prog.diagnostic_names))),
+            "jumps": buf("jumps", want_diagnostics, (n_inst, n_steps, prog.n_unknowns // 3)),
+            "worst_row": buf("worst_row", want_worst_row, (n_inst,), np.int32),
         }
         if want_diagnostics and not prog.diagnostic_names:
             raise ValueError("This topology was compiled without a diagnostic program")
         if want_metrics and not prog.metric_names:
             raise ValueError("This topology was compiled without a metric program")
-        dev = np.ascontiguousarray(devices if devices is not None else [0], dtype=np.int32)
-
-        io = BatchIO.of(hardpoints=hp, params=par, target_values=tv, **out)
+        io = BatchIO.of(hardpoints=hp, params=par, target_values=tv, instance_targets=itv, **out)
         check(load().okin_solve_batch(self.handle, ctypes.byref(cfg), n_inst, n_steps, ctypes.byref(io),
                                       dev.ctypes.data, dev.size), "okin_solve_batch")
         return out

@@ -21,8 +21,12 @@ from .state import SuspensionState
 from .targeting import PointTarget, resolve_target
 from .topology import compile_topology
 
-# A state handed in for evaluation must be a solution of the constraints it is evaluated with.
-STATE_MATCH_TOL_MM = 1e-5
+# A state handed in for evaluation must be a solution of the constraints it is evaluated with.  The
+# bound is the accuracy of states the reference itself produces and accepts: its default-tolerance
+# solves sit 0.6-2.3e-5 mm from the tight solution (tests/golden, positions_default vs
+# positions_tight) and it accepts any state with max|r| <= SOLVE_ACCEPT_RESIDUAL = 1e-3
+# (primitives/constants.py:20); tangents and metrics move by (their derivative) x (that distance).
+STATE_MATCH_TOL_MM = 1e-3
 
 
 @dataclass(frozen=True)

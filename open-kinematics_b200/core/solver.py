@@ -34,8 +34,10 @@ STATUS_OK, STATUS_NOT_CONVERGED, STATUS_RESIDUAL_REJECTED, STATUS_INVALID_GEOMET
 class SolverConfig(NamedTuple):
     """Reference ``SolverConfig`` (solver.py:65-80).  ``residual_tolerance`` is honoured
     exactly.  ``ftol/xtol/gtol`` are MINPACK stopping rules with no counterpart in the
-    device iteration, which always converges to ``max|dx| <= 1e-9 mm`` (tighter than any
-    setting the reference accepts); they are kept for call compatibility."""
+    device iteration (Gauss-Newton ended by a step below ``fine_tol`` = 1e-4 mm, which leaves an
+    error of second order in it, ~1e-10 mm on mm-scale linkages, or by a verification step below
+    1e-6 mm; measured <= 3e-8 mm from the reference's tight-tolerance solution on every golden
+    sweep); they are kept for call compatibility."""
 
     ftol: float = SOLVE_TOLERANCE_VALUE
     xtol: float = SOLVE_TOLERANCE_STEP
@@ -98,13 +100,28 @@ def _device_cfg(solver_config: SolverConfig):
     return _lib.default_cfg(residual_tol=float(solver_config.residual_tolerance))
 
 
-def _failure(program: TopologyProgram, constraints, heads, values, step, status, max_residual, tol) -> RuntimeError:
+def describe_worst_residual(program: TopologyProgram, worst_row: int, constraints: list, step_targets: list) -> str:
+    """The constraint or target owning the largest residual row (solver.py:640-651).  The device
+    reports its own row index; ``program.row_source`` maps it back to the reference's row (a pin or
+    report row of a point-on-line constraint maps to that constraint)."""
+    source = program.row_source[worst_row]
+    if source[0] == "target":
+        target = step_targets[source[1]]
+        point_name = getattr(target.point_id, "name", str(target.point_id))
+        return f"target on point '{point_name}' (direction {target.direction})"
+    return f"constraint {describe_constraint(constraints[source[1]])}"
+
+
+def _failure(program: TopologyProgram, constraints, heads, values, step, status, max_residual, tol,
+             worst_row: int = -1) -> RuntimeError:
     step_targets = [PointTarget(h.point_id, h.direction, float(values[j, step]), h.mode) for j, h in enumerate(heads)]
     if status == STATUS_RESIDUAL_REJECTED:
+        worst = describe_worst_residual(program, worst_row, constraints, step_targets) if worst_row >= 0 \
+            else "unknown"
         return RuntimeError(
             f"Solve at sweep step {step} did not reach an acceptable residual: worst residual "
             f"{max_residual:.6g} exceeds the acceptance tolerance {tol:.6g}. Worst residual row: "
-            "see okin status output. The mechanism likely cannot reach the requested targets "
+            f"{worst}. The mechanism likely cannot reach the requested targets "
             "(kinematic lock-out / infeasible target combination)."
         )
     reason = "invalid geometry (NaN in the design pose)" if status == STATUS_INVALID_GEOMETRY else \
@@ -135,13 +152,14 @@ def solve_suspension_sweep(
     topo = _lib.DeviceTopology(program)
     try:
         hardpoints = np.array([initial_state.positions[k].data for k in program.in_keys]).reshape(1, -1)
-        out = topo.solve_batch(hardpoints, values, _device_cfg(solver_config))
+        out = topo.solve_batch(hardpoints, values, _device_cfg(solver_config), want_worst_row=True)
     finally:
         topo.close()
     status, failed = int(out["status"][0]), int(out["failed_step"][0])
     if status != STATUS_OK:
         raise _failure(program, constraints, heads, values, failed, status,
-                       float(out["max_residual"][0, failed]), solver_config.residual_tolerance)
+                       float(out["max_residual"][0, failed]), solver_config.residual_tolerance,
+                       int(out["worst_row"][0]))
     states, stats = [], []
     for s in range(n_steps):
         positions = {k: Point3(out["positions"][0, s, i]) for i, k in enumerate(program.out_keys)}

@@ -56,6 +56,29 @@ class BatchSweepResult:
     tangent_health: np.ndarray | None = None   # [n_instances, n_steps, 2] (sigma_min, cond)
     diagnostics: np.ndarray | None = None      # [n_instances, n_steps, n_diagnostics]; ``diagnostic_names``
     jumps: np.ndarray | None = None            # [n_instances, n_steps, n_free]; row 0 = thresholds
+    worst_row: np.ndarray | None = None        # [n_instances] device row owning max|r| at the failed step, or -1
+    design: np.ndarray | None = None           # [n_instances, n_out_points, 3] design (setup) pose
+
+    _BUFFERS = (("positions", "positions"), ("status", "status"), ("failed_step", "failed_step"), ("nfev", "iters"),
+                ("max_residual", "max_residual"), ("tangents", "tangents"), ("metrics", "metrics"),
+                ("velocities", "velocities"), ("tangent_health", "tangent_health"), ("diagnostics", "diagnostics"),
+                ("jumps", "jumps"), ("worst_row", "worst_row"), ("design", "design"))
+
+    def buffers(self) -> dict:
+        """The arrays keyed like ``DeviceTopology.solve_batch``'s result (for ``solve(out=...)`` reuse)."""
+        return {abi: getattr(self, field) for field, abi in self._BUFFERS}
+
+    def describe_worst_residual(self, instance: int, constraints: list, heads: list) -> str | None:
+        """Text of the reference's "Worst residual row" (describe_worst_residual, solver.py:640-651)
+        for a failed instance; None when the instance did not fail or ``worst_row`` was not requested."""
+        if self.worst_row is None or int(self.worst_row[instance]) < 0:
+            return None
+        source = self.program.row_source[int(self.worst_row[instance])]
+        if source[0] == "target":
+            head = heads[source[1]]
+            return f"target on point '{getattr(head.point_id, 'name', str(head.point_id))}' (direction {head.direction})"
+        from .solver import describe_constraint
+        return f"constraint {describe_constraint(constraints[source[1]])}"
 
     @property
     def point_keys(self) -> list:
@@ -122,20 +145,35 @@ class BatchSolver:
     def solve(self, hardpoints: np.ndarray, solver_config: SolverConfig = SolverConfig(), devices=None,
               want_positions: bool = True, want_tangents: bool = False,
               want_metrics: bool = False, params: np.ndarray | None = None, want_velocities: bool = False,
-              want_health: bool = False, want_diagnostics: bool = False) -> BatchSweepResult:
+              want_health: bool = False, want_diagnostics: bool = False, want_design: bool = False,
+              want_worst_row: bool = False, instance_targets: np.ndarray | None = None,
+              out: BatchSweepResult | None = None, pinned: bool = False) -> BatchSweepResult:
         """``params``: optional ``[n_instances, n_params]`` per-instance scalars in the order of
-        ``program.param_names`` (camber-shim datums and thicknesses); default = the model's."""
+        ``program.param_names`` (camber-shim datums and thicknesses); default = the model's.
+        ``instance_targets``: optional ``[n_instances, n_targets, n_steps]`` per-instance sweep tables
+        (same meaning as the sweep's own values: relative displacement / absolute coordinate).
+        ``devices``: CUDA device ids; the instance range is split evenly over them.
+        ``out``: an earlier result of the same shape whose arrays are overwritten (no allocation);
+        ``pinned``: allocate result arrays in page-locked host memory (slow to allocate, fast to fill:
+        keep the result and pass it back as ``out``)."""
         cfg = _lib.default_cfg(residual_tol=float(solver_config.residual_tolerance))
         hp = np.asarray(hardpoints, dtype=np.float64)
         hp = hp.reshape(hp.shape[0], -1)
-        out = self.topology.solve_batch(hp, self.values, cfg, devices=devices,
+        res = self.topology.solve_batch(hp, self.values, cfg, devices=devices,
                                         want_positions=want_positions, want_tangents=want_tangents,
                                         want_metrics=want_metrics, params=params,
                                         want_velocities=want_velocities, want_health=want_health,
-                                        want_diagnostics=want_diagnostics)
-        return BatchSweepResult(self.program, out["positions"], out["status"], out["failed_step"],
-                                out["iters"], out["max_residual"], out["tangents"], out["metrics"],
-                                out["velocities"], out["tangent_health"], out["diagnostics"], out["jumps"])
+                                        want_diagnostics=want_diagnostics, want_design=want_design,
+                                        want_worst_row=want_worst_row, instance_targets=instance_targets,
+                                        out=out.buffers() if out is not None else None, pinned=pinned)
+        return BatchSweepResult(self.program, res["positions"], res["status"], res["failed_step"],
+                                res["iters"], res["max_residual"], res["tangents"], res["metrics"],
+                                res["velocities"], res["tangent_health"], res["diagnostics"], res["jumps"],
+                                res.get("worst_row"), res.get("design"))
+
+    def pinned_hardpoints(self, n_instances: int, device: int = 0) -> np.ndarray:
+        """Page-locked ``[n_instances, n_in*3]`` input array (fill it, pass it to ``solve``)."""
+        return _lib.pinned_empty((n_instances, 3 * self.program.n_in), np.float64, device)
 
     def close(self) -> None:
         self.topology.close()

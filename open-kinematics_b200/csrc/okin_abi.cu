@@ -11,11 +11,16 @@
 // of the diagnostics is a second kernel on the same stream.
 #include <cuda_runtime.h>
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/okin.h"
@@ -43,7 +48,12 @@ int fail(int code, const std::string& msg) {
       return fail(OKIN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));           \
   } while (0)
 
+// cudaFuncSetAttribute + launch of the (process-wide) kernel functions must not interleave between
+// threads driving different topologies on the same device.
+std::mutex g_launch_mu[OKIN_MAX_DEVICES];
+
 struct DeviceCopy {
+  int device = 0;
   bool ready = false;
   int32_t* hdr = nullptr;
   int32_t* ib = nullptr;
@@ -78,7 +88,7 @@ template <bool FULL, bool SHIM>
 __global__ void __launch_bounds__(OKIN_MAX_THREADS, 1)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, OkinSolverCfg cfg, okin_batch_io io, int n_iblob,
-                  int table_doubles) {
+                  int table_doubles, double* __restrict__ backup) {
   // [section pointers][header][hot tables][one state slice per warp]
   const int32_t** sec = reinterpret_cast<const int32_t**>(okin_smem);
   int32_t* shdr = reinterpret_cast<int32_t*>(okin_smem + OKIN_S_COUNT);
@@ -115,9 +125,12 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
     out.diagnostics = io.diagnostics ? io.diagnostics + (size_t)i * n_steps * hdr[OKIN_H_NDIAG] : nullptr;
     out.status = io.status + i;
     out.failed_step = io.failed_step + i;
+    out.worst_row = io.worst_row ? io.worst_row + i : nullptr;
+    out.backup = backup + ((size_t)blockIdx.x * warps_per_cta + warp) * n;
     okin_sweep<FULL, SHIM>(pr, sm, io.hardpoints + (size_t)i * 3 * nin,
-               io.params ? io.params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, io.target_values, n_steps, cfg,
-               out);
+               io.params ? io.params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr,
+               io.instance_targets ? io.instance_targets + (size_t)i * nt * n_steps : io.target_values, n_steps,
+               cfg, out);
     __syncwarp();
   }
 }
@@ -163,6 +176,7 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
   std::lock_guard<std::mutex> lock(t->mu);
   DeviceCopy& d = t->dev[device];
   if (!d.ready) {
+    d.device = device;
     OKIN_CUDA(cudaSetDevice(device));
     OKIN_CUDA(cudaMalloc(&d.hdr, t->hdr.size() * sizeof(int32_t)));
     OKIN_CUDA(cudaMalloc(&d.ib, std::max<size_t>(t->ib.size(), 1) * sizeof(int32_t)));
@@ -229,9 +243,18 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
   const bool shim = t->hdr[OKIN_H_NSHIM] > 0;
   auto kernel = full ? (shim ? okin_sweep_kernel<true, true> : okin_sweep_kernel<true, false>)
                      : (shim ? okin_sweep_kernel<false, true> : okin_sweep_kernel<false, false>);
+  // The attribute belongs to the kernel function of this device context, not to a topology: another
+  // live topology may have lowered it since ensure_device ran, so it is set before every launch.
+  std::lock_guard<std::mutex> launch_lock(g_launch_mu[d->device]);
+  OKIN_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_bytes));
+  // Stream-ordered scratch: one row per warp of this launch for its instance's last accepted solution.
+  double* backup = nullptr;
+  OKIN_CUDA(cudaMallocAsync(&backup, (size_t)grid * w * 3 * std::max(t->hdr[OKIN_H_NF], 1) * sizeof(double), stream));
   kernel<<<grid, w * 32, d->smem_bytes, stream>>>(
-      d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, c, io, (int)t->ib.size(), d->table_doubles);
-  OKIN_CUDA(cudaGetLastError());
+      d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, c, io, (int)t->ib.size(), d->table_doubles, backup);
+  const cudaError_t launch_err = cudaGetLastError();
+  OKIN_CUDA(cudaFreeAsync(backup, stream));
+  OKIN_CUDA(launch_err);
   if (io.diagnostics && t->hdr[OKIN_H_NDIAG] && n_steps > 0) {
     // continuity pass over the position rows the sweep kernel just wrote (same stream)
     const int stride = (n_steps - 1) | 1;   // odd: lanes walk their histories on different banks
@@ -258,12 +281,191 @@ int check_common(const okin_topology* t, const okin_solver_cfg* cfg, int64_t n_i
   const void *hp = io->hardpoints, *tv = io->target_values, *status = io->status, *failed = io->failed_step;
   if (n_instances < 0 || n_steps < 0) return fail(OKIN_ERR_USAGE, "negative size");
   if (n_instances > 0 && (!hp || !status || !failed)) return fail(OKIN_ERR_USAGE, "null required buffer");
-  if (n_steps > 0 && t->hdr[OKIN_H_NT] > 0 && !tv) return fail(OKIN_ERR_USAGE, "null target_values");
+  if (n_steps > 0 && t->hdr[OKIN_H_NT] > 0 && !tv && !io->instance_targets)
+    return fail(OKIN_ERR_USAGE, "null target_values (and no instance_targets)");
   if ((io->diagnostics || io->jumps) && !t->hdr[OKIN_H_NDIAG])
     return fail(OKIN_ERR_USAGE, "topology was compiled without a diagnostic program");
   if (io->jumps && !io->diagnostics) return fail(OKIN_ERR_USAGE, "jumps output needs the diagnostics output");
   if (cfg->max_iter < 1 || !(cfg->step_tol > 0.0) || !(cfg->coarse_tol >= cfg->step_tol)) return fail(OKIN_ERR_USAGE, "invalid solver config");
   return OKIN_OK;
+}
+
+// ---- host-buffer path ------------------------------------------------------------------------
+// Every per-instance array of a call is one "lane" of a pipeline slot: (host pointer, bytes per
+// instance).  scratch: device buffer needed although the caller does not want the array back.
+struct Lane { const void* host; size_t per_inst; bool input; bool scratch; size_t bytes; };
+constexpr int kLanes = 16;
+
+struct HostBatch {
+  Lane lanes[kLanes];
+  size_t chunk, b_tv, slot_bytes, tv_count;
+  const okin_batch_io* io;
+  int32_t n_steps;
+  HostBatch(const okin_topology* t, int64_t n_instances, int32_t n_steps_, const okin_batch_io* io_) : io(io_), n_steps(n_steps_) {
+    const int32_t* h = t->hdr.data();
+    const size_t nin3 = 3 * (size_t)h[OKIN_H_NIN], nout3 = 3 * (size_t)h[OKIN_H_NOUT];
+    const size_t nt = h[OKIN_H_NT], n = 3 * (size_t)h[OKIN_H_NF];
+    const size_t nm = (size_t)h[OKIN_H_NM], npar = (size_t)h[OKIN_H_NPARAM], nd = (size_t)h[OKIN_H_NDIAG];
+    const size_t S = (size_t)n_steps;
+    const Lane init[kLanes] = {
+        {io->hardpoints, nin3 * 8, true, false, 0},
+        {(io->params && npar) ? io->params : nullptr, npar * 8, true, false, 0},
+        {io->status, 4, false, false, 0},
+        {io->failed_step, 4, false, false, 0},
+        {io->positions, S * nout3 * 8, false, io->diagnostics && !io->positions, 0},
+        {io->iters, S * 4, false, false, 0},
+        {io->max_residual, S * 8, false, false, 0},
+        {io->tangents, S * nt * n * 8, false, false, 0},
+        {io->velocities, S * nt * nout3 * 8, false, false, 0},
+        {io->tangent_health, S * 2 * 8, false, false, 0},
+        {(io->metrics && nm) ? io->metrics : nullptr, S * nm * 8, false, false, 0},
+        {io->design, nout3 * 8, false, false, 0},
+        {io->diagnostics, S * nd * 8, false, false, 0},
+        {io->jumps, S * (n / 3) * 8, false, false, 0},
+        {(io->instance_targets && nt * S) ? io->instance_targets : nullptr, nt * S * 8, true, false, 0},
+        {io->worst_row, 4, false, false, 0},
+    };
+    std::memcpy(lanes, init, sizeof(init));
+    chunk = (size_t)std::min<int64_t>(std::max<int64_t>(n_instances, 1), OKIN_PIPE_CHUNK);
+    tv_count = nt * S;
+    b_tv = align(std::max<size_t>(tv_count, 1) * 8);
+    slot_bytes = b_tv;
+    for (Lane& l : lanes) {
+      l.bytes = (l.host || l.scratch) ? align(chunk * std::max<size_t>(l.per_inst, 1)) : 0;
+      slot_bytes += l.bytes;
+    }
+  }
+  static size_t align(size_t b) { return (b + 255) & ~(size_t)255; }
+};
+
+struct Shard {
+  int device = 0;
+  DeviceCopy* d = nullptr;
+  int64_t begin = 0, count = 0;
+  int rc = OKIN_OK;
+  std::string err;
+};
+
+// Moves the calling thread onto the CPUs of the NUMA node `device` hangs off (sysfs); false when
+// the box does not say (virtual machines often report node -1).
+bool bind_thread_near_device(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return false;
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  int node = -1;
+  {
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+    if (!(f >> node) || node < 0) return false;
+  }
+  std::ifstream f("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist");
+  std::string list;
+  if (!std::getline(f, list) || list.empty()) return false;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  size_t pos = 0;
+  int n_set = 0;
+  while (pos < list.size()) {
+    size_t end = list.find(',', pos);
+    if (end == std::string::npos) end = list.size();
+    const std::string tok = list.substr(pos, end - pos);
+    const size_t dash = tok.find('-');
+    const int lo = std::atoi(tok.c_str());
+    const int hi = dash == std::string::npos ? lo : std::atoi(tok.c_str() + dash + 1);
+    for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) { CPU_SET(c, &set); ++n_set; }
+    pos = end + 1;
+  }
+  if (n_set == 0) return false;
+  // keep only CPUs this process may run on
+  cpu_set_t allowed;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+    cpu_set_t both;
+    CPU_AND(&both, &set, &allowed);
+    if (CPU_COUNT(&both) == 0) return false;
+    set = both;
+  }
+  return pthread_setaffinity_np(pthread_self(), sizeof(set), &set) == 0;
+}
+
+// One device's instance range: chunks rotate over OKIN_PIPE_SLOTS streams, so the H2D copy of chunk
+// k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k.  Whatever happens, the streams are
+// drained before returning: no copy may still be writing into caller buffers after the call.
+void run_shard(okin_topology* t, const okin_solver_cfg* cfg, const HostBatch& hb, Shard& sh) {
+  DeviceCopy* d = sh.d;
+  auto drain = [&] {
+    for (int k = 0; k < OKIN_PIPE_SLOTS; ++k) cudaStreamSynchronize(d->streams[k]);
+  };
+  auto cuda_fail = [&](const char* what, cudaError_t err) {
+    drain();
+    sh.rc = OKIN_ERR_CUDA;
+    sh.err = std::string(what) + ": " + cudaGetErrorString(err);
+  };
+#define OKIN_SHARD_CUDA(call)                                  \
+  do {                                                         \
+    cudaError_t err__ = (call);                                \
+    if (err__ != cudaSuccess) { cuda_fail(#call, err__); return; } \
+  } while (0)
+  OKIN_SHARD_CUDA(cudaSetDevice(sh.device));
+  const size_t chunk = hb.chunk;
+  const int slots = (int)std::min<int64_t>(OKIN_PIPE_SLOTS, (sh.count + (int64_t)chunk - 1) / (int64_t)chunk);
+  if (hb.slot_bytes * slots > d->ws_bytes) {
+    if (d->ws) OKIN_SHARD_CUDA(cudaFree(d->ws));
+    d->ws = nullptr;
+    d->ws_bytes = 0;
+    OKIN_SHARD_CUDA(cudaMalloc(&d->ws, hb.slot_bytes * slots));
+    d->ws_bytes = hb.slot_bytes * slots;
+  }
+  int64_t done = 0;
+  for (int ck = 0; done < sh.count; ++ck, done += (int64_t)chunk) {
+    const int slot = ck % slots;
+    const size_t c = (size_t)std::min<int64_t>((int64_t)chunk, sh.count - done);
+    const size_t b0 = (size_t)(sh.begin + done);
+    cudaStream_t st = d->streams[slot];
+    char* p = (char*)d->ws + hb.slot_bytes * slot;
+    void* dev[kLanes];
+    double* w_tv = (double*)p;
+    p += hb.b_tv;
+    for (int l = 0; l < kLanes; ++l) {
+      dev[l] = hb.lanes[l].bytes ? p : nullptr;
+      p += hb.lanes[l].bytes;
+    }
+    for (int l = 0; l < kLanes; ++l)
+      if (dev[l] && hb.lanes[l].input)
+        OKIN_SHARD_CUDA(cudaMemcpyAsync(dev[l], (const char*)hb.lanes[l].host + b0 * hb.lanes[l].per_inst,
+                                        c * hb.lanes[l].per_inst, cudaMemcpyHostToDevice, st));
+    if (hb.tv_count && hb.io->target_values && ck < slots)
+      OKIN_SHARD_CUDA(cudaMemcpyAsync(w_tv, hb.io->target_values, hb.tv_count * 8, cudaMemcpyHostToDevice, st));
+    okin_batch_io dio{};
+    dio.hardpoints = (const double*)dev[0];
+    dio.params = (const double*)dev[1];
+    dio.target_values = hb.io->target_values ? w_tv : nullptr;
+    dio.status = (int32_t*)dev[2];
+    dio.failed_step = (int32_t*)dev[3];
+    dio.positions = (double*)dev[4];
+    dio.iters = (int32_t*)dev[5];
+    dio.max_residual = (double*)dev[6];
+    dio.tangents = (double*)dev[7];
+    dio.velocities = (double*)dev[8];
+    dio.tangent_health = (double*)dev[9];
+    dio.metrics = (double*)dev[10];
+    dio.design = (double*)dev[11];
+    dio.diagnostics = (double*)dev[12];
+    dio.jumps = (double*)dev[13];
+    dio.instance_targets = (const double*)dev[14];
+    dio.worst_row = (int32_t*)dev[15];
+    const int rc = launch(t, d, cfg, st, (int64_t)c, hb.n_steps, dio);
+    if (rc) {
+      drain();
+      sh.rc = rc;
+      sh.err = g_last_error;
+      return;
+    }
+    for (int l = 0; l < kLanes; ++l)
+      if (dev[l] && hb.lanes[l].host && !hb.lanes[l].input && hb.lanes[l].per_inst)
+        OKIN_SHARD_CUDA(cudaMemcpyAsync((char*)const_cast<void*>(hb.lanes[l].host) + b0 * hb.lanes[l].per_inst, dev[l],
+                                        c * hb.lanes[l].per_inst, cudaMemcpyDeviceToHost, st));
+  }
+  for (int k = 0; k < OKIN_PIPE_SLOTS; ++k) OKIN_SHARD_CUDA(cudaStreamSynchronize(d->streams[k]));
+#undef OKIN_SHARD_CUDA
 }
 
 }  // namespace
@@ -411,111 +613,54 @@ int okin_solve_batch(okin_topology* t, const okin_solver_cfg* cfg, int64_t n_ins
     n_devices = 1;
   }
   if (n_devices > OKIN_MAX_DEVICES) return fail(OKIN_ERR_USAGE, "too many devices");
-  const int32_t* h = t->hdr.data();
-  const size_t nin3 = 3 * (size_t)h[OKIN_H_NIN], nout3 = 3 * (size_t)h[OKIN_H_NOUT];
-  const size_t nt = h[OKIN_H_NT], n = 3 * (size_t)h[OKIN_H_NF];
-  const size_t nm = (size_t)h[OKIN_H_NM], npar = (size_t)h[OKIN_H_NPARAM];
-  const size_t S = (size_t)n_steps;
+  for (int a = 0; a < n_devices; ++a)
+    for (int b = a + 1; b < n_devices; ++b)
+      if (device_ids[a] == device_ids[b]) return fail(OKIN_ERR_USAGE, "device listed twice");
+  HostBatch hb(t, n_instances, n_steps, io);
 
   // Contiguous instance ranges [k*N/G, (k+1)*N/G) per device: the host-side "gather" is the D2H
-  // copies.  Inside a device the range is cut into chunks that rotate over OKIN_PIPE_SLOTS streams,
-  // so the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k.
-  // Every per-instance array is one "lane" of a slot: (host pointer, bytes per instance).
-  // scratch: device buffer needed although the caller does not want the array back.
-  struct Lane { const void* host; size_t per_inst; bool input; bool scratch; size_t bytes; };
-  const size_t nd = (size_t)h[OKIN_H_NDIAG];
-  Lane lanes[] = {
-      {io->hardpoints, nin3 * 8, true, false, 0},
-      {(io->params && npar) ? io->params : nullptr, npar * 8, true, false, 0},
-      {io->status, 4, false, false, 0},
-      {io->failed_step, 4, false, false, 0},
-      {io->positions, S * nout3 * 8, false, io->diagnostics && !io->positions, 0},
-      {io->iters, S * 4, false, false, 0},
-      {io->max_residual, S * 8, false, false, 0},
-      {io->tangents, S * nt * n * 8, false, false, 0},
-      {io->velocities, S * nt * nout3 * 8, false, false, 0},
-      {io->tangent_health, S * 2 * 8, false, false, 0},
-      {(io->metrics && nm) ? io->metrics : nullptr, S * nm * 8, false, false, 0},
-      {io->design, nout3 * 8, false, false, 0},
-      {io->diagnostics, S * nd * 8, false, false, 0},
-      {io->jumps, S * (n / 3) * 8, false, false, 0},
-  };
-  constexpr int n_lanes = (int)(sizeof(lanes) / sizeof(lanes[0]));
-  auto align = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  const size_t chunk = (size_t)std::min<int64_t>(std::max<int64_t>(n_instances, 1), OKIN_PIPE_CHUNK);
-  const size_t b_tv = align(std::max<size_t>(nt * S, 1) * 8);
-  size_t slot_bytes = b_tv;
-  for (Lane& l : lanes) {
-    l.bytes = (l.host || l.scratch) ? align(chunk * std::max<size_t>(l.per_inst, 1)) : 0;
-    slot_bytes += l.bytes;
-  }
-
-  std::vector<std::pair<int, DeviceCopy*>> used;
+  // copies.  One host thread per device (copies from / to pageable caller buffers block the
+  // issuing thread; with a thread per device the devices still run concurrently).
+  std::vector<Shard> shards;
   for (int k = 0; k < n_devices; ++k) {
-    int64_t begin = 0, count = 0;
-    okin_shard_range(n_instances, k, n_devices, &begin, &count);
-    if (count == 0) continue;
-    DeviceCopy* d = nullptr;
-    rc = ensure_device(t, device_ids[k], &d);
+    Shard sh;
+    okin_shard_range(n_instances, k, n_devices, &sh.begin, &sh.count);
+    if (sh.count == 0) continue;
+    sh.device = device_ids[k];
+    rc = ensure_device(t, sh.device, &sh.d);
     if (rc) return rc;
-    OKIN_CUDA(cudaSetDevice(device_ids[k]));
-    used.push_back({device_ids[k], d});
-    const int slots = (int)std::min<int64_t>(OKIN_PIPE_SLOTS, (count + (int64_t)chunk - 1) / (int64_t)chunk);
-    if (slot_bytes * slots > d->ws_bytes) {
-      if (d->ws) OKIN_CUDA(cudaFree(d->ws));
-      d->ws = nullptr;
-      d->ws_bytes = 0;
-      OKIN_CUDA(cudaMalloc(&d->ws, slot_bytes * slots));
-      d->ws_bytes = slot_bytes * slots;
-    }
-    int64_t done = 0;
-    for (int ck = 0; done < count; ++ck, done += (int64_t)chunk) {
-      const int slot = ck % slots;
-      const size_t c = (size_t)std::min<int64_t>((int64_t)chunk, count - done);
-      const size_t b0 = (size_t)(begin + done);
-      cudaStream_t st = d->streams[slot];
-      char* p = (char*)d->ws + slot_bytes * slot;
-      void* dev[n_lanes];
-      double* w_tv = (double*)p;
-      p += b_tv;
-      for (int l = 0; l < n_lanes; ++l) {
-        dev[l] = lanes[l].bytes ? p : nullptr;
-        p += lanes[l].bytes;
-      }
-      for (int l = 0; l < n_lanes; ++l)
-        if (dev[l] && lanes[l].input)
-          OKIN_CUDA(cudaMemcpyAsync(dev[l], (const char*)lanes[l].host + b0 * lanes[l].per_inst, c * lanes[l].per_inst,
-                                    cudaMemcpyHostToDevice, st));
-      if (nt * S && ck < slots)
-        OKIN_CUDA(cudaMemcpyAsync(w_tv, io->target_values, nt * S * 8, cudaMemcpyHostToDevice, st));
-      okin_batch_io dio{};
-      dio.hardpoints = (const double*)dev[0];
-      dio.params = (const double*)dev[1];
-      dio.target_values = w_tv;
-      dio.status = (int32_t*)dev[2];
-      dio.failed_step = (int32_t*)dev[3];
-      dio.positions = (double*)dev[4];
-      dio.iters = (int32_t*)dev[5];
-      dio.max_residual = (double*)dev[6];
-      dio.tangents = (double*)dev[7];
-      dio.velocities = (double*)dev[8];
-      dio.tangent_health = (double*)dev[9];
-      dio.metrics = (double*)dev[10];
-      dio.design = (double*)dev[11];
-      dio.diagnostics = (double*)dev[12];
-      dio.jumps = (double*)dev[13];
-      rc = launch(t, d, cfg, st, (int64_t)c, n_steps, dio);
-      if (rc) return rc;
-      for (int l = 0; l < n_lanes; ++l)
-        if (dev[l] && lanes[l].host && !lanes[l].input && lanes[l].per_inst)
-          OKIN_CUDA(cudaMemcpyAsync((char*)const_cast<void*>(lanes[l].host) + b0 * lanes[l].per_inst, dev[l],
-                                    c * lanes[l].per_inst, cudaMemcpyDeviceToHost, st));
-    }
+    shards.push_back(sh);
   }
-  for (auto& u : used) {
-    OKIN_CUDA(cudaSetDevice(u.first));
-    for (int k = 0; k < OKIN_PIPE_SLOTS; ++k) OKIN_CUDA(cudaStreamSynchronize(u.second->streams[k]));
+  if (shards.size() == 1) {
+    run_shard(t, cfg, hb, shards[0]);
+  } else {
+    std::vector<std::thread> workers;
+    for (Shard& sh : shards) workers.emplace_back([&, psh = &sh] { run_shard(t, cfg, hb, *psh); });
+    for (std::thread& w : workers) w.join();
   }
+  for (const Shard& sh : shards)
+    if (sh.rc) return fail(sh.rc, sh.err);
+  return OKIN_OK;
+}
+
+int okin_host_alloc(int64_t bytes, int32_t device, void** out) {
+  if (!out || bytes < 0) return fail(OKIN_ERR_USAGE, "invalid host allocation request");
+  *out = nullptr;
+  if (bytes == 0) return OKIN_OK;
+  // Page-locked, portable (usable from every device context).  Pages are placed on the NUMA node of
+  // the allocating thread, so the thread is moved next to `device` for the duration of the call.
+  cpu_set_t saved;
+  const bool have_saved = pthread_getaffinity_np(pthread_self(), sizeof(saved), &saved) == 0;
+  const bool moved = device >= 0 && have_saved && bind_thread_near_device(device);
+  cudaError_t err = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable);
+  if (moved) pthread_setaffinity_np(pthread_self(), sizeof(saved), &saved);
+  if (err != cudaSuccess) return fail(OKIN_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(err));
+  return OKIN_OK;
+}
+
+int okin_host_free(void* p) {
+  if (!p) return OKIN_OK;
+  OKIN_CUDA(cudaFreeHost(p));
   return OKIN_OK;
 }
 

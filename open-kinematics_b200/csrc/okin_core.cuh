@@ -1660,7 +1660,47 @@ struct OkinOutputs {
   double* diagnostics;    // [n_steps][NDIAG] or null
   int32_t* status;        // [1]
   int32_t* failed_step;   // [1]
+  int32_t* worst_row;     // [1] or null: row owning max|r| at the failed step (solver.py:640-651), else -1
+  double* backup;         // scratch [3*NF] (global memory, one per resident warp): the last accepted
+                          // solution, for the retry from the plain warm start
 };
+
+// Index of the row with the largest |r| in r[0 .. nrows) (first one on ties, like np.argmax;
+// a NaN row wins).  Warp-uniform result.  Only runs when a sweep fails.
+template <typename Dummy = void>
+OKIN_FN int okin_worst_row(const OkinProgram& pr, double* sm) {
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
+  const int nrows = hdr[OKIN_H_NROW] + hdr[OKIN_H_NREP];
+  const double* r = sm + hdr[OKIN_H_OFF_R];
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  OKIN_PHASE_BEGIN
+  double mx = -1.0;
+  for (int t = lane; t < nrows; t += 32) {
+    const double ar = fabs(r[t]);
+    if (ar > mx || ar != ar) mx = ar;
+  }
+  red[lane] = mx;
+  OKIN_PHASE_END
+  const double rmax = okin_red_max(red);
+  OKIN_PHASE_BEGIN
+  int first = 1 << 30;
+  for (int t = lane; t < nrows; t += 32) {
+    const double ar = fabs(r[t]);
+    if ((ar == rmax || (ar != ar && rmax != rmax)) && t < first) first = t;
+  }
+  red[lane] = (double)first;
+  OKIN_PHASE_END
+  OKIN_PHASE_BEGIN
+  if (lane == 0) {
+    double lo = red[0];
+    for (int k = 1; k < 32; ++k) lo = red[k] < lo ? red[k] : lo;
+    red[0] = lo;
+  }
+  OKIN_PHASE_END
+  const int row = (int)red[0];
+  return row < nrows ? row : -1;
+}
 
 // Whole sweep for one instance (solver.py:716-774).  tvals: [NT][n_steps] relative/absolute
 // sweep values shared by all instances of the launch.
@@ -1679,6 +1719,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   const int nout = hdr[OKIN_H_NOUT];
   const int32_t* out_point = OKIN_SHARED(okin_sec(pr, OKIN_S_OUT_POINT));
   const int32_t* ecol = okin_sec(pr, OKIN_S_ELIM_COL);
+  const int32_t* elim_point = OKIN_SHARED(okin_sec(pr, OKIN_S_ELIM_POINT));
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
   // outputs only the full instantiation knows about
@@ -1708,6 +1749,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   OKIN_PHASE_END
   bool have_tangent = false;
   int history = 0;
+  int worst = -1;
 
   for (int s = 0; s < n_steps; ++s) {
     if (status == OKIN_STATUS_OK) {
@@ -1734,8 +1776,22 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       bool conv = false, tangents_ready = false;
       const bool relinearise = o_tangents || o_velocities || o_health || o_metrics;
       bool at_solution = false;
-      const int nfev = okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready, relinearise, &at_solution);
-      const bool valid = st.rmax == st.rmax;
+      int nfev = 0;
+      bool valid = true;
+      // The reference starts every step from the previous solution (solver.py:717-774, x_0 = result.x).
+      // The predicted start is an optimisation only: if the step fails from it, the previous solution
+      // is restored and the step is solved again from the plain warm start before it is flagged.
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        if (attempt == 1) {
+          OKIN_PHASE_BEGIN
+          for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3] = out.backup[u];
+          OKIN_PHASE_END
+          history = 0;
+        }
+        nfev += okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready, relinearise, &at_solution);
+        valid = st.rmax == st.rmax;
+        if ((conv && valid && st.rmax <= cfg.residual_tol) || !predict || s == 0) break;
+      }
       if (!conv || !valid) {
         status = valid ? OKIN_STATUS_NOT_CONVERGED : OKIN_STATUS_INVALID_GEOMETRY;
         failed = s;
@@ -1743,6 +1799,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
         status = OKIN_STATUS_RESIDUAL_REJECTED;
         failed = s;
       }
+      if (status != OKIN_STATUS_OK && out.worst_row) worst = okin_worst_row(pr, sm);
       OKIN_PHASE_BEGIN
       if (lane == 0) {
         if (out.iters) out.iters[s] = nfev;
@@ -1776,11 +1833,14 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       OKIN_PHASE_END
     }
     const bool ok = status == OKIN_STATUS_OK;
-    if (out.positions) {
-      double* dst = out.positions + (size_t)s * 3 * nout;
+    {
+      double* dst = out.positions ? out.positions + (size_t)s * 3 * nout : nullptr;
       OKIN_PHASE_BEGIN
-      for (int t = lane; t < 3 * nout; t += 32)
-        dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
+      if (dst)
+        for (int t = lane; t < 3 * nout; t += 32)
+          dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
+      if (ok && cfg.use_predictor)   // last accepted solution (only a predicted start can be retried)
+        for (int u = lane; u < n; u += 32) out.backup[u] = pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3];
       OKIN_PHASE_END
     }
     if (FULL && o_metrics) {
@@ -1830,6 +1890,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   if (lane == 0) {
     out.status[0] = status;
     out.failed_step[0] = failed;
+    if (out.worst_row) out.worst_row[0] = worst;
   }
   OKIN_PHASE_END
 }

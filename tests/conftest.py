@@ -33,11 +33,13 @@ def emu_device(monkeypatch):
 
         def solve_batch(self, hardpoints, target_values, cfg=None, devices=None, want_positions=True,
                         want_tangents=False, want_metrics=False, want_design=False, params=None,
-                        want_velocities=False, want_health=False, want_diagnostics=False):
+                        want_velocities=False, want_health=False, want_diagnostics=False, instance_targets=None,
+                        want_worst_row=False, out=None, pinned=False):
             import numpy as np
             over = {} if cfg is None else {name: getattr(cfg, name) for name, _ in _lib.SolverCfg._fields_}
             tv = np.asarray(target_values, dtype=np.float64).reshape(len(self.program.target_points), -1)
-            out = emu_solve(self.program, hardpoints, tv, params=params, want_health=want_health, **over)
+            out = emu_solve(self.program, hardpoints, tv, params=params, want_health=want_health,
+                            instance_targets=instance_targets, **over)
             if not want_metrics:
                 out["metrics"] = None
             return out

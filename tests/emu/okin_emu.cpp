@@ -17,7 +17,7 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
   OkinSolverCfg cfg{c->step_tol, c->coarse_tol, c->fine_tol, c->residual_tol, c->mu_init, c->max_iter,
                     c->use_predictor};
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
-  std::vector<double> sm(hdr[OKIN_H_SMEM_DOUBLES]);
+  std::vector<double> sm(hdr[OKIN_H_SMEM_DOUBLES]), backup(n + 1);
   for (long i = 0; i < n_instances; ++i) {
     std::fill(sm.begin(), sm.end(), 0.0);
     OkinOutputs out;
@@ -33,9 +33,12 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
     out.diagnostics = (io->diagnostics && nd) ? io->diagnostics + (size_t)i * n_steps * nd : nullptr;
     out.status = io->status + i;
     out.failed_step = io->failed_step + i;
+    out.worst_row = io->worst_row ? io->worst_row + i : nullptr;
+    out.backup = backup.data();
     okin_sweep<true, true>(pr, sm.data(), io->hardpoints + (size_t)i * 3 * nin,
-               io->params ? io->params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr, io->target_values, n_steps, cfg,
-               out);
+               io->params ? io->params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr,
+               io->instance_targets ? io->instance_targets + (size_t)i * nt * n_steps : io->target_values, n_steps,
+               cfg, out);
     if (out.diagnostics && n_steps > 0) {  // continuity pass, as the product's second kernel does
       const int stride = (n_steps - 1) | 1;
       std::vector<double> scratch((size_t)32 * stride + 64);

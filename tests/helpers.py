@@ -196,7 +196,8 @@ def generic_mechanism():
     return state, cons, sweep, manager, spec, arrays
 
 
-def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, want_health=False, **cfg) -> dict:
+def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, want_health=False,
+              instance_targets=None, **cfg) -> dict:
     """Run the lane-emulation build of the device core; ``cfg`` overrides ``okin_solver_cfg`` fields."""
     from open_kinematics_b200._lib import BatchIO, SolverCfg
     hp = np.ascontiguousarray(hardpoints, dtype=np.float64).reshape(-1, 3 * program.n_in)
@@ -212,14 +213,16 @@ def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, 
         "design": np.zeros((n_inst, program.n_out, 3)),
         "diagnostics": np.zeros((n_inst, n_steps, len(program.diagnostic_names))) if program.diagnostic_names else None,
         "jumps": np.zeros((n_inst, n_steps, n // 3)) if program.diagnostic_names else None,
+        "worst_row": np.zeros(n_inst, np.int32),
     }
+    itv = None if instance_targets is None else np.ascontiguousarray(instance_targets, dtype=np.float64)
     par = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
     settings = dict(step_tol=1e-6, coarse_tol=1e-3, fine_tol=1e-4, residual_tol=1e-3, mu_init=1e-3, max_iter=50,
                     use_predictor=3)
     settings.update(cfg)
     c = SolverCfg(**settings)
     hdr = np.ascontiguousarray(program.hdr)
-    io = BatchIO.of(hardpoints=hp, params=par, target_values=tv, **out)
+    io = BatchIO.of(hardpoints=hp, params=par, target_values=tv, instance_targets=itv, **out)
     rc = emu_lib().okin_emu_sweep(
         hdr.ctypes.data, program.iblob.ctypes.data, program.fblob.ctypes.data, n_inst, n_steps,
         ctypes.byref(c), ctypes.byref(io))

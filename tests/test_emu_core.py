@@ -110,41 +110,71 @@ def test_perturbed_instances_match_reference(batch, case):
     assert diff <= POS_TOL_MM, diff
 
 
-def check_failure_flags(solve, cases: dict) -> None:
-    """Flag contract against the reference (shared with the GPU test):
-
-    * reference ok                      -> ok, every step;
-    * reference residual rejection (2)  -> failed, first failed step within one sweep increment;
-    * reference "failed to converge" (1) is MINPACK exhausting 100*n evaluations on the
-      rank-deficient system (hard part 3).  The target may still be
-      feasible: then the device solve may succeed, and the returned state must verify as a root
-      of the reference's own residuals (checked with the oracle); otherwise it must fail within
-      one sweep increment.  The failure class itself is best-effort.
-    """
+def reference_root_checker(sus, sweep, prog, hardpoints=None):
+    """``is_root(positions_row, values_column)``: max|r| of the *reference's* residuals (oracle
+    restatement, pinned to the reference's rows by tests/test_oracle_golden.py) at a device state."""
     from oracle.solve import ResidualComputer, design_setup, target_bases
+    problem, _ = oracle_problem(sus, sweep)
+    authored = authored_positions(sus) if hardpoints is None else hardpoints
+    pos0, consts = design_setup(problem, authored)
+    rc = ResidualComputer(problem, pos0, consts)
+    bases = target_bases(problem, pos0)
 
+    def max_residual(row, column):
+        x = np.concatenate([row[prog.out_keys.index(k)] for k in problem.free_order])
+        return float(np.abs(rc.compute(x, bases + column)).max())
+    return max_residual
+
+
+def check_flag_contract(label, ref_status, ref_failed, dev_status, dev_failed, positions, values, max_residual,
+                        tol=1e-3) -> str:
+    """The flag contract against the reference, one sweep (shared by the CPU and GPU tests and by
+    tools/failure_confusion.py).  Returns the cell of the confusion matrix the sweep falls in.
+
+    * reference ok (0)                    -> device ok on every step;
+    * reference residual rejection (2)    -> device residual rejection at the SAME step (solver.py:735-747:
+      the optimiser converged to a least-squares compromise of an unreachable target);
+    * reference "failed to converge" (1)  is MINPACK running out of its 100*n evaluation budget while it
+      still crawls towards a root (measured: 1500-1800 evaluations, cost still falling, tests/golden/
+      generate_batches.py) -- a statement about the optimiser, not about the mechanism.  The device
+      iteration pins the rank-deficient point-on-line rows and converges there in a handful of steps.
+      Contract: the device never fails EARLIER than the reference, and every state it accepts from the
+      reference's failed step on is verified to be a root of the reference's own residual function
+      (max|r| <= the acceptance tolerance), i.e. a state the reference would have accepted had MINPACK
+      reached it.
+    """
+    n_steps = values.shape[1]
+    if ref_status == 0:
+        assert dev_status == 0 and dev_failed == -1, (label, dev_status, dev_failed)
+        return "ok/ok"
+    accepted_to = n_steps if dev_status == 0 else dev_failed
+    assert np.isfinite(positions[:accepted_to]).all() and np.isnan(positions[accepted_to:]).all(), label
+    if ref_status == 2:
+        assert (dev_status, dev_failed) == (2, ref_failed), (label, dev_status, dev_failed, ref_failed)
+        return "rejected/rejected same step"
+    assert ref_status == 1, (label, ref_status)
+    assert accepted_to >= ref_failed, (label, "device failed earlier than the reference", dev_failed, ref_failed)
+    for s in range(ref_failed, accepted_to):
+        r = max_residual(positions[s], values[:, s])
+        assert r <= tol, (label, s, r)
+    if dev_status == 0:
+        return "not converged/ok (all extra states verified roots)"
+    kind = "not converged" if dev_status == 1 else "rejected"
+    return f"not converged/{kind} " + ("same step" if dev_failed == ref_failed else
+                                        f"+{dev_failed - ref_failed} steps (extra states verified roots)")
+
+
+def check_failure_flags(solve, cases: dict) -> dict:
+    cells = {}
     for label, rec in cases.items():
         sus, sweep = build_case(rec)
         prog, values = _program(sus, sweep)
         out = solve(prog, _nominal(sus, prog), values)
-        ok = out["status"][0] == 0
-        failed = int(out["failed_step"][0])
-        if rec["status"] == 0:
-            assert ok, label
-            continue
-        if not ok:
-            assert abs(failed - rec["failed_step"]) <= 1, (label, failed, rec["failed_step"])
-            assert np.isnan(out["positions"][0, failed:]).all()
-            assert np.isfinite(out["positions"][0, :failed]).all()
-            continue
-        assert rec["status"] == 1, label  # a residual rejection must never be accepted
-        problem, _ = oracle_problem(sus, sweep)
-        pos0, consts = design_setup(problem, authored_positions(sus))
-        rc = ResidualComputer(problem, pos0, consts)
-        bases = target_bases(problem, pos0)
-        for s in range(rec["failed_step"], values.shape[1]):
-            x = np.concatenate([out["positions"][0, s, prog.out_keys.index(k)] for k in problem.free_order])
-            assert np.abs(rc.compute(x, bases + values[:, s])).max() <= 1e-3, (label, s)
+        cell = check_flag_contract(label, rec["status"], rec["failed_step"], int(out["status"][0]),
+                                   int(out["failed_step"][0]), out["positions"][0], values,
+                                   reference_root_checker(sus, sweep, prog))
+        cells[label] = cell
+    return cells
 
 
 def test_failure_flags_match_reference():

@@ -33,3 +33,38 @@ def test_result_files(emu_device, tmp_path):
 @pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll"])
 def test_analyze_sweep(emu_device, case):
     G.test_analyze_sweep_matches_reference(case)
+
+
+@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll"])
+def test_metrics_of_default_tolerance_states(emu_device, case):
+    """States of reference accuracy (its default ftol = 1e-5 run, up to 2.3e-5 mm from the tight
+    solution) are valid inputs of the B2/B3 facade: nothing raises, and the metric rows agree with
+    the reference's rows for the tight states to that accuracy."""
+    import numpy as np
+    from helpers import build_case, key_from_name, load_golden
+    from open_kinematics_b200.core.metrics.main import AxleMetricRows
+    from open_kinematics_b200.core.primitives.geometry import Point3
+    from open_kinematics_b200.core.state import SuspensionState
+    from open_kinematics_b200.core.sweep import compute_sweep_metrics
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    keys = [key_from_name(n) for n in meta["point_keys"]]
+    free = set(sus.initial_state().free_points)
+    states = [SuspensionState(positions={k: Point3(arr["positions_default"][s, i]) for i, k in enumerate(keys)},
+                              free_points=set(free)) for s in range(sweep.n_steps)]
+    assert np.abs(arr["positions_default"] - arr["positions_tight"]).max() > 5e-6   # the case is meaningful
+    result = compute_sweep_metrics(sus, sweep, states)
+    flat = [row.flat_row() if isinstance(row, AxleMetricRows) else row for row in result.rows]
+    got = np.array([[np.nan if r[k] is None else r[k] for k in meta["metric_names"]] for r in flat])
+    ref = arr["metrics"]
+    assert (np.isnan(got) == np.isnan(ref)).all()
+    scale = np.maximum(1.0, np.abs(ref))
+    assert np.nanmax(np.abs(got - ref) / scale) <= 1e-4
+
+
+def test_per_instance_target_tables(emu_device):
+    G.test_per_instance_target_tables()
+
+
+def test_worst_residual_row_is_reported(emu_device):
+    G.test_worst_residual_row_is_reported()

@@ -587,3 +587,147 @@ def test_optional_outputs_are_independent():
         assert (full["diagnostics"][:, :, 0] == 0).all()
     finally:
         topo.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Round 2: launch-shape robustness, in-process multi-device split, page-locked result reuse,
+# per-instance target tables, worst-residual-row reporting, tuned layout on the device.
+# ---------------------------------------------------------------------------------------------
+def _solver(case, **kw):
+    from open_kinematics_b200.core.sweep import BatchSolver
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    return BatchSolver(sus, sweep, **kw), meta, arr
+
+
+def _perturbed(solver, n, sigma=0.5, seed=5):
+    rng = np.random.default_rng(seed)
+    nominal = solver.nominal_hardpoints()
+    return nominal[None, :] + rng.normal(0.0, sigma, size=(n, nominal.size)) * (nominal != 0)[None, :]
+
+
+def test_interleaved_topologies_keep_their_launch_shape():
+    """Two live topologies with very different shared-memory sizes used alternately (the dynamic
+    shared-memory attribute belongs to the kernel function, not to a topology: round-1 ADVICE)."""
+    big, _, _ = _solver("c3_rocker_ubar_coilover_roll")
+    small, _, _ = _solver("c1_dw_corner_bump")
+    try:
+        hb, hs = _perturbed(big, 600), _perturbed(small, 600)
+        first = big.solve(hb)
+        s1 = small.solve(hs)
+        again = big.solve(hb)
+        s2 = small.solve(hs, want_metrics=True)      # full instantiation of the small one
+        third = big.solve(hb, want_metrics=True)
+        assert (first.status == 0).all() and (s1.status == 0).all()
+        assert np.array_equal(first.positions, again.positions)
+        assert np.array_equal(s1.positions, s2.positions)
+        assert np.abs(first.positions - third.positions).max() <= 1e-9
+    finally:
+        big.close()
+        small.close()
+
+
+@pytest.mark.parametrize("case", ["c3_rocker_ubar_coilover_roll", "c1_dw_corner_bump", "c4_tbar_heave_shim_roll"])
+def test_tuned_layout_matches_reference_on_device(case):
+    """The configuration bench.py runs (tune_layout=True) against the reference's tight run."""
+    solver, meta, arr = _solver(case, tune_layout=True)
+    try:
+        res = solver.solve(solver.nominal_hardpoints()[None, :], want_tangents=True, want_metrics=True)
+        assert res.status[0] == 0
+        prog = solver.program
+        order = [prog.out_keys.index(key_from_name(n)) for n in meta["point_keys"]]
+        assert np.abs(res.positions[0][:, order] - arr["positions_tight"]).max() <= POS_TOL_MM
+        assert np.abs(res.tangents[0] - arr["tangents"]).max() <= 1e-7 * max(1.0, np.abs(arr["tangents"]).max())
+        from test_emu_metrics import check_metrics
+        check_metrics(prog.metric_names, res.metrics[0], arr["metrics"])
+    finally:
+        solver.close()
+
+
+def test_multi_device_split_matches_single_device():
+    """okin_solve_batch(device_ids, n > 1): instance ranges per device, one host thread each; the
+    result is bit-identical to the single-device call (needs >= 2 visible devices)."""
+    from open_kinematics_b200 import _lib
+    n_dev = _lib.device_count()
+    if n_dev < 2:
+        pytest.skip("one visible device")
+    solver, _, _ = _solver("c3_rocker_ubar_coilover_roll")
+    try:
+        hp = _perturbed(solver, 70001)               # odd count: uneven shards, several chunks per device
+        one = solver.solve(hp, devices=[0])
+        for devices in ([0, 1], list(range(n_dev)), [n_dev - 1, 0]):
+            many = solver.solve(hp, devices=devices, pinned=True)
+            assert np.array_equal(one.status, many.status) and np.array_equal(one.failed_step, many.failed_step)
+            assert np.array_equal(one.positions, many.positions, equal_nan=True)
+            assert np.array_equal(one.nfev, many.nfev)
+        with pytest.raises(RuntimeError, match="twice"):
+            solver.solve(hp[:10], devices=[0, 0])
+    finally:
+        solver.close()
+
+
+def test_pinned_result_is_reused():
+    solver, _, _ = _solver("c1_dw_corner_bump")
+    try:
+        a = _perturbed(solver, 5000, seed=1)
+        b = _perturbed(solver, 5000, seed=2)
+        hp = solver.pinned_hardpoints(5000)
+        hp[:] = a
+        first = solver.solve(hp, pinned=True, want_metrics=True)
+        plain = solver.solve(a, want_metrics=True)
+        assert np.array_equal(first.positions, plain.positions) and np.array_equal(first.metrics, plain.metrics, equal_nan=True)
+        keep = first.positions
+        hp[:] = b
+        second = solver.solve(hp, out=first, want_metrics=True)
+        assert second.positions is keep and second.metrics is first.metrics     # overwritten in place
+        assert np.array_equal(second.positions, solver.solve(b).positions)
+    finally:
+        solver.close()
+
+
+def test_per_instance_target_tables():
+    """instance_targets[n_instances][n_targets][n_steps] replaces the shared table (Monte Carlo over
+    the sweep itself): each instance must equal a plain solve with its own table."""
+    from open_kinematics_b200.core.sweep import BatchSolver
+    solver, meta, arr = _solver("c1_dw_corner_bump_steer")
+    try:
+        values = solver.values
+        scales = np.array([1.0, 0.5, -0.25, 0.8])
+        tables = values[None, :, :] * scales[:, None, None]
+        hp = np.repeat(solver.nominal_hardpoints()[None, :], len(scales), axis=0)
+        res = solver.solve(hp, instance_targets=tables, want_tangents=True)
+        assert (res.status == 0).all()
+        for i, sc in enumerate(scales):
+            solver.values = values * sc
+            single = solver.solve(hp[:1], want_tangents=True)
+            assert np.array_equal(single.positions[0], res.positions[i])
+            assert np.array_equal(single.tangents[0], res.tangents[i])
+        solver.values = values
+        if type(solver.topology).__name__ == "DeviceTopology":      # shape validation of the ctypes binding
+            with pytest.raises(ValueError, match="instance_targets"):
+                solver.solve(hp, instance_targets=tables[:, :, :-1])
+    finally:
+        solver.close()
+
+
+def test_worst_residual_row_is_reported():
+    """The rejection message names the same row as the reference (solver.py:640-651, :738-747)."""
+    from open_kinematics_b200.core.sweep import BatchSolver, solve_sweep
+    rec = json.load(open(os.path.join(GOLDEN, "failures.json")))["dw_corner_rocker_bump_-60_+80"]
+    sus, sweep = build_case(rec)
+    with pytest.raises(RuntimeError) as err:
+        solve_sweep(sus, sweep)
+    ref_row = rec["message"].split("Worst residual row: ")[1].split(". The mechanism")[0]
+    assert f"Worst residual row: {ref_row}." in str(err.value), (str(err.value), ref_row)
+    # batch form: the row index maps through program.row_source
+    solver = BatchSolver(sus, sweep)
+    try:
+        res = solver.solve(solver.nominal_hardpoints()[None, :], want_worst_row=True)
+        assert res.status[0] == 2 and res.worst_row[0] >= 0
+        _, constraints = sus.structure()
+        assert res.describe_worst_residual(0, constraints, solver.heads) == ref_row
+        ok = solver.solve(solver.nominal_hardpoints()[None, :], want_worst_row=True,
+                          instance_targets=solver.values[None, :, :] * 0.5)
+        assert ok.status[0] == 0 and ok.worst_row[0] == -1
+    finally:
+        solver.close()
