@@ -801,6 +801,7 @@ def compile_topology(
         "OKIN_S_DESIGN_PT": design_pts, "OKIN_S_MCORNER": mcorners, "OKIN_S_MOP": mops, "OKIN_S_MAXLE": maxle,
         "OKIN_S_SHIM": shim_recs, "OKIN_S_SHIM_PTS": shim_pts,
         "OKIN_S_FREE_OUT": free_out, "OKIN_S_DGOP": dprog.ops if dprog else [],
+        "OKIN_S_ELIM_OUT": [free_out[c] for c in elim_col],
     }
     isecs["OKIN_S_ROW_HOT"] = row_hot
     # Cold sections (setup, outputs requested per state, metrics, diagnostics) go last: the kernel
@@ -844,6 +845,7 @@ def compile_topology(
         "OKIN_H_NMC": len(mcorners), "OKIN_H_NMOP": len(mops), "OKIN_H_NMAXLE": len(maxle), "OKIN_H_NDSN": ndsn,
         "OKIN_H_NSHIM": len(shim_recs), "OKIN_H_NPARAM": len(param_default),
         "OKIN_H_NDROW": len(fast_rows), "OKIN_H_NGROW": len(row_order),
+        "OKIN_H_FREE_ALL_OUT": int(all(v >= 0 for v in free_out)),
         "OKIN_H_NHOT": n_hot, "OKIN_H_NDIAG": len(dprog.names) if dprog else 0, "OKIN_H_NDGOP": len(dprog.ops) if dprog else 0,
         **layout,
     }

@@ -1720,6 +1720,10 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   const int32_t* out_point = OKIN_SHARED(okin_sec(pr, OKIN_S_OUT_POINT));
   const int32_t* ecol = okin_sec(pr, OKIN_S_ELIM_COL);
   const int32_t* elim_point = OKIN_SHARED(okin_sec(pr, OKIN_S_ELIM_POINT));
+  const int32_t* elim_out = okin_sec(pr, OKIN_S_ELIM_OUT);
+  // The last accepted solution (for the retry from the plain warm start) is the position row just
+  // written when every free point is exported; otherwise it is kept in the global backup row.
+  const bool from_rows = out.positions && hdr[OKIN_H_FREE_ALL_OUT];
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
   // outputs only the full instantiation knows about
@@ -1783,8 +1787,11 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       // is restored and the step is solved again from the plain warm start before it is flagged.
       for (int attempt = 0; attempt < 2; ++attempt) {
         if (attempt == 1) {
+          const double* prev = from_rows ? out.positions + (size_t)(s - 1) * 3 * nout : out.backup;
           OKIN_PHASE_BEGIN
-          for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3] = out.backup[u];
+          for (int u = lane; u < n; u += 32)
+            pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3] =
+                from_rows ? prev[3 * OKIN_LDG(elim_out + u / 3) + u % 3] : prev[u];
           OKIN_PHASE_END
           history = 0;
         }
@@ -1839,7 +1846,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       if (dst)
         for (int t = lane; t < 3 * nout; t += 32)
           dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
-      if (ok && cfg.use_predictor)   // last accepted solution (only a predicted start can be retried)
+      if (ok && cfg.use_predictor && !from_rows)   // last accepted solution (only a predicted start is retried)
         for (int u = lane; u < n; u += 32) out.backup[u] = pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3];
       OKIN_PHASE_END
     }

@@ -127,6 +127,7 @@ enum okin_hdr_slot {
                    // iteration; the kernel keeps them in shared memory, the rest stays in global memory)
   OKIN_H_NDIAG,    // diagnostic columns per state (OKIN_DIAG_BASE + topology columns), 0 = no program
   OKIN_H_NDGOP,    // topology diagnostic ops
+  OKIN_H_FREE_ALL_OUT,  // 1 when every free point is an output point (ELIM_OUT has no -1)
   OKIN_H_SEC0 = 64,                      // room for 64 scalar slots,
   OKIN_H_FSEC0 = 64 + 2 * 64,            // 64 int32 sections
   OKIN_HDR_SIZE = 64 + 2 * 64 + 2 * 8    // and 8 double sections
@@ -186,6 +187,7 @@ enum okin_isec {
   OKIN_S_FREE_OUT,       // [NF] output slot of free point k (reference column order), -1 = not exported
   OKIN_S_DGOP,           // [NDGOP][OKIN_DGOP_STRIDE] topology diagnostic ops
   OKIN_S_ELIM_COL,       // [NF] elimination position -> reference column block (sorted free-point order)
+  OKIN_S_ELIM_OUT,       // [NF] elimination position -> output slot of that free point, -1 = not exported
   OKIN_S_COUNT
 };
 #define OKIN_ASM_DIAG 0x40000000

@@ -75,11 +75,18 @@ _FAMILY = {
 }
 
 
-def oracle_problem(suspension, sweep_config, from_design: bool = True) -> OracleProblem:
-    """Describe a built product model to the oracle (declarations only; no product arithmetic)."""
-    state = suspension.initial_state()
+def oracle_problem(suspension, sweep_config, from_design: bool = True, structure_only: bool = False) -> OracleProblem:
+    """Describe a built product model to the oracle (declarations only; no product arithmetic).
+    ``structure_only``: take points and constraint declarations from ``structure()`` (authored pose, no
+    camber-shim pre-solve, which needs the device); every design constant must then come from
+    ``design_setup`` (``from_design``)."""
+    if structure_only:
+        assert from_design
+        state, constraints = suspension.structure()
+    else:
+        state, constraints = suspension.initial_state(), suspension.constraints()
     cons = []
-    for c in suspension.constraints():
+    for c in constraints:
         fam = _FAMILY[type(c)]
         if fam == "distance":
             consts = [c.target_distance]

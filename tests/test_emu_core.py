@@ -110,12 +110,15 @@ def test_perturbed_instances_match_reference(batch, case):
     assert diff <= POS_TOL_MM, diff
 
 
-def reference_root_checker(sus, sweep, prog, hardpoints=None):
-    """``is_root(positions_row, values_column)``: max|r| of the *reference's* residuals (oracle
-    restatement, pinned to the reference's rows by tests/test_oracle_golden.py) at a device state."""
+def reference_root_checker(sus, sweep, prog, hardpoints=None, setup_pose=None):
+    """``max_residual(positions_row, values_column)``: max|r| of the *reference's* residuals (oracle
+    restatement, pinned to the reference's rows by tests/test_oracle_golden.py) at a device state.
+    ``setup_pose``: for camber-shimmed models, the setup pose of the input points ({key: xyz}, the
+    solver's own ``design`` output, itself checked against the reference's shim solve in
+    test_camber_shim_presolve_matches_reference); the design constants are taken there."""
     from oracle.solve import ResidualComputer, design_setup, target_bases
-    problem, _ = oracle_problem(sus, sweep)
-    authored = authored_positions(sus) if hardpoints is None else hardpoints
+    problem, _ = oracle_problem(sus, sweep, structure_only=setup_pose is not None)
+    authored = setup_pose if setup_pose is not None else (authored_positions(sus) if hardpoints is None else hardpoints)
     pos0, consts = design_setup(problem, authored)
     rc = ResidualComputer(problem, pos0, consts)
     bases = target_bases(problem, pos0)

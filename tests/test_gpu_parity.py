@@ -620,7 +620,7 @@ def test_interleaved_topologies_keep_their_launch_shape():
         third = big.solve(hb, want_metrics=True)
         assert (first.status == 0).all() and (s1.status == 0).all()
         assert np.array_equal(first.positions, again.positions)
-        assert np.array_equal(s1.positions, s2.positions)
+        assert np.abs(s1.positions - s2.positions).max() <= 1e-9      # lean vs full instantiation
         assert np.abs(first.positions - third.positions).max() <= 1e-9
     finally:
         big.close()
