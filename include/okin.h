@@ -44,7 +44,9 @@
  *                                                    the Cholesky factor (estimates from inside)
  *   metrics_out     [n_instances][n_steps][n_metrics]  state / mechanism / derivative metric columns in
  *                                                    the reference's flat export order; NaN where the
- *                                                    reference yields None
+ *                                                    reference yields None, +inf in a derivative column whose
+ *                                                    driver tangents tie (the reference raises there,
+ *                                                    metrics/derivatives.py:299-304)
  *   design_out      [n_instances][n_out_points*3]    design (setup) pose after the camber-shim
  *                                                    pre-solve and derived points
  *   diagnostics_out [n_instances][n_steps][n_diagnostics]  sweep diagnostics as per-state reductions
@@ -114,7 +116,9 @@ typedef struct okin_solver_cfg {
   double residual_tol;   /* default 1e-3 */
   double mu_init;        /* first Marquardt damping after a rejected step; default 1e-3 */
   int32_t max_iter;      /* factorisations per step; default 50 */
-  int32_t use_predictor; /* continuation predictor order 0..3 (Adams-Bashforth on the tangents); default 3 */
+  int32_t use_predictor; /* highest continuation predictor order, 0 = plain warm start; default 4.  Full-output
+                            kernels: Adams-Bashforth on the tangents (orders 1..3); lean kernels: backward-
+                            difference extrapolation of the solution history (orders 1..4) */
 } okin_solver_cfg;
 
 typedef struct okin_topology_info {

@@ -46,12 +46,17 @@ def flatten_metric_rows(metrics: MetricRow, corner_metrics: Mapping) -> MetricRo
 
 def rows_from_columns(values: np.ndarray, locations: list, is_axle: bool, with_derivatives: bool = True):
     """One device metric record (``values[n_metrics]``, NaN == None) -> the reference's row shape.
-    ``locations[c] = (Side | None, key)`` as recorded by the metric-program builder."""
+    ``locations[c] = (Side | None, key)`` as recorded by the metric-program builder.  A derivative
+    column holding +inf is the device's mark for tied driver tangents: the reference raises there
+    (metrics/derivatives.py:299-304), and so does this."""
     axle_row: MetricRow = OrderedDict()
     corner_rows = {Side.LEFT: OrderedDict(), Side.RIGHT: OrderedDict()} if is_axle else {}
     for value, (side, key) in zip(values, locations):
         if not with_derivatives and key.startswith("deriv_"):
             continue
+        if key.startswith("deriv_") and np.isposinf(value):
+            raise ValueError(f"Ambiguous derivative driver for column '{key}': "
+                             "multiple matching tangents have equal strength")
         item = None if np.isnan(value) else float(value)
         (corner_rows[side] if (is_axle and side is not None) else axle_row)[key] = item
     return AxleMetricRows(axle=axle_row, corners=corner_rows) if is_axle else axle_row

@@ -300,6 +300,8 @@ def compile_topology(
     use); ``False`` bakes the explicit constants of the given constraint objects
     (the single-instance ``solve_suspension_sweep`` boundary).
     """
+    # gather lists padded to a multiple of list_pad (kernel experiments: csrc built with OKIN_PAIR_LOOPS=1)
+    list_pad = int(os.environ.get("OKIN_LIST_PAD", "1"))
     positions = initial_state.positions
     manager = DerivedPointsManager(derived_spec)
     derived_keys = list(manager.update_order)
@@ -557,9 +559,13 @@ def compile_topology(
                 contrib.setdefault((pa, pb), []).append(word)
     tasks = sorted(block_id.items(), key=lambda kv: (-len(contrib.get(kv[0], [])), kv[1]))
     asm_ptr, asm_task, asm_con = [0], [], []
+    NULL_RG = "NULL_RG"           # rg-relative offset of the zero block, known once the layout is
     for (i, j), b in tasks:       # heaviest first: lanes take tasks round-robin
         asm_task.append(b | (D["OKIN_ASM_DIAG"] if i == j else 0))
-        asm_con.extend(contrib.get((i, j), []))
+        words = contrib.get((i, j), [])
+        asm_con.extend(words)
+        if list_pad == 2 and len(words) % 2:
+            asm_con.append(NULL_RG)
         asm_ptr.append(len(asm_con))
     NAT = len(asm_task)
 
@@ -572,7 +578,10 @@ def compile_topology(
             per_block.setdefault(pos_of[cblk], []).append(
                 (off_e << 16) | row_index[id(row)] | (D["OKIN_CON_NEG"] if neg else 0))
     for j in range(NF):
-        g_con.extend(per_block.get(j, []))
+        words = per_block.get(j, [])
+        g_con.extend(words)
+        if list_pad == 2 and len(words) % 2:
+            g_con.append(NULL_RG)
         g_ptr.append(len(g_con))
 
     # ---- left-looking update lists, scale tasks -------------------------------
@@ -588,29 +597,44 @@ def compile_topology(
     lev_cols = [[j for j in range(NF) if level[j] == lv] for lv in range(NLEV)]
     lev_upd, upd_dst, upd_ptr, upd_con = [0], [], [0], []
     lev_scl, scl = [0], []
-    LB, VEC = "LB", "VEC"      # symbolic bases, resolved once the layout is known
+    lev_upd_mid, lev_scl_mid = [], []   # end of the tasks a solve without tangents needs, per level
+    LB, VEC, ZERO = "LB", "VEC", "ZERO"      # symbolic bases, resolved once the layout is known
+    NULL_UPD = ((ZERO, 0), (ZERO, 0))        # a = 0: contributes nothing (pads a list to even length)
+
+    def add_update(dst, cons):
+        upd_dst.append(dst)
+        upd_con.extend(cons)
+        if list_pad == 2 and len(cons) % 2:
+            upd_con.append(NULL_UPD)
+        upd_ptr.append(len(upd_con))
+
     for lv in range(NLEV):
-        for j in lev_cols[lv]:
-            for i in [j] + struct[j]:
-                ks = [k for k in cols_with[j] if i == j or i in struct[k]]
-                if not ks:
-                    continue
-                for r in range(3):
-                    upd_dst.append((LB, boff(i, j) + 3 * r))
-                    for k in ks:
-                        upd_con.append(((LB, boff(i, k) + 3 * r), (LB, boff(j, k))))
-                    upd_ptr.append(len(upd_con))
-            if cols_with[j]:
-                for rhs in range(1 + len(targets)):     # carried right-hand sides: step + tangents
-                    upd_dst.append((VEC, rhs * 3 * NF + 3 * j))
-                    for k in cols_with[j]:
-                        upd_con.append(((VEC, rhs * 3 * NF + 3 * k), (LB, boff(j, k))))
-                    upd_ptr.append(len(upd_con))
-            for i in struct[j]:
-                for r in range(3):
-                    scl.append(((LB, boff(j, j)), (LB, boff(i, j) + 3 * r)))
-            for rhs in range(1 + len(targets)):
-                scl.append(((LB, boff(j, j)), (VEC, rhs * 3 * NF + 3 * j)))
+        # block rows and the step right-hand side first, the tangent right-hand sides last: a solve that
+        # does not carry tangents (lean kernel) stops at the "mid" pointer of the level
+        for tangent_pass in (False, True):
+            for j in lev_cols[lv]:
+                if not tangent_pass:
+                    for i in [j] + struct[j]:
+                        ks = [k for k in cols_with[j] if i == j or i in struct[k]]
+                        if not ks:
+                            continue
+                        for r in range(3):
+                            add_update((LB, boff(i, j) + 3 * r),
+                                       [((LB, boff(i, k) + 3 * r), (LB, boff(j, k))) for k in ks])
+                if cols_with[j]:
+                    for rhs in (range(1, 1 + len(targets)) if tangent_pass else (0,)):
+                        # carried right-hand sides: step (0) and tangents (1..NT)
+                        add_update((VEC, rhs * 3 * NF + 3 * j),
+                                   [((VEC, rhs * 3 * NF + 3 * k), (LB, boff(j, k))) for k in cols_with[j]])
+                if not tangent_pass:
+                    for i in struct[j]:
+                        for r in range(3):
+                            scl.append(((LB, boff(j, j)), (LB, boff(i, j) + 3 * r)))
+                for rhs in (range(1, 1 + len(targets)) if tangent_pass else (0,)):
+                    scl.append(((LB, boff(j, j)), (VEC, rhs * 3 * NF + 3 * j)))
+            if not tangent_pass:
+                lev_upd_mid.append(len(upd_dst))
+                lev_scl_mid.append(len(scl))
         lev_upd.append(len(upd_dst))
         lev_scl.append(len(scl))
 
@@ -618,9 +642,13 @@ def compile_topology(
     for j in range(NF):
         for k in cols_with[j]:
             fw_con.append(((LB, boff(j, k)), 3 * k))
+        if list_pad == 2 and len(cols_with[j]) % 2:
+            fw_con.append(((ZERO, 0), 0))          # null block: pads the list to even length
         fw_ptr.append(len(fw_con))
         for i in struct[j]:
             bw_con.append(((LB, boff(i, j)), 3 * i))
+        if list_pad == 2 and len(struct[j]) % 2:
+            bw_con.append(((ZERO, 0), 0))
         bw_ptr.append(len(bw_con))
     lev_col_ptr, lev_col = [0], []
     for lv in range(NLEV):
@@ -663,18 +691,29 @@ def compile_topology(
         off += n
         return start
 
+    # What a solve without tangents / metrics needs comes first: the lean kernel instantiation only
+    # reserves the slice up to the end of vec[0] (OKIN_H_SMEM_DOUBLES_LEAN).
     layout = {
         "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
-        "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)), "OKIN_H_OFF_LB": take(9 * NB),
-        "OKIN_H_OFF_VEC": take((1 + NT) * N),
+        "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)),
+        "OKIN_H_OFF_ZERO": take(9),      # a 3x3 block of zeros: operand of the null contributions
+        "OKIN_H_OFF_LB": take(9 * NB),
         "OKIN_H_OFF_RED": take(32), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)),
-        # predictor history: two float32 vectors (stored two per double slot)
-        "OKIN_H_OFF_PPREV": take((N + 1) // 2), "OKIN_H_OFF_PPREV2": take((N + 1) // 2),
         "OKIN_H_OFF_TGT": take(2 * D["OKIN_MAX_TARGETS"]),
+        # extrapolation predictor: previous solution (doubles) + three older increments (float32 pairs)
+        "OKIN_H_OFF_XPREV": take(N), "OKIN_H_OFF_DHIST": take(3 * ((N + 1) // 2)),
+        "OKIN_H_OFF_VEC": take(N),
     }
+    layout["OKIN_H_SMEM_DOUBLES_LEAN"] = off
+    take(NT * N)                         # vec[1..NT]: tangents (contiguous with vec[0])
     if off >= 65536:
         raise ValueError("Per-instance state exceeds the 16-bit shared-memory offset range")
-    base = {LB: layout["OKIN_H_OFF_LB"], VEC: layout["OKIN_H_OFF_VEC"]}
+    base = {LB: layout["OKIN_H_OFF_LB"], VEC: layout["OKIN_H_OFF_VEC"], ZERO: layout["OKIN_H_OFF_ZERO"]}
+    null_rg = layout["OKIN_H_OFF_ZERO"] - layout["OKIN_H_OFF_RG"]
+    if not 0 <= null_rg < 32768:
+        raise ValueError("Zero block out of the 15-bit row-gradient offset range")
+    asm_con = [((null_rg << 16) | null_rg) if w == NULL_RG else w for w in asm_con]
+    g_con = [(null_rg << 16) if w == NULL_RG else w for w in g_con]
 
     # ---- optional: bank-conflict-aware placement of the factor blocks (core/layout_tuning.py) ------
     slot = list(range(NB))
@@ -684,7 +723,7 @@ def compile_topology(
         trace = AccessTrace(base[LB])
 
         def ref(r):
-            return ("LB", r[1]) if r[0] == LB else ("ABS", base[VEC] + r[1])
+            return ("LB", r[1]) if r[0] == LB else ("ABS", base[r[0]] + r[1])
 
         for lv in range(NLEV):
             for r0 in range(lev_upd[lv], lev_upd[lv + 1], 32):          # update rounds
@@ -790,6 +829,7 @@ def compile_topology(
         "OKIN_S_ROW": row_tab, "OKIN_S_DER": der_desc,
         "OKIN_S_ASM_PTR": asm_ptr, "OKIN_S_ASM_TASK": asm_task, "OKIN_S_ASM_CON": asm_con,
         "OKIN_S_G_PTR": g_ptr, "OKIN_S_G_CON": g_con,
+        "OKIN_S_LEV_UPD_MID": lev_upd_mid, "OKIN_S_LEV_SCL_MID": lev_scl_mid,
         "OKIN_S_LEV_UPD": lev_upd, "OKIN_S_UPD_DST": upd_dst, "OKIN_S_UPD_PTR": upd_ptr, "OKIN_S_UPD_CON": upd_con,
         "OKIN_S_LEV_SCL": lev_scl, "OKIN_S_SCL": scl,
         "OKIN_S_LEV_COL_PTR": lev_col_ptr, "OKIN_S_LEV_COL": lev_col,
@@ -819,6 +859,8 @@ def compile_topology(
         s = D[name]
         hdr[D["OKIN_H_SEC0"] + 2 * s] = cursor
         hdr[D["OKIN_H_SEC0"] + 2 * s + 1] = arr.size
+        if arr.size % 2:                 # sections start on even words: contribution pairs are read 64 bits wide
+            arr = np.concatenate([arr, np.zeros(1, np.int64)])
         chunks.append((arr & 0xFFFFFFFF).astype(np.uint32).view(np.int32))   # flag bit 31 wraps to sign
         cursor += arr.size
     iblob = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <mutex>
@@ -26,8 +27,13 @@
 #include "../../include/okin.h"
 #include "okin_core.cuh"
 
-#define OKIN_MAX_THREADS 512   // 16 warps: the most one CTA may hold (register cap 128 per thread)
+#define OKIN_MAX_THREADS 512   // 16 warps: the most a full-output CTA may hold (register cap 128 per thread)
 #define OKIN_REGS_PER_THREAD 128
+// The lean instantiation (positions + solver statistics only) owns a shorter slice; with more warps
+// per CTA its register cap drops accordingly (65536 / threads).
+#ifndef OKIN_LEAN_MAX_THREADS
+#define OKIN_LEAN_MAX_THREADS 512
+#endif
 #define OKIN_MAX_DEVICES 16
 #define OKIN_PIPE_SLOTS 3        // streams / workspace slots of the host-buffer pipeline
 #define OKIN_PIPE_CHUNK 32768   // instances per pipelined chunk
@@ -59,9 +65,8 @@ struct DeviceCopy {
   int32_t* ib = nullptr;
   double* fb = nullptr;
   int num_sms = 0;
-  int ctas_per_sm = 0;
-  int warps_per_cta = 0;
-  int smem_bytes = 0;
+  // launch shape per instantiation family: [0] lean (short slice), [1] full outputs
+  struct Shape { int ctas_per_sm = 0, warps_per_cta = 0, smem_bytes = 0; } shape[2];
   int table_doubles = 0;
   int smem_optin = 0;
   // grow-only workspace for the host-buffer entry point
@@ -85,10 +90,10 @@ struct okin_topology {
 // Register cap 128 = 65536 / 512: up to 16 resident warps per SM in any CTA shape the host picks
 // (only the once-per-instance shim pre-solve spills at that cap).
 template <bool FULL, bool SHIM>
-__global__ void __launch_bounds__(OKIN_MAX_THREADS, 1)
+__global__ void __launch_bounds__(FULL ? OKIN_MAX_THREADS : OKIN_LEAN_MAX_THREADS, 1)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, OkinSolverCfg cfg, okin_batch_io io, int n_iblob,
-                  int table_doubles, double* __restrict__ backup) {
+                  int table_doubles) {
   // [section pointers][header][hot tables][one state slice per warp]
   const int32_t** sec = reinterpret_cast<const int32_t**>(okin_smem);
   int32_t* shdr = reinterpret_cast<int32_t*>(okin_smem + OKIN_S_COUNT);
@@ -102,7 +107,7 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
   OkinProgram pr{shdr, tab, fb, ib, sec};
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
-  double* sm = okin_smem + table_doubles + (size_t)warp * hdr[OKIN_H_SMEM_DOUBLES];
+  double* sm = okin_smem + table_doubles + (size_t)warp * hdr[FULL ? OKIN_H_SMEM_DOUBLES : OKIN_H_SMEM_DOUBLES_LEAN];
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
   const long long stride = (long long)gridDim.x * warps_per_cta;
   // The trip count is uniform over the CTA and every round starts with a CTA barrier: the warps
@@ -126,7 +131,6 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
     out.status = io.status + i;
     out.failed_step = io.failed_step + i;
     out.worst_row = io.worst_row ? io.worst_row + i : nullptr;
-    out.backup = backup + ((size_t)blockIdx.x * warps_per_cta + warp) * n;
     okin_sweep<FULL, SHIM>(pr, sm, io.hardpoints + (size_t)i * 3 * nin,
                io.params ? io.params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr,
                io.instance_targets ? io.instance_targets + (size_t)i * nt * n_steps : io.target_values, n_steps,
@@ -189,38 +193,47 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
     d.num_sms = prop.multiProcessorCount;
     d.smem_optin = (int)prop.sharedMemPerBlockOptin;
     // CTA shape: W warps sharing one copy of the tables; pick the W that keeps the most warps resident
-    // (shared memory, the 64K-register file at OKIN_REGS_PER_THREAD, 1 KB per-CTA reservation).
+    // (shared memory, the 64K-register file at the instantiation's register cap, 1 KB per-CTA
+    // reservation).  The lean instantiations own a shorter slice than the full ones.
     d.table_doubles =
         OKIN_S_COUNT + (int)((((size_t)t->hdr[OKIN_H_NHOT] + OKIN_HDR_SIZE) * sizeof(int32_t) + 7) / 8);
     const size_t table_bytes = (size_t)d.table_doubles * 8;
-    const size_t slice_bytes = (size_t)t->hdr[OKIN_H_SMEM_DOUBLES] * sizeof(double);
     const size_t sm_budget = prop.sharedMemPerMultiprocessor;
-    int best_w = 0, best_ctas = 0;
-    for (int w = 1; w <= OKIN_MAX_THREADS / 32; ++w) {
-      const size_t cta_bytes = table_bytes + w * slice_bytes;
-      if (cta_bytes > prop.sharedMemPerBlockOptin) break;
-      int ctas = (int)(sm_budget / (cta_bytes + 1024));
-      ctas = std::min(ctas, (int)(prop.regsPerMultiprocessor / (OKIN_REGS_PER_THREAD * 32 * w)));
-      ctas = std::min(ctas, 32);
-      if (ctas * w > best_w * best_ctas || (ctas * w == best_w * best_ctas && w < best_w && ctas * w > 0)) {
-        best_w = w;
-        best_ctas = ctas;
+    for (int full = 0; full < 2; ++full) {
+      const size_t slice_bytes =
+          (size_t)t->hdr[full ? OKIN_H_SMEM_DOUBLES : OKIN_H_SMEM_DOUBLES_LEAN] * sizeof(double);
+      const int max_threads = full ? OKIN_MAX_THREADS : OKIN_LEAN_MAX_THREADS;
+      const int regs_per_thread = (int)(prop.regsPerMultiprocessor / max_threads) & ~7;
+      int best_w = 0, best_ctas = 0;
+      const char* forced = getenv("OKIN_WARPS_PER_CTA");     // kernel experiments
+      for (int w = 1; w <= max_threads / 32; ++w) {
+        if (forced && atoi(forced) > 0 && w != atoi(forced)) continue;
+        const size_t cta_bytes = table_bytes + w * slice_bytes;
+        if (cta_bytes > prop.sharedMemPerBlockOptin) break;
+        int ctas = (int)(sm_budget / (cta_bytes + 1024));
+        ctas = std::min(ctas, (int)(prop.regsPerMultiprocessor / (regs_per_thread * 32 * w)));
+        ctas = std::min(ctas, 32);
+        if (ctas * w > best_w * best_ctas || (ctas * w == best_w * best_ctas && w < best_w && ctas * w > 0)) {
+          best_w = w;
+          best_ctas = ctas;
+        }
       }
+      if (best_w == 0 || best_ctas == 0)
+        return fail(OKIN_ERR_USAGE, "topology needs more shared memory per CTA than the device offers");
+      DeviceCopy::Shape& sh = d.shape[full];
+      sh.warps_per_cta = best_w;
+      sh.smem_bytes = (int)(table_bytes + best_w * slice_bytes);
+      sh.ctas_per_sm = 1 << 30;
+      const void* kernels[2] = {full ? (const void*)okin_sweep_kernel<true, false> : (const void*)okin_sweep_kernel<false, false>,
+                                full ? (const void*)okin_sweep_kernel<true, true> : (const void*)okin_sweep_kernel<false, true>};
+      for (const void* kernel : kernels) {
+        OKIN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh.smem_bytes));
+        int ctas = 0;
+        OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, best_w * 32, sh.smem_bytes));
+        sh.ctas_per_sm = std::min(sh.ctas_per_sm, ctas);
+      }
+      if (sh.ctas_per_sm < 1) return fail(OKIN_ERR_CUDA, "kernel does not fit on an SM");
     }
-    if (best_w == 0 || best_ctas == 0)
-      return fail(OKIN_ERR_USAGE, "topology needs more shared memory per CTA than the device offers");
-    d.warps_per_cta = best_w;
-    d.smem_bytes = (int)(table_bytes + best_w * slice_bytes);
-    // The four instantiations share one launch shape (same register cap, same shared memory).
-    d.ctas_per_sm = 1 << 30;
-    for (const void* kernel : {(const void*)okin_sweep_kernel<false, false>, (const void*)okin_sweep_kernel<false, true>,
-                               (const void*)okin_sweep_kernel<true, false>, (const void*)okin_sweep_kernel<true, true>}) {
-      OKIN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_bytes));
-      int ctas = 0;
-      OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, best_w * 32, d.smem_bytes));
-      d.ctas_per_sm = std::min(d.ctas_per_sm, ctas);
-    }
-    if (d.ctas_per_sm < 1) return fail(OKIN_ERR_CUDA, "kernel does not fit on an SM");
     for (int k = 0; k < OKIN_PIPE_SLOTS; ++k)
       OKIN_CUDA(cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking));
     d.ready = true;
@@ -234,27 +247,25 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
   if (n_instances == 0) return OKIN_OK;
   OkinSolverCfg c{cfg->step_tol, cfg->coarse_tol, cfg->fine_tol, cfg->residual_tol, cfg->mu_init, cfg->max_iter,
                   cfg->use_predictor};
-  const int w = d->warps_per_cta;
-  const int64_t needed = (n_instances + w - 1) / w;
-  const int64_t resident = (int64_t)d->num_sms * d->ctas_per_sm;
-  const int grid = (int)std::min<int64_t>(needed, resident);
   // lean instantiation when no per-state tangent / metric / diagnostic output is wanted
   const bool full = io.tangents || io.velocities || io.tangent_health || io.metrics || io.diagnostics;
   const bool shim = t->hdr[OKIN_H_NSHIM] > 0;
+  const DeviceCopy::Shape& sh = d->shape[full ? 1 : 0];
+  const int w = sh.warps_per_cta;
+  const int64_t needed = (n_instances + w - 1) / w;
+  const int64_t resident = (int64_t)d->num_sms * sh.ctas_per_sm;
+  const int grid = (int)std::min<int64_t>(needed, resident);
   auto kernel = full ? (shim ? okin_sweep_kernel<true, true> : okin_sweep_kernel<true, false>)
                      : (shim ? okin_sweep_kernel<false, true> : okin_sweep_kernel<false, false>);
-  // The attribute belongs to the kernel function of this device context, not to a topology: another
-  // live topology may have lowered it since ensure_device ran, so it is set before every launch.
-  std::lock_guard<std::mutex> launch_lock(g_launch_mu[d->device]);
-  OKIN_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d->smem_bytes));
-  // Stream-ordered scratch: one row per warp of this launch for its instance's last accepted solution.
-  double* backup = nullptr;
-  OKIN_CUDA(cudaMallocAsync(&backup, (size_t)grid * w * 3 * std::max(t->hdr[OKIN_H_NF], 1) * sizeof(double), stream));
-  kernel<<<grid, w * 32, d->smem_bytes, stream>>>(
-      d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, c, io, (int)t->ib.size(), d->table_doubles, backup);
-  const cudaError_t launch_err = cudaGetLastError();
-  OKIN_CUDA(cudaFreeAsync(backup, stream));
-  OKIN_CUDA(launch_err);
+  {
+    // The attribute belongs to the kernel function of this device context, not to a topology: another
+    // live topology may have lowered it since ensure_device ran, so it is set before every launch.
+    std::lock_guard<std::mutex> launch_lock(g_launch_mu[d->device]);
+    OKIN_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh.smem_bytes));
+    kernel<<<grid, w * 32, sh.smem_bytes, stream>>>(
+        d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, c, io, (int)t->ib.size(), d->table_doubles);
+    OKIN_CUDA(cudaGetLastError());
+  }
   if (io.diagnostics && t->hdr[OKIN_H_NDIAG] && n_steps > 0) {
     // continuity pass over the position rows the sweep kernel just wrote (same stream)
     const int stride = (n_steps - 1) | 1;   // odd: lanes walk their histories on different banks
@@ -498,7 +509,7 @@ int okin_default_cfg(okin_solver_cfg* out) {
   out->residual_tol = 1e-3;
   out->mu_init = 1e-3;
   out->max_iter = 50;
-  out->use_predictor = 3;
+  out->use_predictor = 4;
   return OKIN_OK;
 }
 
@@ -574,11 +585,12 @@ int okin_launch_geometry(okin_topology* t, int32_t device, int64_t n_instances, 
   DeviceCopy* d = nullptr;
   int rc = ensure_device(t, device, &d);
   if (rc) return rc;
-  const int64_t needed = (n_instances + d->warps_per_cta - 1) / d->warps_per_cta;
-  if (grid) *grid = (int32_t)std::min<int64_t>(needed, (int64_t)d->num_sms * d->ctas_per_sm);
-  if (block) *block = d->warps_per_cta * 32;
-  if (smem_bytes) *smem_bytes = d->smem_bytes;
-  if (ctas_per_sm) *ctas_per_sm = d->ctas_per_sm;
+  const DeviceCopy::Shape& sh = d->shape[0];     // the lean instantiation (positions + solver statistics)
+  const int64_t needed = (n_instances + sh.warps_per_cta - 1) / sh.warps_per_cta;
+  if (grid) *grid = (int32_t)std::min<int64_t>(needed, (int64_t)d->num_sms * sh.ctas_per_sm);
+  if (block) *block = sh.warps_per_cta * 32;
+  if (smem_bytes) *smem_bytes = sh.smem_bytes;
+  if (ctas_per_sm) *ctas_per_sm = sh.ctas_per_sm;
   return OKIN_OK;
 }
 

@@ -110,6 +110,26 @@ OKIN_HD double okin_red_max(const double* red) {
 }
 #endif
 
+// Gather lists (factor update, triangular solves, assembly) are padded by the host compiler to even
+// length with null contributions (operands in the slice's zero block), so the loops below take two
+// contributions per trip without a remainder: one 64-bit index load, two independent accumulator
+// sets (the second contribution's loads do not wait for the first one's FMA chain).
+#ifndef OKIN_PAIR_LOOPS
+#define OKIN_PAIR_LOOPS 0     // 1: the topology must be compiled with list_pad = 2 (core/topology.py)
+#endif
+#ifndef OKIN_FMA_CHAIN
+#define OKIN_FMA_CHAIN 1
+#endif
+struct OkinPair { uint32_t x, y; };
+OKIN_HD OkinPair okin_pair(const int32_t* p) {
+#if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return OkinPair{v.x, v.y};
+#else
+  return OkinPair{(uint32_t)p[0], (uint32_t)p[1]};
+#endif
+}
+
 struct OkinProgram {
   const int32_t* hdr;  // [OKIN_HDR_SIZE]
   const int32_t* ib;   // int32 blob: at least its hot prefix hdr[OKIN_H_NHOT] (shared memory in the kernel)
@@ -409,16 +429,18 @@ OKIN_FN void okin_shim_presolve(const OkinProgram& pr, double* sm, const double*
 // ---------------------------------------------------------------------------------------
 template <bool SHIM>
 OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restrict__ hardpoints,
-                        const double* __restrict__ params, int* invalid) {
+                        const double* __restrict__ params, int* invalid, bool keep_design) {
   sm = OKIN_SHARED(sm);
   const int32_t* hdr = OKIN_SHARED(pr.hdr);
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* cst = sm + hdr[OKIN_H_OFF_CST];
   double* par = sm + hdr[OKIN_H_OFF_PAR];
+  double* zero = sm + hdr[OKIN_H_OFF_ZERO];
   const int nin = hdr[OKIN_H_NIN];
   const int32_t* in_point = okin_sec(pr, OKIN_S_IN_POINT);
   OKIN_PHASE_BEGIN
   for (int t = lane; t < 3 * nin; t += 32) pos[3 * OKIN_LDG(in_point + t / 3) + t % 3] = hardpoints[t];
+  if (lane < 9) zero[lane] = 0.0;
   OKIN_PHASE_END
   if (SHIM) okin_shim_presolve(pr, sm, params ? params : okin_fsec(pr, OKIN_F_PARAM_DEFAULT), invalid);
 
@@ -447,7 +469,7 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
 
   okin_derived_update(pr, sm, false);
 
-  {  // design positions kept for the metrics (travel references, rotation datums)
+  if (keep_design) {  // design positions kept for the metrics (travel references, rotation datums)
     const int ndsn = hdr[OKIN_H_NDSN];
     const int32_t* dpt = okin_sec(pr, OKIN_S_DESIGN_PT);
     double* dsn = sm + hdr[OKIN_H_OFF_DSN];
@@ -640,6 +662,26 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
       // one 3x3 block of A: sum of outer products ga gb^T over the rows coupling the two points
       const int b = OKIN_LDG(aptr + t), e = OKIN_LDG(aptr + t + 1);
       double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
+#if OKIN_PAIR_LOOPS
+      double b00 = 0, b01 = 0, b02 = 0, b10 = 0, b11 = 0, b12 = 0, b20 = 0, b21 = 0, b22 = 0;
+      for (int q = b; q < e; q += 2) {
+        const OkinPair w = okin_pair(acon + q);
+        const double* ga = rg + ((w.x >> 16) & 0x7fffu);
+        const double* gb = rg + (w.x & 0xffffu);
+        const double* ha = rg + ((w.y >> 16) & 0x7fffu);
+        const double* hb = rg + (w.y & 0xffffu);
+        const double sg = (w.x & OKIN_CON_NEG) ? -1.0 : 1.0, sh = (w.y & OKIN_CON_NEG) ? -1.0 : 1.0;
+        const double x0 = sg * ga[0], x1 = sg * ga[1], x2 = sg * ga[2], y0 = gb[0], y1 = gb[1], y2 = gb[2];
+        const double u0 = sh * ha[0], u1 = sh * ha[1], u2 = sh * ha[2], v0 = hb[0], v1 = hb[1], v2 = hb[2];
+        a00 = fma(x0, y0, a00); a01 = fma(x0, y1, a01); a02 = fma(x0, y2, a02);
+        a10 = fma(x1, y0, a10); a11 = fma(x1, y1, a11); a12 = fma(x1, y2, a12);
+        a20 = fma(x2, y0, a20); a21 = fma(x2, y1, a21); a22 = fma(x2, y2, a22);
+        b00 = fma(u0, v0, b00); b01 = fma(u0, v1, b01); b02 = fma(u0, v2, b02);
+        b10 = fma(u1, v0, b10); b11 = fma(u1, v1, b11); b12 = fma(u1, v2, b12);
+        b20 = fma(u2, v0, b20); b21 = fma(u2, v1, b21); b22 = fma(u2, v2, b22);
+      }
+      a00 += b00; a01 += b01; a02 += b02; a10 += b10; a11 += b11; a12 += b12; a20 += b20; a21 += b21; a22 += b22;
+#else
       OKIN_UNROLL_INNER
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(acon + q);
@@ -651,6 +693,7 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
         a10 = fma(x1, y0, a10); a11 = fma(x1, y1, a11); a12 = fma(x1, y2, a12);
         a20 = fma(x2, y0, a20); a21 = fma(x2, y1, a21); a22 = fma(x2, y2, a22);
       }
+#endif
       const int task = OKIN_LDG(atask + t);
       if (task & OKIN_ASM_DIAG) { a00 *= damp; a11 *= damp; a22 *= damp; }
       double* dst = Lb + 9 * (task & 0xffff);
@@ -659,7 +702,18 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
     } else {
       const int j = t - nat;
       const int b = OKIN_LDG(gptr + j), e = OKIN_LDG(gptr + j + 1);
-      double g0 = 0, g1 = 0, g2 = 0;
+      double g0 = 0, g1 = 0, g2 = 0, h0 = 0, h1 = 0, h2 = 0;
+#if OKIN_PAIR_LOOPS
+      for (int q = b; q < e; q += 2) {
+        const OkinPair w = okin_pair(gcon + q);
+        const double* ga = rg + ((w.x >> 16) & 0x7fffu);
+        const double* ha = rg + ((w.y >> 16) & 0x7fffu);
+        const double ra = (w.x & OKIN_CON_NEG) ? -r[w.x & 0xffffu] : r[w.x & 0xffffu];
+        const double rb = (w.y & OKIN_CON_NEG) ? -r[w.y & 0xffffu] : r[w.y & 0xffffu];
+        g0 = fma(ga[0], ra, g0); g1 = fma(ga[1], ra, g1); g2 = fma(ga[2], ra, g2);
+        h0 = fma(ha[0], rb, h0); h1 = fma(ha[1], rb, h1); h2 = fma(ha[2], rb, h2);
+      }
+#else
       OKIN_UNROLL_INNER
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(gcon + q);
@@ -667,7 +721,8 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
         const double res = (w & OKIN_CON_NEG) ? -r[w & 0xffffu] : r[w & 0xffffu];
         g0 = fma(ga[0], res, g0); g1 = fma(ga[1], res, g1); g2 = fma(ga[2], res, g2);
       }
-      vec[3 * j] = -g0; vec[3 * j + 1] = -g1; vec[3 * j + 2] = -g2;  // right-hand side of A h = -g
+#endif
+      vec[3 * j] = -(g0 + h0); vec[3 * j + 1] = -(g1 + h1); vec[3 * j + 2] = -(g2 + h2);  // right-hand side of A h = -g
     }
   }
   OKIN_PHASE_END
@@ -704,16 +759,20 @@ OKIN_HD void okin_write_diag_factor(double* sm, int doff, double* red, int lane)
   if (!ok) red[lane] = 1.0;
 }
 
+// carry_tangents: also run the update / scale tasks of the tangent right-hand sides vec[1..NT]
+// (ordered last in every level by the host compiler).
 template <typename Dummy = void>
-OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
+OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, bool carry_tangents) {
   sm = OKIN_SHARED(sm);
   const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nlev = hdr[OKIN_H_NLEV];
   const int32_t* lev_upd = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_UPD));
+  const int32_t* lev_upd_mid = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_UPD_MID));
   const int32_t* udst = OKIN_SHARED(okin_sec(pr, OKIN_S_UPD_DST));
   const int32_t* uptr = OKIN_SHARED(okin_sec(pr, OKIN_S_UPD_PTR));
   const int32_t* ucon = OKIN_SHARED(okin_sec(pr, OKIN_S_UPD_CON));
   const int32_t* lev_scl = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_SCL));
+  const int32_t* lev_scl_mid = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_SCL_MID));
   const int32_t* scl = OKIN_SHARED(okin_sec(pr, OKIN_S_SCL));
   const int32_t* lcp = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_COL_PTR));
   const int32_t* lcol = OKIN_SHARED(okin_sec(pr, OKIN_S_LEV_COL));
@@ -723,25 +782,48 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
   red[lane] = 0.0;
   OKIN_PHASE_END
   for (int lv = 0; lv < nlev; ++lv) {
-    const int ub = OKIN_LDG(lev_upd + lv), ue = OKIN_LDG(lev_upd + lv + 1);
+    const int ub = OKIN_LDG(lev_upd + lv), ue = carry_tangents ? OKIN_LDG(lev_upd + lv + 1) : OKIN_LDG(lev_upd_mid + lv);
     if (ue > ub) {
       OKIN_PHASE_BEGIN
-      // left-looking update of one block row (or of the carried right-hand side)
+      // left-looking update of one block row (or of a carried right-hand side), two contributions per trip
       for (int t = ub + lane; t < ue; t += 32) {
         const int b = OKIN_LDG(uptr + t), e = OKIN_LDG(uptr + t + 1);
         double* dst = sm + OKIN_LDG(udst + t);
-        double c0 = dst[0], c1 = dst[1], c2 = dst[2];
+        double c0 = dst[0], c1 = dst[1], c2 = dst[2], d0 = 0.0, d1 = 0.0, d2 = 0.0;
+#if OKIN_PAIR_LOOPS
+        for (int q = b; q < e; q += 2) {
+          const OkinPair w = okin_pair(ucon + q);
+          const double* a = sm + (w.x >> 16);
+          const double* B = sm + (w.x & 0xffffu);
+          const double* p = sm + (w.y >> 16);
+          const double* Q = sm + (w.y & 0xffffu);
+          const double a0 = a[0], a1 = a[1], a2 = a[2], p0 = p[0], p1 = p[1], p2 = p[2];
+          c0 = fma(-a0, B[0], c0); c1 = fma(-a0, B[3], c1); c2 = fma(-a0, B[6], c2);
+          d0 = fma(-p0, Q[0], d0); d1 = fma(-p0, Q[3], d1); d2 = fma(-p0, Q[6], d2);
+          c0 = fma(-a1, B[1], c0); c1 = fma(-a1, B[4], c1); c2 = fma(-a1, B[7], c2);
+          d0 = fma(-p1, Q[1], d0); d1 = fma(-p1, Q[4], d1); d2 = fma(-p1, Q[7], d2);
+          c0 = fma(-a2, B[2], c0); c1 = fma(-a2, B[5], c1); c2 = fma(-a2, B[8], c2);
+          d0 = fma(-p2, Q[2], d0); d1 = fma(-p2, Q[5], d1); d2 = fma(-p2, Q[8], d2);
+        }
+#else
         OKIN_UNROLL_INNER
         for (int q = b; q < e; ++q) {
           const uint32_t w = (uint32_t)OKIN_LDG(ucon + q);
           const double* a = sm + (w >> 16);
           const double* B = sm + (w & 0xffffu);
           const double a0 = a[0], a1 = a[1], a2 = a[2];
+#if OKIN_FMA_CHAIN
+          c0 = fma(-a0, B[0], c0); c1 = fma(-a0, B[3], c1); c2 = fma(-a0, B[6], c2);
+          c0 = fma(-a1, B[1], c0); c1 = fma(-a1, B[4], c1); c2 = fma(-a1, B[7], c2);
+          c0 = fma(-a2, B[2], c0); c1 = fma(-a2, B[5], c1); c2 = fma(-a2, B[8], c2);
+#else
           c0 -= a0 * B[0] + a1 * B[1] + a2 * B[2];
           c1 -= a0 * B[3] + a1 * B[4] + a2 * B[5];
           c2 -= a0 * B[6] + a1 * B[7] + a2 * B[8];
+#endif
         }
-        dst[0] = c0; dst[1] = c1; dst[2] = c2;
+#endif
+        dst[0] = c0 + d0; dst[1] = c1 + d1; dst[2] = c2 + d2;
       }
       OKIN_PHASE_END
     }
@@ -752,7 +834,7 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st) {
     for (int c = wb + lane; c < we; c += 32)
       okin_write_diag_factor(sm, OKIN_LDG(doffs + OKIN_LDG(lcol + c)), red, lane);
     OKIN_PHASE_END
-    const int sb = OKIN_LDG(lev_scl + lv), se = OKIN_LDG(lev_scl + lv + 1);
+    const int sb = OKIN_LDG(lev_scl + lv), se = carry_tangents ? OKIN_LDG(lev_scl + lv + 1) : OKIN_LDG(lev_scl_mid + lv);
     OKIN_PHASE_BEGIN
     for (int t = sb + lane; t < se; t += 32) {
       const uint32_t w = (uint32_t)OKIN_LDG(scl + t);
@@ -792,16 +874,41 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
     for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
       const int j = OKIN_LDG(lcol + cb + t / nrhs);
       double* v = vec + (t % nrhs) * n;
-      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2];
+      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2], s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#if OKIN_PAIR_LOOPS
+      for (int q = OKIN_LDG(fptr + j), e = OKIN_LDG(fptr + j + 1); q < e; q += 2) {
+        const OkinPair w = okin_pair(fcon + q);
+        const double* B = Lb + (w.x >> 16);
+        const double* y = v + (w.x & 0xffffu);
+        const double* C = Lb + (w.y >> 16);
+        const double* z = v + (w.y & 0xffffu);
+        const double y0 = y[0], y1 = y[1], y2 = y[2], z0 = z[0], z1 = z[1], z2 = z[2];
+        t0 = fma(-B[0], y0, t0); t1 = fma(-B[3], y0, t1); t2 = fma(-B[6], y0, t2);
+        s0 = fma(-C[0], z0, s0); s1 = fma(-C[3], z0, s1); s2 = fma(-C[6], z0, s2);
+        t0 = fma(-B[1], y1, t0); t1 = fma(-B[4], y1, t1); t2 = fma(-B[7], y1, t2);
+        s0 = fma(-C[1], z1, s0); s1 = fma(-C[4], z1, s1); s2 = fma(-C[7], z1, s2);
+        t0 = fma(-B[2], y2, t0); t1 = fma(-B[5], y2, t1); t2 = fma(-B[8], y2, t2);
+        s0 = fma(-C[2], z2, s0); s1 = fma(-C[5], z2, s1); s2 = fma(-C[8], z2, s2);
+      }
+#else
       OKIN_UNROLL_INNER
       for (int q = OKIN_LDG(fptr + j); q < OKIN_LDG(fptr + j + 1); ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(fcon + q);
         const double* B = Lb + (w >> 16);
         const double* y = v + (w & 0xffffu);
+#if OKIN_FMA_CHAIN
+        const double y0 = y[0], y1 = y[1], y2 = y[2];
+        t0 = fma(-B[0], y0, t0); t1 = fma(-B[3], y0, t1); t2 = fma(-B[6], y0, t2);
+        t0 = fma(-B[1], y1, t0); t1 = fma(-B[4], y1, t1); t2 = fma(-B[7], y1, t2);
+        t0 = fma(-B[2], y2, t0); t1 = fma(-B[5], y2, t1); t2 = fma(-B[8], y2, t2);
+#else
         t0 -= B[0] * y[0] + B[1] * y[1] + B[2] * y[2];
         t1 -= B[3] * y[0] + B[4] * y[1] + B[5] * y[2];
         t2 -= B[6] * y[0] + B[7] * y[1] + B[8] * y[2];
+#endif
       }
+#endif
+      t0 += s0; t1 += s1; t2 += s2;
       const double* f = sm + OKIN_LDG(doffs + j);
       const double y0 = t0 * f[6];
       const double y1 = (t1 - f[1] * y0) * f[7];
@@ -816,16 +923,41 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
     for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
       const int j = OKIN_LDG(lcol + cb + t / nrhs);
       double* v = vec + (t % nrhs) * n;
-      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2];
+      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2], s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#if OKIN_PAIR_LOOPS
+      for (int q = OKIN_LDG(bptr + j), e = OKIN_LDG(bptr + j + 1); q < e; q += 2) {
+        const OkinPair w = okin_pair(bcon + q);
+        const double* B = Lb + (w.x >> 16);
+        const double* x = v + (w.x & 0xffffu);
+        const double* C = Lb + (w.y >> 16);
+        const double* z = v + (w.y & 0xffffu);
+        const double x0 = x[0], x1 = x[1], x2 = x[2], z0 = z[0], z1 = z[1], z2 = z[2];
+        t0 = fma(-B[0], x0, t0); t1 = fma(-B[1], x0, t1); t2 = fma(-B[2], x0, t2);
+        s0 = fma(-C[0], z0, s0); s1 = fma(-C[1], z0, s1); s2 = fma(-C[2], z0, s2);
+        t0 = fma(-B[3], x1, t0); t1 = fma(-B[4], x1, t1); t2 = fma(-B[5], x1, t2);
+        s0 = fma(-C[3], z1, s0); s1 = fma(-C[4], z1, s1); s2 = fma(-C[5], z1, s2);
+        t0 = fma(-B[6], x2, t0); t1 = fma(-B[7], x2, t1); t2 = fma(-B[8], x2, t2);
+        s0 = fma(-C[6], z2, s0); s1 = fma(-C[7], z2, s1); s2 = fma(-C[8], z2, s2);
+      }
+#else
       OKIN_UNROLL_INNER
       for (int q = OKIN_LDG(bptr + j); q < OKIN_LDG(bptr + j + 1); ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(bcon + q);
         const double* B = Lb + (w >> 16);
         const double* x = v + (w & 0xffffu);
+#if OKIN_FMA_CHAIN
+        const double x0 = x[0], x1 = x[1], x2 = x[2];
+        t0 = fma(-B[0], x0, t0); t1 = fma(-B[1], x0, t1); t2 = fma(-B[2], x0, t2);
+        t0 = fma(-B[3], x1, t0); t1 = fma(-B[4], x1, t1); t2 = fma(-B[5], x1, t2);
+        t0 = fma(-B[6], x2, t0); t1 = fma(-B[7], x2, t1); t2 = fma(-B[8], x2, t2);
+#else
         t0 -= B[0] * x[0] + B[3] * x[1] + B[6] * x[2];
         t1 -= B[1] * x[0] + B[4] * x[1] + B[7] * x[2];
         t2 -= B[2] * x[0] + B[5] * x[1] + B[8] * x[2];
+#endif
       }
+#endif
+      t0 += s0; t1 += s1; t2 += s2;
       const double* f = sm + OKIN_LDG(doffs + j);
       const double x2 = t2 * f[8];
       const double x1 = (t1 - f[4] * x2) * f[7];
@@ -892,34 +1024,40 @@ OKIN_FN double okin_vec_max(const OkinProgram& pr, double* sm, int which) {
   return okin_red_max(red);
 }
 
-// Continuation predictor on the solution path x(t): p_k = sum_j V_j(t_k) dt_j is h x'(t_k) for
-// uniform target increments, and x(t_{k+1}) - x(t_k) is extrapolated Adams-Bashforth style:
-//   order 1: p_k     order 2: p_k + (p_k - p_{k-1})/2     order 3: (23 p_k - 16 p_{k-1} + 5 p_{k-2})/12
-// V_j are the tangents of the previous state; p_{k-1}, p_{k-2} are kept in shared memory.
+// Continuation predictor (no tangents needed): with the last accepted
+// solutions x_k (in pos), x_{k-1} (xprev) and the two older increments d1 = x_{k-1} - x_{k-2},
+// d2 = x_{k-2} - x_{k-3} (float32: they only shape the starting point), the next increment for
+// uniform target steps is the Newton backward-difference extrapolation
+//   order 1: d0      order 2: 2 d0 - d1      order 3: 3 d0 - 3 d1 + d2,      d0 = x_k - x_{k-1}.
+// Always shifts the history and leaves xprev = x_k: the start of the step, which is also what a failed
+// predicted start is retried from (the reference's plain warm start, solver.py:774).
 template <typename Dummy = void>
-OKIN_FN void okin_predict(const OkinProgram& pr, double* sm, const double* dt, int order) {
+OKIN_FN void okin_extrapolate(const OkinProgram& pr, double* sm, int order) {
   sm = OKIN_SHARED(sm);
   const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int n = 3 * hdr[OKIN_H_NF];
-  const int nt = hdr[OKIN_H_NT];
   const int32_t* ep = OKIN_SHARED(okin_sec(pr, OKIN_S_ELIM_POINT));
   double* pos = sm + hdr[OKIN_H_OFF_POS];
-  const double* V = sm + hdr[OKIN_H_OFF_VEC] + n;
-  // The history only shapes the starting point of the iteration, never the converged answer:
-  // single precision (1e-7 relative on mm-scale increments) is plenty and halves its footprint.
-  float* p1 = reinterpret_cast<float*>(sm + hdr[OKIN_H_OFF_PPREV]);
-  float* p2 = reinterpret_cast<float*>(sm + hdr[OKIN_H_OFF_PPREV2]);
+  double* xprev = sm + hdr[OKIN_H_OFF_XPREV];
+  float* h1 = reinterpret_cast<float*>(sm + hdr[OKIN_H_OFF_DHIST]);
+  float* h2 = h1 + 2 * ((n + 1) / 2);
+  float* h3 = h2 + 2 * ((n + 1) / 2);
   OKIN_PHASE_BEGIN
   for (int u = lane; u < n; u += 32) {
-    double p = 0.0;
-    for (int j = 0; j < nt; ++j) p = fma(V[j * n + u], dt[j], p);
-    const double a = (double)p1[u], b = (double)p2[u];
-    double step = p;
-    if (order == 2) step = p + 0.5 * (p - a);
-    if (order >= 3) step = (23.0 * p - 16.0 * a + 5.0 * b) * (1.0 / 12.0);
-    p2[u] = p1[u];
-    p1[u] = (float)p;
-    pos[3 * OKIN_LDG(ep + u / 3) + u % 3] += step;
+    const int idx = 3 * OKIN_LDG(ep + u / 3) + u % 3;
+    const double x = pos[idx];
+    const double d0 = x - xprev[u];
+    const double d1 = (double)h1[u], d2 = (double)h2[u], d3 = (double)h3[u];
+    double step = 0.0;
+    if (order == 1) step = d0;
+    if (order == 2) step = 2.0 * d0 - d1;
+    if (order == 3) step = 3.0 * (d0 - d1) + d2;
+    if (order >= 4) step = 4.0 * (d0 + d2) - 6.0 * d1 - d3;
+    h3[u] = h2[u];
+    h2[u] = h1[u];
+    h1[u] = (float)d0;
+    xprev[u] = x;
+    pos[idx] = x + step;
   }
   OKIN_PHASE_END
 }
@@ -954,35 +1092,32 @@ OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
 // after a step that fails to reduce ||r||^2.  A step below fine_tol ends the iteration (error
 // second order in it); a step below coarse_tol is verified and finished by a chord step.
 // Returns the number of residual evaluations (the SolverInfo.nfev analogue).  On return r[] holds
-// the residuals at (within step_tol of) the final point, vec[1..NT] the tangents of the last
-// undamped linearisation when *tangents_ready.
+// the residuals at (within step_tol of) the final point; *gradients_at_solution: rg[] holds the row
+// gradients there too (only asked for when the caller linearises at the solution afterwards).
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
 OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tval, const OkinSolverCfg& cfg,
-                            OkinState& st, bool* converged, bool* tangents_ready, bool relinearise,
-                            bool* gradients_at_solution) {
+                            OkinState& st, bool* converged, bool relinearise, bool* gradients_at_solution) {
   *gradients_at_solution = false;
   sm = OKIN_SHARED(sm);
-  const int nt = pr.hdr[OKIN_H_NT];
   int nfev = 0;
-  *tangents_ready = false;
   st.mu = 0.0;
   double nu = 2.0;
   okin_eval_rows(pr, sm, tval, true, st);
   ++nfev;
   *converged = false;
   for (int it = 0; it < cfg.max_iter; ++it) {
-    // The factorisation carries the step right-hand side and the tangent right-hand sides as
-    // extra rows, so one backward pass yields the step and dq/dt_j of this linearisation.
+    // The factorisation carries the step right-hand side as an extra block row, so the forward
+    // substitution is part of it and one backward pass yields the step.  (The tangent right-hand sides
+    // ride along only when the caller linearises at a solution for the exported tangents / metrics.)
     okin_assemble(pr, sm, st.mu, false);
-    okin_tangent_rhs(pr, sm);
-    okin_factor(pr, sm, st);
+    okin_factor(pr, sm, st, false);
     if (st.notpd) {  // rank-deficient normal matrix: damp and retry from the same point
       st.mu = st.mu > 0.0 ? st.mu * 10.0 : cfg.mu_init;
       if (st.mu > 1e12) break;
       continue;
     }
-    okin_solve(pr, sm, 0, 1 + nt, true);
+    okin_solve(pr, sm, 0, 1, true);
     const double hmax = okin_apply_step(pr, sm, 0, 1.0, true);
     if (!(hmax == hmax)) {  // NaN step: invalid geometry
       okin_restore(pr, sm);
@@ -996,7 +1131,6 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       const bool last = hmax <= cfg.fine_tol;
       okin_eval_rows(pr, sm, tval, relinearise && last, st);
       ++nfev;
-      *tangents_ready = true;                    // linearised within hmax of the solution
       if (last) {                                // error left ~ k hmax^2: done without verification
         *gradients_at_solution = relinearise;
         *converged = true;
@@ -1012,7 +1146,6 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
         break;
       }
       okin_restore(pr, sm);
-      *tangents_ready = false;
       // Not contracting fast enough: relinearise at the current point.
       okin_eval_rows(pr, sm, tval, true, st);
       ++nfev;
@@ -1310,8 +1443,10 @@ OKIN_FN void okin_metrics(const OkinProgram& pr, double* sm, double* out) {
         if (rate > strongest + OKIN_GEOM_EPS) { best = j; strongest = rate; best_rate = v[da]; tied = false; }
         else if (rate >= OKIN_GEOM_EPS && fabs(rate - strongest) <= OKIN_GEOM_EPS) tied = true;
       }
-      if (best < 0 || strongest < OKIN_GEOM_EPS || tied) {
-        value = NAN;
+      if (best < 0 || strongest < OKIN_GEOM_EPS) {
+        value = NAN;            // no driver tangent: the reference's None
+      } else if (tied) {
+        value = INFINITY;       // equal-strength drivers: the reference raises (derivatives.py:299-304)
       } else {
         const OkinDual resp = okin_response<OkinDual>(pr, sm, rec, best);
         value = resp.d / best_rate;
@@ -1661,8 +1796,6 @@ struct OkinOutputs {
   int32_t* status;        // [1]
   int32_t* failed_step;   // [1]
   int32_t* worst_row;     // [1] or null: row owning max|r| at the failed step (solver.py:640-651), else -1
-  double* backup;         // scratch [3*NF] (global memory, one per resident warp): the last accepted
-                          // solution, for the retry from the plain warm start
 };
 
 // Index of the row with the largest |r| in r[0 .. nrows) (first one on ties, like np.argmax;
@@ -1720,12 +1853,9 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   const int32_t* out_point = OKIN_SHARED(okin_sec(pr, OKIN_S_OUT_POINT));
   const int32_t* ecol = okin_sec(pr, OKIN_S_ELIM_COL);
   const int32_t* elim_point = OKIN_SHARED(okin_sec(pr, OKIN_S_ELIM_POINT));
-  const int32_t* elim_out = okin_sec(pr, OKIN_S_ELIM_OUT);
-  // The last accepted solution (for the retry from the plain warm start) is the position row just
-  // written when every free point is exported; otherwise it is kept in the global backup row.
-  const bool from_rows = out.positions && hdr[OKIN_H_FREE_ALL_OUT];
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
+  const double* xprev = sm + hdr[OKIN_H_OFF_XPREV];
   // outputs only the full instantiation knows about
   double* const o_tangents = FULL ? out.tangents : nullptr;
   double* const o_velocities = FULL ? out.velocities : nullptr;
@@ -1733,7 +1863,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   double* const o_metrics = FULL ? out.metrics : nullptr;
   double* const o_diagnostics = FULL ? out.diagnostics : nullptr;
   int invalid = 0;
-  okin_setup<SHIM>(pr, sm, hardpoints, params, &invalid);
+  okin_setup<SHIM>(pr, sm, hardpoints, params, &invalid, FULL);
   if (out.design) {  // design (setup) pose of every output point
     OKIN_PHASE_BEGIN
     for (int t = lane; t < 3 * nout; t += 32) out.design[t] = pos[3 * OKIN_LDG(out_point + t / 3) + t % 3];
@@ -1750,34 +1880,36 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   for (int j = lane; j < 2 * OKIN_MAX_TARGETS; j += 32) tcur[j] = 0.0;
+  {   // increment history of the extrapolation predictor
+    float* h = reinterpret_cast<float*>(sm + hdr[OKIN_H_OFF_DHIST]);
+    for (int u = lane; u < 6 * ((n + 1) / 2); u += 32) h[u] = 0.0f;
+  }
   OKIN_PHASE_END
-  bool have_tangent = false;
-  int history = 0;
+  int run = 0;      // consecutive sweep steps (ending at the current one) with the same target increments
   int worst = -1;
 
   for (int s = 0; s < n_steps; ++s) {
     if (status == OKIN_STATUS_OK) {
-      const bool predict = cfg.use_predictor && have_tangent;
       OKIN_PHASE_BEGIN
       double changed = 0.0;
       if (lane < nt) {
         const double cur = OKIN_LDG(tvals + lane * n_steps + s);
         const double d = cur - tcur[lane], dprev = dt[lane];
         tcur[lane] = cur;
-        if (predict) {
-          if (fabs(d - dprev) > 1e-9 * (fabs(d) + fabs(dprev))) changed = 1.0;
-          dt[lane] = d;
-        }
+        if (fabs(d - dprev) > 1e-9 * (fabs(d) + fabs(dprev))) changed = 1.0;
+        dt[lane] = d;
       }
       red[lane] = changed;
       OKIN_PHASE_END
-      if (predict) {
-        const bool same = okin_red_sum(red) == 0.0;
-        history = same ? history + 1 : 1;   // consecutive predictor steps with the same increments
-        const int order = history < cfg.use_predictor ? history : cfg.use_predictor;
-        okin_predict(pr, sm, dt, order);
-      }
-      bool conv = false, tangents_ready = false;
+      const bool same = okin_red_sum(red) == 0.0;
+      run = s == 0 ? 0 : (same && run > 0 ? run + 1 : 1);
+      // Predicted start: extrapolation of the solution history (first increment known at step 2, order
+      // limited by the run of equal target increments).
+      int order = run - 1 < cfg.use_predictor ? run - 1 : cfg.use_predictor;
+      if (order < 0) order = 0;
+      okin_extrapolate(pr, sm, order);
+      const bool predicted = order > 0;
+      bool conv = false;
       const bool relinearise = o_tangents || o_velocities || o_health || o_metrics;
       bool at_solution = false;
       int nfev = 0;
@@ -1787,17 +1919,14 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       // is restored and the step is solved again from the plain warm start before it is flagged.
       for (int attempt = 0; attempt < 2; ++attempt) {
         if (attempt == 1) {
-          const double* prev = from_rows ? out.positions + (size_t)(s - 1) * 3 * nout : out.backup;
           OKIN_PHASE_BEGIN
-          for (int u = lane; u < n; u += 32)
-            pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3] =
-                from_rows ? prev[3 * OKIN_LDG(elim_out + u / 3) + u % 3] : prev[u];
+          for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3] = xprev[u];
           OKIN_PHASE_END
-          history = 0;
+          run = 1;
         }
-        nfev += okin_solve_step(pr, sm, tcur, cfg, st, &conv, &tangents_ready, relinearise, &at_solution);
+        nfev += okin_solve_step(pr, sm, tcur, cfg, st, &conv, relinearise, &at_solution);
         valid = st.rmax == st.rmax;
-        if ((conv && valid && st.rmax <= cfg.residual_tol) || !predict || s == 0) break;
+        if ((conv && valid && st.rmax <= cfg.residual_tol) || !predicted) break;
       }
       if (!conv || !valid) {
         status = valid ? OKIN_STATUS_NOT_CONVERGED : OKIN_STATUS_INVALID_GEOMETRY;
@@ -1814,10 +1943,9 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       }
       OKIN_PHASE_END
       if (status == OKIN_STATUS_OK) {
-        if (relinearise || !tangents_ready) {
-          // Exported tangents are taken at the solution itself: relinearise there.  (For the
-          // predictor alone the factor of the last Gauss-Newton point, <= coarse_tol away, is
-          // enough and was solved together with the chord step.)
+        if (FULL && relinearise) {
+          // Exported tangents are taken at the solution itself: linearise there, carrying the tangent
+          // right-hand sides through the factorisation (the iteration itself never needs them).
           if (!at_solution) {
             const double rmax = st.rmax;
             okin_eval_rows(pr, sm, tcur, true, st);
@@ -1825,11 +1953,10 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
           }
           okin_assemble(pr, sm, 0.0, false);
           okin_tangent_rhs(pr, sm);
-          okin_factor(pr, sm, st);
+          okin_factor(pr, sm, st, true);
           okin_solve(pr, sm, 1, nt, true);
         }
         okin_derived_update(pr, sm, false);
-        have_tangent = true;
       }
     } else {
       OKIN_PHASE_BEGIN
@@ -1840,14 +1967,11 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       OKIN_PHASE_END
     }
     const bool ok = status == OKIN_STATUS_OK;
-    {
-      double* dst = out.positions ? out.positions + (size_t)s * 3 * nout : nullptr;
+    if (out.positions) {
+      double* dst = out.positions + (size_t)s * 3 * nout;
       OKIN_PHASE_BEGIN
-      if (dst)
-        for (int t = lane; t < 3 * nout; t += 32)
-          dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
-      if (ok && cfg.use_predictor && !from_rows)   // last accepted solution (only a predicted start is retried)
-        for (int u = lane; u < n; u += 32) out.backup[u] = pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3];
+      for (int t = lane; t < 3 * nout; t += 32)
+        dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
       OKIN_PHASE_END
     }
     if (FULL && o_metrics) {

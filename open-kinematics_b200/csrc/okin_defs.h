@@ -108,7 +108,7 @@ enum okin_hdr_slot {
   // shared-memory layout (offsets in doubles from the instance's base)
   OKIN_H_OFF_POS, OKIN_H_OFF_CST, OKIN_H_OFF_R, OKIN_H_OFF_RG, OKIN_H_OFF_DBLK, OKIN_H_OFF_LB,
   OKIN_H_OFF_VEC, OKIN_H_OFF_RED, OKIN_H_OFF_PAR,
-  OKIN_H_OFF_PPREV,
+  OKIN_H_UNUSED0,
   OKIN_H_SMEM_DOUBLES, // shared-memory doubles per instance
   // metric program (csrc/okin_metrics.cuh)
   OKIN_H_NM,       // metric columns per state
@@ -121,13 +121,17 @@ enum okin_hdr_slot {
   OKIN_H_NPARAM,   // per-instance scalar parameters (doubles)
   OKIN_H_NDROW,    // distance rows on the fast evaluation path
   OKIN_H_NGROW,    // rows on the generic evaluation path (ROW_ORDER entries)
-  OKIN_H_OFF_PPREV2,  // second predictor-history vector
+  OKIN_H_UNUSED1,
   OKIN_H_OFF_TGT,  // [2][OKIN_MAX_TARGETS] target values of the current step and their last increments
   OKIN_H_NHOT,     // int32 words of the hot prefix of the int blob (sections used inside the
                    // iteration; the kernel keeps them in shared memory, the rest stays in global memory)
   OKIN_H_NDIAG,    // diagnostic columns per state (OKIN_DIAG_BASE + topology columns), 0 = no program
   OKIN_H_NDGOP,    // topology diagnostic ops
   OKIN_H_FREE_ALL_OUT,  // 1 when every free point is an output point (ELIM_OUT has no -1)
+  OKIN_H_OFF_ZERO,   // 9 doubles kept at zero: operands of the null contributions that pad gather lists
+  OKIN_H_OFF_XPREV,  // previous accepted solution (3*NF doubles, elimination order)
+  OKIN_H_OFF_DHIST,  // three older solution increments as float32 vectors (extrapolation predictor)
+  OKIN_H_SMEM_DOUBLES_LEAN,  // slice size of an instance solved without tangents / metrics / diagnostics
   OKIN_H_SEC0 = 64,                      // room for 64 scalar slots,
   OKIN_H_FSEC0 = 64 + 2 * 64,            // 64 int32 sections
   OKIN_HDR_SIZE = 64 + 2 * 64 + 2 * 8    // and 8 double sections
@@ -147,6 +151,8 @@ enum okin_isec {
   OKIN_S_ASM_CON,        // (ia << 16) | ib: rg[] offsets of the two 3-vectors whose outer product is added
   OKIN_S_G_PTR,          // [NF+1]  (elimination-ordered block columns)
   OKIN_S_G_CON,          // (irg << 16) | row: g_j += rg[irg..irg+3) * r[row]
+  OKIN_S_LEV_UPD_MID,    // [NLEV] end of the level's update tasks that do not belong to tangent right-hand sides
+  OKIN_S_LEV_SCL_MID,    // [NLEV] same for the scale tasks
   OKIN_S_LEV_UPD,        // [NLEV+1] ranges into UPD_DST/UPD_PTR
   OKIN_S_UPD_DST,        // shared-memory offset of the 3-entry row being updated
   OKIN_S_UPD_PTR,        // [n_upd+1]

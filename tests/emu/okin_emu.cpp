@@ -17,9 +17,14 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
   OkinSolverCfg cfg{c->step_tol, c->coarse_tol, c->fine_tol, c->residual_tol, c->mu_init, c->max_iter,
                     c->use_predictor};
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
-  std::vector<double> sm(hdr[OKIN_H_SMEM_DOUBLES]), backup(n + 1);
+  std::vector<double> sm(hdr[OKIN_H_SMEM_DOUBLES]);
+  // the library's launch() rule: lean instantiation when no per-state tangent / metric / diagnostic
+  // output is wanted (it only owns the lean part of the slice)
+  const bool full = io->tangents || io->velocities || io->tangent_health || io->metrics || io->diagnostics;
+  const size_t live = full ? (size_t)hdr[OKIN_H_SMEM_DOUBLES] : (size_t)hdr[OKIN_H_SMEM_DOUBLES_LEAN];
   for (long i = 0; i < n_instances; ++i) {
-    std::fill(sm.begin(), sm.end(), 0.0);
+    std::fill(sm.begin(), sm.begin() + live, 0.0);
+    std::fill(sm.begin() + live, sm.end(), NAN);     // a lean run must not touch the rest
     OkinOutputs out;
     out.positions = io->positions ? io->positions + (size_t)i * n_steps * 3 * nout : nullptr;
     out.iters = io->iters ? io->iters + (size_t)i * n_steps : nullptr;
@@ -34,11 +39,14 @@ extern "C" int okin_emu_sweep(const int32_t* hdr, const int32_t* ib, const doubl
     out.status = io->status + i;
     out.failed_step = io->failed_step + i;
     out.worst_row = io->worst_row ? io->worst_row + i : nullptr;
-    out.backup = backup.data();
-    okin_sweep<true, true>(pr, sm.data(), io->hardpoints + (size_t)i * 3 * nin,
-               io->params ? io->params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr,
-               io->instance_targets ? io->instance_targets + (size_t)i * nt * n_steps : io->target_values, n_steps,
-               cfg, out);
+    const double* tv = io->instance_targets ? io->instance_targets + (size_t)i * nt * n_steps : io->target_values;
+    const double* par = io->params ? io->params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr;
+    if (full)
+      okin_sweep<true, true>(pr, sm.data(), io->hardpoints + (size_t)i * 3 * nin, par, tv, n_steps, cfg, out);
+    else
+      okin_sweep<false, true>(pr, sm.data(), io->hardpoints + (size_t)i * 3 * nin, par, tv, n_steps, cfg, out);
+    for (size_t k = live; k < sm.size(); ++k)
+      if (sm[k] == sm[k]) return -2;                   // lean instantiation wrote outside its slice
     if (out.diagnostics && n_steps > 0) {  // continuity pass, as the product's second kernel does
       const int stride = (n_steps - 1) | 1;
       std::vector<double> scratch((size_t)32 * stride + 64);

@@ -204,8 +204,10 @@ def generic_mechanism():
 
 
 def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, want_health=False,
-              instance_targets=None, **cfg) -> dict:
-    """Run the lane-emulation build of the device core; ``cfg`` overrides ``okin_solver_cfg`` fields."""
+              instance_targets=None, lean=False, **cfg) -> dict:
+    """Run the lane-emulation build of the device core; ``cfg`` overrides ``okin_solver_cfg`` fields.
+    ``lean``: no tangent / metric / diagnostic outputs, i.e. the lean kernel instantiation (its own
+    predictor and the short slice)."""
     from open_kinematics_b200._lib import BatchIO, SolverCfg
     hp = np.ascontiguousarray(hardpoints, dtype=np.float64).reshape(-1, 3 * program.n_in)
     tv = np.ascontiguousarray(values, dtype=np.float64)
@@ -223,9 +225,12 @@ def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, 
         "worst_row": np.zeros(n_inst, np.int32),
     }
     itv = None if instance_targets is None else np.ascontiguousarray(instance_targets, dtype=np.float64)
+    if lean:
+        for name in ("tangents", "velocities", "tangent_health", "metrics", "diagnostics", "jumps"):
+            out[name] = None
     par = None if params is None else np.ascontiguousarray(params, dtype=np.float64)
     settings = dict(step_tol=1e-6, coarse_tol=1e-3, fine_tol=1e-4, residual_tol=1e-3, mu_init=1e-3, max_iter=50,
-                    use_predictor=3)
+                    use_predictor=4)
     settings.update(cfg)
     c = SolverCfg(**settings)
     hdr = np.ascontiguousarray(program.hdr)
@@ -233,7 +238,7 @@ def emu_solve(program, hardpoints: np.ndarray, values: np.ndarray, params=None, 
     rc = emu_lib().okin_emu_sweep(
         hdr.ctypes.data, program.iblob.ctypes.data, program.fblob.ctypes.data, n_inst, n_steps,
         ctypes.byref(c), ctypes.byref(io))
-    assert rc == 0
+    assert rc == 0, rc
     if out["metrics"] is None:
         out["metrics"] = np.zeros((n_inst, n_steps, 1))
     return out

@@ -278,3 +278,28 @@ def test_tuned_block_placement_keeps_the_answer(case):
     assert np.abs(a["tangents"] - b["tangents"]).max() <= 1e-9
     order = [tuned.out_keys.index(key_from_name(n)) for n in meta["point_keys"]]
     assert np.abs(b["positions"][0][:, order] - arr["positions_tight"]).max() <= POS_TOL_MM
+
+
+# ---------------------------------------------------------------------------------------------
+# Lean kernel instantiation (positions + solver statistics only): its own predictor (extrapolation
+# of the solution history, no tangents carried through the factorisation) and the short slice.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", SWEEP_CASES + ["c1_shim_plus2mm", "c4_tbar_heave_shim_roll", "c4_tbar_heave_shim_bump"])
+def test_lean_instantiation_matches_reference_tight_run(case):
+    meta, arr = load_golden(case)
+    sus, sweep = build_case(meta)
+    prog, values = _program(sus, sweep)
+    out = emu_solve(prog, _nominal(sus, prog), values, lean=True)
+    assert out["status"][0] == 0 and out["failed_step"][0] == -1
+    order = [prog.out_keys.index(key_from_name(n)) for n in meta["point_keys"]]
+    assert np.abs(out["positions"][0][:, order] - arr["positions_tight"]).max() <= POS_TOL_MM
+    assert out["max_residual"].max() < 1e-5
+    # the predictor pays off: fewer evaluations than the plain warm start, same answer
+    plain = emu_solve(prog, _nominal(sus, prog), values, lean=True, use_predictor=0)
+    assert np.abs(plain["positions"] - out["positions"]).max() < 1e-8
+    assert out["iters"].sum() < plain["iters"].sum()
+
+
+def test_lean_instantiation_failure_flags_match_reference():
+    cases = json.load(open(os.path.join(GOLDEN, "failures.json")))
+    check_failure_flags(lambda prog, hp, values: emu_solve(prog, hp, values, lean=True), cases)

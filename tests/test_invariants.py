@@ -139,3 +139,17 @@ def test_invariants_on_the_lane_emulation(emu_device, body):
 @pytest.mark.parametrize("body", BODIES, ids=lambda f: f.__name__)
 def test_invariants_on_the_device(body):
     body()
+
+
+def test_tied_derivative_drivers_raise_like_the_reference():
+    """The device marks a derivative column whose driver tangents tie with +inf (NaN = the
+    reference's None); the row builder turns it into the reference's ValueError
+    (metrics/derivatives.py:299-304)."""
+    import numpy as np
+    import pytest
+    from open_kinematics_b200.core.metrics.main import rows_from_columns
+    locations = [(None, "camber"), (None, "deriv_camber_wrt_wheel_travel")]
+    row = rows_from_columns(np.array([1.5, np.nan]), locations, is_axle=False)
+    assert row["camber"] == 1.5 and row["deriv_camber_wrt_wheel_travel"] is None
+    with pytest.raises(ValueError, match="Ambiguous derivative driver for column 'deriv_camber_wrt_wheel_travel'"):
+        rows_from_columns(np.array([1.5, np.inf]), locations, is_axle=False)

@@ -97,6 +97,12 @@ def run(label, sus, sweep, n, sigma, metrics=False, shim_mc=False):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+    print(json.dumps({"lib": _lib.LIB_PATH}), flush=True)
+    meta, _ = load_golden("c3_rocker_ubar_coilover_roll")
+    run("c3_axle_roll21_lean", *build_case(meta), 2 * n, 0.5)
+    if os.environ.get("OKIN_C3_ONLY"):
+        run("c5_c3_axle_roll21_metrics", *build_case(meta), n, 0.5, metrics=True)
+        return
     meta, _ = load_golden("c1_dw_corner_bump")
     run("c1_dw_corner_bump36", *build_case(meta), n, 0.5)
     meta, _ = load_golden("c2_macpherson_bump_steer")
