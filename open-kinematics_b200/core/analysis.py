@@ -1,10 +1,11 @@
 """Structured sweep analysis (reference core/analysis.py:52-316): frames of named positions and
 metric rows, the solved setup-reference pose, sweep parameters and diagnostics.
 
-The numbers come from the device through the sweep facade (``core/sweep.py``).  Presentation
-metadata of the reference's analysis object (element paths, wheel dimensions and references,
-metric display labels; core/presentation.py, core/assembly.py) is outside the solve path and is
-not mirrored: frames carry every point of the solved state under its public name.
+The numbers come from the device through the sweep facade (``core/sweep.py``).  Frames and the
+setup reference carry the reference's named positions: every point of the solved state under its
+public name plus the presentation points (rocker-pickup axis projections, T-bar midpoint;
+``core/presentation.py``).  The drawing metadata of the reference's analysis object (element
+paths, wheel dimensions, metric display labels) is outside the solve path and is not mirrored.
 """
 
 from __future__ import annotations
@@ -14,6 +15,7 @@ from dataclasses import dataclass, field
 from .diagnostics import DiagnosticCategory, DiagnosticIssue, DiagnosticSeverity
 from .enums import TargetPositionMode
 from .metrics.main import AxleMetricRows
+from .presentation import named_point_keys, resolve_positions
 from .primitives.point_ref import PointRef, Side
 from .solver import SolverInfo
 from .sweep import (EvaluatedSweep, compute_sweep_metrics, evaluate_solved_sweep, solve_evaluated_sweep, solve_sweep)
@@ -116,14 +118,14 @@ def setup_reference(suspension, sweep_config: SweepConfig) -> tuple:
             None, DiagnosticCategory.REFERENCE, DiagnosticSeverity.WARNING,
             f"Setup reference unavailable: reference solve failed ({type(error).__name__}: {error}).", None)
     metrics, corner_metrics = _split_metric_rows(row)
-    return ReferenceCondition("Setup", named_positions(states[0].positions), metrics, corner_metrics), None
+    return ReferenceCondition("Setup", resolve_positions(states[0].positions, suspension), metrics, corner_metrics), None
 
 
 def analyze_evaluated_sweep(suspension, sweep_config: SweepConfig, evaluated: EvaluatedSweep) -> SweepAnalysis:
     frames = []
     for index, (state, info, row) in enumerate(zip(evaluated.states, evaluated.solver_stats, evaluated.metrics.rows)):
         metrics, corner_metrics = _split_metric_rows(row)
-        frames.append(AnalyzedFrame(index, named_positions(state.positions), metrics, corner_metrics, info))
+        frames.append(AnalyzedFrame(index, resolve_positions(state.positions, suspension), metrics, corner_metrics, info))
     metric_keys, corner_metric_keys, locations = [], [], []
     for frame in frames:
         if not frame.metrics and not frame.corner_metrics:
@@ -140,7 +142,7 @@ def analyze_evaluated_sweep(suspension, sweep_config: SweepConfig, evaluated: Ev
     units = getattr(getattr(suspension, "units", None), "symbol", "mm")
     return SweepAnalysis(
         suspension=SuspensionInfo(suspension.name, str(suspension.reported_type_key()), units),
-        point_keys=list(frames[0].positions) if frames else [],
+        point_keys=named_point_keys(suspension, evaluated.states[0].positions) if frames else [],
         metric_keys=metric_keys, corner_metric_keys=corner_metric_keys, locations=locations,
         sweep_parameters=sweep_parameters(sweep_config), references=references, diagnostics=diagnostics,
         frames=frames)

@@ -34,7 +34,7 @@ R_COORD, R_DIST, R_CAMBER, R_TOE, R_CASTER, R_KPI, R_ROTATION, R_ROTATION_DIFF, 
 R_TBAR_TWIST_DEG, R_TBAR_TWIST_DELTA, R_TBAR_HEAVE = 9, 10, 11
 MOP_VALUE, MOP_DERIV = 0, 1
 MOP_STRIDE, MCORNER_STRIDE, MAXLE_STRIDE = 16, 24, 16
-IC_DW, IC_MAC = 0, 1
+IC_DW, IC_MAC, IC_NONE = 0, 1, 2
 MF_FRONT, MF_REAR, MF_HAS_BIAS, MF_DRIVEN_HERE = 1, 2, 4, 8
 
 
@@ -95,8 +95,8 @@ def _corner_block(b: _Builder, corner, key, suffix: str, candidates) -> None:
     elif isinstance(corner, MacPhersonSuspension):
         ic = [IC_MAC, P.LOWER_WISHBONE_INBOARD_FRONT, P.LOWER_WISHBONE_INBOARD_REAR, P.LOWER_WISHBONE_OUTBOARD,
               P.STRUT_TOP, None, None]
-    else:
-        raise TypeError(f"No metric program for {type(corner).__name__}")
+    else:   # user-defined architecture composed through the role hooks: no instant-centre declaration
+        ic = [IC_NONE, None, None, None, None, None, None]
     damper = corner.damper_points() or (None, None)
     flags = 0
     if cfg.axle_position is AxlePosition.FRONT:

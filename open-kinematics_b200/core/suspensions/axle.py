@@ -293,6 +293,19 @@ class AxleSuspension(Suspension):
         rows += self.anti_roll.constraints(self)
         return rows
 
+    def topology_diagnostics(self, states: list) -> list:
+        """Corner-owned diagnostics followed by the shared axle checks (reference
+        axle/suspension.py:241-251).  Checks of the shipped architectures run in the device's
+        diagnostic program (base class); a user-defined corner that overrides
+        ``topology_diagnostics`` is asked directly, with its own side's states."""
+        issues: list = []
+        for side in _SIDES:
+            corner = self.corners[side]
+            if type(corner).topology_diagnostics is not Suspension.topology_diagnostics:
+                issues.extend(corner.topology_diagnostics([self.corner_state(state, side) for state in states]))
+        issues.extend(super().topology_diagnostics(states))
+        return issues
+
     def derived_spec(self) -> DerivedPointsSpec:
         functions: dict = {}
         dependencies: dict = {}

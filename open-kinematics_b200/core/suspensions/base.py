@@ -126,8 +126,25 @@ class CornerSuspension(Suspension):
         if unknown:
             raise ValueError("Invalid hardpoints: " + ", ".join(sorted(p.name for p in unknown)))
 
+    # -- role hooks: what the axle composer, the metric program and the diagnostics ask of ANY corner
+    # (reference corner/base.py:20-101); user-defined corners override them -----------------------
     def wheel_axis_points(self) -> tuple:
         return (PointID.AXLE_INBOARD, PointID.AXLE_OUTBOARD)
+
+    def authored_state(self) -> SuspensionState:
+        """Design pose before any setup shim; a corner without shims has only one pose."""
+        return self.initial_state()
+
+    def constraints_at(self, positions) -> list:
+        """Constraints with their design constants taken at ``positions``.  Corners that compute
+        their constants from their own initial state need not override this."""
+        return self.constraints()
+
+    def instant_center_points(self):
+        """``(kind, points)`` of the planes whose intersection is the instant axis, or None when the
+        architecture declares no instant centres (then the side- / front-view instant-centre and
+        anti-geometry columns are None, as for the reference's compute_*_instant_center -> None)."""
+        return None
 
     def steering_axis_points(self) -> tuple:
         raise NotImplementedError

@@ -1324,9 +1324,10 @@ OKIN_HD void okin_corner_metrics(const OkinProgram& pr, double* sm, const int32_
     o[4] = gp[0] - cp[0];                                                  // mechanical trail
   }
   // instant axis = intersection of two planes n.x + d = 0 (geometric.py:216-302)
-  double n1[3], n2[3], d1, d2;
-  bool ok = true;
-  {
+  double n1[3] = {1.0, 0.0, 0.0}, n2[3] = {0.0, 1.0, 0.0}, d1 = 0.0, d2 = 0.0;
+  const int ic_kind = OKIN_LDG(rec + 6);
+  bool ok = ic_kind != OKIN_IC_NONE;
+  if (ok) {
     const double* a = pos + 3 * OKIN_LDG(rec + 7);
     const double* b = pos + 3 * OKIN_LDG(rec + 8);
     const double* c = pos + 3 * OKIN_LDG(rec + 9);
@@ -1337,7 +1338,7 @@ OKIN_HD void okin_corner_metrics(const OkinProgram& pr, double* sm, const int32_
     n1[0] /= m; n1[1] /= m; n1[2] /= m;
     d1 = -(n1[0] * a[0] + n1[1] * a[1] + n1[2] * a[2]);
   }
-  if (OKIN_LDG(rec + 6) == OKIN_IC_DW) {
+  if (ic_kind == OKIN_IC_DW) {
     const double* a = pos + 3 * OKIN_LDG(rec + 10);
     const double* b = pos + 3 * OKIN_LDG(rec + 11);
     const double* c = pos + 3 * OKIN_LDG(rec + 12);
@@ -1347,7 +1348,7 @@ OKIN_HD void okin_corner_metrics(const OkinProgram& pr, double* sm, const int32_
     ok = ok && m >= OKIN_GEOM_EPS;
     n2[0] /= m; n2[1] /= m; n2[2] /= m;
     d2 = -(n2[0] * a[0] + n2[1] * a[1] + n2[2] * a[2]);
-  } else {  // MacPherson: plane through the strut top normal to the strut axis (macpherson.py:346-355)
+  } else if (ic_kind == OKIN_IC_MAC) {  // plane through the strut top normal to the strut axis (macpherson.py:346-355)
     const double* ball = pos + 3 * OKIN_LDG(rec + 9);
     const double* top = pos + 3 * OKIN_LDG(rec + 10);
     n2[0] = top[0] - ball[0]; n2[1] = top[1] - ball[1]; n2[2] = top[2] - ball[2];

@@ -169,6 +169,7 @@ OKIN_HD T okin_distance(OkinV3<T> a, OkinV3<T> b) {
 #define OKIN_MCORNER_STRIDE 24
 #define OKIN_IC_DW 0   // planes (ic0,ic1,ic2) upper and (ic3,ic4,ic5) lower
 #define OKIN_IC_MAC 1  // plane (ic0,ic1,ic2) lower arm; strut axis ic2 -> ic3 through ic3
+#define OKIN_IC_NONE 2 // the architecture declares no instant centres: those columns are NaN (None)
 #define OKIN_MF_FRONT 1
 #define OKIN_MF_REAR 2
 #define OKIN_MF_HAS_BIAS 4

@@ -533,7 +533,7 @@ def run_result_files() -> None:
     # setup-reference pose of analyze_sweep (core/analysis.py:182-216) for a corner and an axle
     from kinematics.core.analysis import analyze_sweep
     analysis = {}
-    for case in ("c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll"):
+    for case in ("c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll", "c4_tbar_roll"):
         g, sw = CASES[case]
         sus = build_suspension(g)
         res = analyze_sweep(sus, build_sweep(sw, sus))
@@ -545,6 +545,8 @@ def run_result_files() -> None:
             "setup_metrics": ref.metrics, "setup_corner_metrics": ref.corner_metrics,
             "setup_positions": {k: list(v) for k, v in ref.positions.items()},
             "last_frame_metrics": res.frames[-1].metrics,
+            "point_keys": res.point_keys,
+            "last_frame_positions": {k: list(v) for k, v in res.frames[-1].positions.items()},
             "diagnostics": [[d.step, str(d.category.value)] for d in res.diagnostics],
         }
     json.dump({"metric_units": units, "case": "c1_dw_corner_bump_steer", "analysis": analysis},

@@ -30,7 +30,7 @@ def test_result_files(emu_device, tmp_path):
     G.test_result_files_match_reference(tmp_path)
 
 
-@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll"])
+@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll", "c4_tbar_roll"])
 def test_analyze_sweep(emu_device, case):
     G.test_analyze_sweep_matches_reference(case)
 

@@ -437,10 +437,11 @@ def test_result_files_match_reference(tmp_path):
     assert back.column("instance_index").to_pylist()[-1] == 2
 
 
-@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll"])
+@pytest.mark.parametrize("case", ["c1_dw_corner_bump_steer", "c3_rocker_ubar_coilover_roll", "c4_tbar_roll"])
 def test_analyze_sweep_matches_reference(case):
-    """analyze_sweep (reference core/analysis.py:219-316): frame / key structure, sweep parameters
-    and the solved setup-reference pose with its metric rows."""
+    """analyze_sweep (reference core/analysis.py:219-316): frame / key structure, sweep parameters,
+    the named positions of the frames incl. the presentation points (rocker-pickup axis projections,
+    T-bar midpoint; presentation.py:295-348) and the solved setup-reference pose with its metric rows."""
     from open_kinematics_b200.core.analysis import analyze_sweep
     ref = json.load(open(os.path.join(GOLDEN, "result_files.json")))["analysis"][case]
     meta, _ = load_golden(case)
@@ -452,10 +453,14 @@ def test_analyze_sweep_matches_reference(case):
     assert [[d.step, str(d.category.value)] for d in res.diagnostics] == ref["diagnostics"]
     setup = res.references["setup"]
     assert setup.label == "Setup"
-    for name, xyz in ref["setup_positions"].items():      # the reference lists its presentation points
-        if name in setup.positions:
-            assert np.abs(np.array(setup.positions[name]) - np.array(xyz)).max() <= 1e-4, name
-    assert len(set(ref["setup_positions"]) & set(setup.positions)) >= len(meta["output_points"])
+    # every name the reference lists (physical, projected, midpoint) is produced, with its value
+    assert set(res.point_keys) == set(ref["point_keys"]) == set(setup.positions) == set(res.frames[-1].positions)
+    derived = [n for n in ref["point_keys"] if "_axis_projection_" in n or n.endswith("_t_bar_midpoint")]
+    assert res.point_keys[-len(derived):] == derived if derived else True
+    for name, xyz in ref["setup_positions"].items():
+        assert np.abs(np.array(setup.positions[name]) - np.array(xyz)).max() <= 1e-4, name
+    for name, xyz in ref["last_frame_positions"].items():
+        assert np.abs(np.array(res.frames[-1].positions[name]) - np.array(xyz)).max() <= 1e-4, name
 
     def check_row(got, want, label):
         assert list(got) == list(want), label

@@ -153,3 +153,32 @@ def test_tied_derivative_drivers_raise_like_the_reference():
     assert row["camber"] == 1.5 and row["deriv_camber_wrt_wheel_travel"] is None
     with pytest.raises(ValueError, match="Ambiguous derivative driver for column 'deriv_camber_wrt_wheel_travel'"):
         rows_from_columns(np.array([1.5, np.inf]), locations, is_axle=False)
+
+
+def test_resolve_positions_errors_like_the_reference():
+    """presentation.py:304-329: a missing assembly point or a zero-length rotation axis raises."""
+    import numpy as np
+    import pytest
+    from helpers import build_case, load_golden
+    from open_kinematics_b200.core.enums import PointID
+    from open_kinematics_b200.core.presentation import presentation_points, resolve_positions
+    from open_kinematics_b200.core.primitives.point_ref import PointRef, Side
+    meta, arr = load_golden("c4_tbar_roll")
+    sus, _ = build_case(meta)
+    projections, midpoints = presentation_points(sus)
+    assert len(projections) == 4 and len(midpoints) == 1
+    from helpers import key_from_name
+    keys = [key_from_name(n) for n in meta["point_keys"]]
+    positions = {k: arr["positions_tight"][0, i] for i, k in enumerate(keys)}
+    named = resolve_positions(positions, sus)
+    mid = np.array(named["left_droplink_t_bar_right_droplink_t_bar_midpoint"])
+    assert np.allclose(mid, 0.5 * (positions[PointRef(Side.LEFT, PointID.DROPLINK_T_BAR)]
+                                   + positions[PointRef(Side.RIGHT, PointID.DROPLINK_T_BAR)]))
+    broken = dict(positions)
+    del broken[PointRef(Side.LEFT, PointID.PUSHROD_INBOARD)]
+    with pytest.raises(ValueError, match="Cannot resolve missing assembly points"):
+        resolve_positions(broken, sus)
+    flat = dict(positions)
+    flat[PointRef(Side.LEFT, PointID.ROCKER_AXIS_B)] = flat[PointRef(Side.LEFT, PointID.ROCKER_AXIS_A)]
+    with pytest.raises(ValueError, match="zero-length rotation axis"):
+        resolve_positions(flat, sus)

@@ -97,6 +97,11 @@ def main() -> None:
     own_t = torch.tensor(own, device=dev)
     p_left, p_right = torch.tensor(pairs[:, 0], device=dev), torch.tensor(pairs[:, 1], device=dev)
     flip = torch.tensor([1.0, -1.0, 1.0], device=dev, dtype=torch.float64)
+    # centre-line points keep y = 0 (T-bar pivot: the reference's build validation, axle/mechanisms.py:626-643)
+    from open_kinematics_b200.core.primitives.point_ref import Side
+    centre = [i for i, k in enumerate(prog.in_keys) if getattr(k, "side", None) is Side.CENTER
+              and abs(float(solver.nominal_hardpoints()[3 * i + 1])) < 1e-9]
+    centre_t = torch.tensor(centre, device=dev, dtype=torch.int64)
     S, nin, nout, nm = steps, prog.n_in, prog.n_out, len(prog.metric_names)
     chunk = min(args.chunk, max(count, 1))
     # chunk buffers, reused
@@ -132,6 +137,8 @@ def main() -> None:
             grid = doe_levels(begin + lo, c, n_factors, levels, dev)
             for f, (slot, axis) in enumerate(factor_slots):
                 hp[:c, slot, axis] += 2.0 * grid[:, f]
+        if centre:
+            hp[:c, centre_t, 1] = 0.0
         hp[:c, p_right, :] = hp[:c, p_left, :] * flip
 
     def launch(c: int) -> None:
