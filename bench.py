@@ -542,7 +542,8 @@ def run_cuda(args) -> None:
                 "mean_nfev_per_state": mean_iters, "outputs": "positions(all points)+nfev+max_residual+status",
                 "value_is": "device-resident (inputs and outputs in HBM); e2e is the wall-clock metric of SURVEY.md 8(d)",
                 "l2_policy": f"inputs+outputs per launch {n_inst * (nin3 * 8 + S * nout3 * 8) / 1e9:.2f} GB >> 126 MB L2",
-                "launch": geo, "layout_tuning": prog.stats.get("layout_tuning"), "numa_local_cpus": local_cpus,
+                "launch": geo, "lean_kernel_family": topo.lean_calibration(local),
+                "layout_tuning": prog.stats.get("layout_tuning"), "numa_local_cpus": local_cpus,
                 "process_model": "one process, okin_solve_batch splits the instance range over the devices "
                                  "(one host thread each)" if single else "one process per GPU (torchrun)",
                 "e2e_api": "BatchSolver.solve(hardpoints, devices=..., out=previous result) on page-locked NumPy "

@@ -180,6 +180,11 @@ int okin_shard_range(int64_t n_instances, int32_t shard, int32_t n_shards, int64
 int okin_launch_geometry(okin_topology* topo, int32_t device, int64_t n_instances, int32_t* grid, int32_t* block,
                          int32_t* smem_bytes, int32_t* ctas_per_sm);
 
+/* Which lean kernel family (positions + solver statistics only) this topology uses on `device`:
+ * registers = 128 or 168 once the first large batch has timed both on that device, 0 before;
+ * the two calibration times in ms (0 when fixed by OKIN_LEAN_REGS or not yet run). */
+int okin_lean_calibration(okin_topology* topo, int32_t device, int32_t* registers, double* ms_wide, double* ms_128);
+
 /* Dependent-DFMA-chain microbenchmark: measured fp64 FMA peak of `device` in TFLOP/s
  * (the roofline denominator; MEASURED_PEAKS.json carries no fp64 figure). */
 int okin_fp64_peak(int32_t device, double* tflops_out);

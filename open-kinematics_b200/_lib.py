@@ -87,6 +87,7 @@ SIGNATURES = {
     "okin_launch_geometry": (ctypes.c_int, [
         ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, c_i32p, c_i32p, c_i32p, c_i32p]),
     "okin_fp64_peak": (ctypes.c_int, [ctypes.c_int32, c_f64p]),
+    "okin_lean_calibration": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int32, c_i32p, c_f64p, c_f64p]),
     "okin_host_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     "okin_host_free": (ctypes.c_int, [ctypes.c_void_p]),
     "okin_last_error": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32]),
@@ -213,6 +214,13 @@ class DeviceTopology:
         check(load().okin_launch_geometry(self.handle, device, n_instances, *[ctypes.byref(v) for v in vals]),
               "okin_launch_geometry")
         return dict(zip(("grid", "block", "smem_bytes", "ctas_per_sm"), (v.value for v in vals)))
+
+    def lean_calibration(self, device: int = 0) -> dict:
+        """Lean kernel family chosen for this topology on ``device`` (see ``okin_lean_calibration``)."""
+        regs, wide, narrow = ctypes.c_int32(), ctypes.c_double(), ctypes.c_double()
+        check(load().okin_lean_calibration(self.handle, device, ctypes.byref(regs), ctypes.byref(wide),
+                                           ctypes.byref(narrow)), "okin_lean_calibration")
+        return {"registers": regs.value, "ms_168": wide.value, "ms_128": narrow.value}
 
     def close(self) -> None:
         if self.handle:

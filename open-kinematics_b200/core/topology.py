@@ -300,8 +300,6 @@ def compile_topology(
     use); ``False`` bakes the explicit constants of the given constraint objects
     (the single-instance ``solve_suspension_sweep`` boundary).
     """
-    # gather lists padded to a multiple of list_pad (kernel experiments: csrc built with OKIN_PAIR_LOOPS=1)
-    list_pad = int(os.environ.get("OKIN_LIST_PAD", "1"))
     positions = initial_state.positions
     manager = DerivedPointsManager(derived_spec)
     derived_keys = list(manager.update_order)
@@ -559,13 +557,9 @@ def compile_topology(
                 contrib.setdefault((pa, pb), []).append(word)
     tasks = sorted(block_id.items(), key=lambda kv: (-len(contrib.get(kv[0], [])), kv[1]))
     asm_ptr, asm_task, asm_con = [0], [], []
-    NULL_RG = "NULL_RG"           # rg-relative offset of the zero block, known once the layout is
     for (i, j), b in tasks:       # heaviest first: lanes take tasks round-robin
         asm_task.append(b | (D["OKIN_ASM_DIAG"] if i == j else 0))
-        words = contrib.get((i, j), [])
-        asm_con.extend(words)
-        if list_pad == 2 and len(words) % 2:
-            asm_con.append(NULL_RG)
+        asm_con.extend(contrib.get((i, j), []))
         asm_ptr.append(len(asm_con))
     NAT = len(asm_task)
 
@@ -578,10 +572,7 @@ def compile_topology(
             per_block.setdefault(pos_of[cblk], []).append(
                 (off_e << 16) | row_index[id(row)] | (D["OKIN_CON_NEG"] if neg else 0))
     for j in range(NF):
-        words = per_block.get(j, [])
-        g_con.extend(words)
-        if list_pad == 2 and len(words) % 2:
-            g_con.append(NULL_RG)
+        g_con.extend(per_block.get(j, []))
         g_ptr.append(len(g_con))
 
     # ---- left-looking update lists, scale tasks -------------------------------
@@ -598,14 +589,11 @@ def compile_topology(
     lev_upd, upd_dst, upd_ptr, upd_con = [0], [], [0], []
     lev_scl, scl = [0], []
     lev_upd_mid, lev_scl_mid = [], []   # end of the tasks a solve without tangents needs, per level
-    LB, VEC, ZERO = "LB", "VEC", "ZERO"      # symbolic bases, resolved once the layout is known
-    NULL_UPD = ((ZERO, 0), (ZERO, 0))        # a = 0: contributes nothing (pads a list to even length)
+    LB, VEC = "LB", "VEC"      # symbolic bases, resolved once the layout is known
 
     def add_update(dst, cons):
         upd_dst.append(dst)
         upd_con.extend(cons)
-        if list_pad == 2 and len(cons) % 2:
-            upd_con.append(NULL_UPD)
         upd_ptr.append(len(upd_con))
 
     for lv in range(NLEV):
@@ -642,13 +630,9 @@ def compile_topology(
     for j in range(NF):
         for k in cols_with[j]:
             fw_con.append(((LB, boff(j, k)), 3 * k))
-        if list_pad == 2 and len(cols_with[j]) % 2:
-            fw_con.append(((ZERO, 0), 0))          # null block: pads the list to even length
         fw_ptr.append(len(fw_con))
         for i in struct[j]:
             bw_con.append(((LB, boff(i, j)), 3 * i))
-        if list_pad == 2 and len(struct[j]) % 2:
-            bw_con.append(((ZERO, 0), 0))
         bw_ptr.append(len(bw_con))
     lev_col_ptr, lev_col = [0], []
     for lv in range(NLEV):
@@ -696,7 +680,6 @@ def compile_topology(
     layout = {
         "OKIN_H_OFF_POS": take(3 * P), "OKIN_H_OFF_CST": take(max(ncst, 1)), "OKIN_H_OFF_R": take(NROW + NREP),
         "OKIN_H_OFF_RG": take(max(nrg, 1)), "OKIN_H_OFF_DBLK": take(max(ndb, 1)),
-        "OKIN_H_OFF_ZERO": take(9),      # a 3x3 block of zeros: operand of the null contributions
         "OKIN_H_OFF_LB": take(9 * NB),
         "OKIN_H_OFF_RED": take(32), "OKIN_H_OFF_PAR": take(max(len(par_val), 1)),
         "OKIN_H_OFF_TGT": take(2 * D["OKIN_MAX_TARGETS"]),
@@ -708,12 +691,7 @@ def compile_topology(
     take(NT * N)                         # vec[1..NT]: tangents (contiguous with vec[0])
     if off >= 65536:
         raise ValueError("Per-instance state exceeds the 16-bit shared-memory offset range")
-    base = {LB: layout["OKIN_H_OFF_LB"], VEC: layout["OKIN_H_OFF_VEC"], ZERO: layout["OKIN_H_OFF_ZERO"]}
-    null_rg = layout["OKIN_H_OFF_ZERO"] - layout["OKIN_H_OFF_RG"]
-    if not 0 <= null_rg < 32768:
-        raise ValueError("Zero block out of the 15-bit row-gradient offset range")
-    asm_con = [((null_rg << 16) | null_rg) if w == NULL_RG else w for w in asm_con]
-    g_con = [(null_rg << 16) if w == NULL_RG else w for w in g_con]
+    base = {LB: layout["OKIN_H_OFF_LB"], VEC: layout["OKIN_H_OFF_VEC"]}
 
     # ---- optional: bank-conflict-aware placement of the factor blocks (core/layout_tuning.py) ------
     slot = list(range(NB))
@@ -859,8 +837,6 @@ def compile_topology(
         s = D[name]
         hdr[D["OKIN_H_SEC0"] + 2 * s] = cursor
         hdr[D["OKIN_H_SEC0"] + 2 * s + 1] = arr.size
-        if arr.size % 2:                 # sections start on even words: contribution pairs are read 64 bits wide
-            arr = np.concatenate([arr, np.zeros(1, np.int64)])
         chunks.append((arr & 0xFFFFFFFF).astype(np.uint32).view(np.int32))   # flag bit 31 wraps to sign
         cursor += arr.size
     iblob = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)

@@ -27,12 +27,19 @@
 #include "../../include/okin.h"
 #include "okin_core.cuh"
 
-#define OKIN_MAX_THREADS 512   // 16 warps: the most a full-output CTA may hold (register cap 128 per thread)
-#define OKIN_REGS_PER_THREAD 128
-// The lean instantiation (positions + solver statistics only) owns a shorter slice; with more warps
-// per CTA its register cap drops accordingly (65536 / threads).
-#ifndef OKIN_LEAN_MAX_THREADS
-#define OKIN_LEAN_MAX_THREADS 512
+// Kernel families.  The register cap follows from the CTA size limit (65536 / threads):
+//   full outputs        512 threads -> 128 registers, up to 16 warps per SM
+//   lean, 128 registers 512 threads                    (small topologies, long sweeps: occupancy wins)
+//   lean, 168 registers 384 threads -> up to 12 warps  (ptxas only keeps the twelve operand loads of a
+//                       gather-loop trip in flight when it is not squeezed for registers; at 128 it sinks
+//                       every LDS to its DFMA, profiles/r02_*)
+// Which lean family is faster depends on the topology (measured: flagship axle 168, corners and the
+// 101-step T-bar axle 128), so the first large launch of a topology on a device times both.
+#define OKIN_MAX_THREADS 512
+#define OKIN_LEAN_WIDE_THREADS 384
+enum { OKIN_FAM_LEAN_WIDE = 0, OKIN_FAM_FULL = 1, OKIN_FAM_LEAN = 2, OKIN_FAM_COUNT = 3 };
+#ifndef OKIN_ROUND
+#define OKIN_ROUND 1             // instances per warp in one CTA chunk of the dynamic instance queue
 #endif
 #define OKIN_MAX_DEVICES 16
 #define OKIN_PIPE_SLOTS 3        // streams / workspace slots of the host-buffer pipeline
@@ -65,8 +72,10 @@ struct DeviceCopy {
   int32_t* ib = nullptr;
   double* fb = nullptr;
   int num_sms = 0;
-  // launch shape per instantiation family: [0] lean (short slice), [1] full outputs
-  struct Shape { int ctas_per_sm = 0, warps_per_cta = 0, smem_bytes = 0; } shape[2];
+  // launch shape per kernel family (OKIN_FAM_*)
+  struct Shape { int ctas_per_sm = 0, warps_per_cta = 0, smem_bytes = 0; } shape[OKIN_FAM_COUNT];
+  int lean_family = -1;          // OKIN_FAM_LEAN or OKIN_FAM_LEAN_WIDE once timed on this device, -1 before
+  double lean_tune_ms[2] = {0.0, 0.0};   // calibration times {wide, 128-register}
   int table_doubles = 0;
   int smem_optin = 0;
   // grow-only workspace for the host-buffer entry point
@@ -87,13 +96,11 @@ struct okin_topology {
 // Shared memory of a CTA = [topology tables (int32 blob)] [one state slice per warp].  The tables are
 // copied once per (persistent) CTA so that every index lookup of the interpreter is a shared-memory
 // load instead of a global one (ncu round 1: long-scoreboard stalls on __ldg were the top stall).
-// Register cap 128 = 65536 / 512: up to 16 resident warps per SM in any CTA shape the host picks
-// (only the once-per-instance shim pre-solve spills at that cap).
-template <bool FULL, bool SHIM>
-__global__ void __launch_bounds__(FULL ? OKIN_MAX_THREADS : OKIN_LEAN_MAX_THREADS, 1)
+template <bool FULL, bool SHIM, int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ ib, const double* __restrict__ fb,
                   long long n_instances, int n_steps, OkinSolverCfg cfg, okin_batch_io io, int n_iblob,
-                  int table_doubles) {
+                  int table_doubles, unsigned long long* __restrict__ counter) {
   // [section pointers][header][hot tables][one state slice per warp]
   const int32_t** sec = reinterpret_cast<const int32_t**>(okin_smem);
   int32_t* shdr = reinterpret_cast<int32_t*>(okin_smem + OKIN_S_COUNT);
@@ -109,33 +116,51 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
   const int warps_per_cta = blockDim.x >> 5;
   double* sm = okin_smem + table_doubles + (size_t)warp * hdr[FULL ? OKIN_H_SMEM_DOUBLES : OKIN_H_SMEM_DOUBLES_LEAN];
   const int nin = hdr[OKIN_H_NIN], nout = hdr[OKIN_H_NOUT], nt = hdr[OKIN_H_NT], n = 3 * hdr[OKIN_H_NF];
-  const long long stride = (long long)gridDim.x * warps_per_cta;
-  // The trip count is uniform over the CTA and every round starts with a CTA barrier: the warps
-  // of a CTA run the same code region at the same time, which keeps the (large) interpreter in
-  // the instruction cache.  Without it the warps of a long-lived persistent CTA drift apart and
-  // throughput drops ~10 % between a 2 k-instance and a 1 M-instance launch (measured).
-  for (long long base = (long long)blockIdx.x * warps_per_cta; base < n_instances; base += stride) {
+  // Instances are claimed dynamically.  A CTA takes a chunk of OKIN_ROUND instances per warp from the
+  // global counter; its warps claim instances inside the chunk one at a time (shared counter), so a
+  // warp whose instance is slow (a failing sweep costs several normal ones) simply claims fewer and
+  // nobody waits for it until the chunk is used up.  The two CTA barriers per chunk re-align the
+  // warps: they run the same code region at about the same time, which keeps the (large) interpreter
+  // in the instruction cache (without any barrier the warps of a long-lived persistent CTA drift
+  // apart and throughput drops ~10 % between a 2 k-instance and a 1 M-instance launch, measured in
+  // round 1 with a barrier per instance; OKIN_ROUND == 1 is that scheme with a dynamic chunk).
+  __shared__ long long s_base;
+  __shared__ int s_next;
+  const int quota = warps_per_cta * OKIN_ROUND;
+  for (;;) {
     __syncthreads();
-    const long long i = base + warp;
-    if (i >= n_instances) continue;
-    OkinOutputs out;
-    out.positions = io.positions ? io.positions + (size_t)i * n_steps * 3 * nout : nullptr;
-    out.iters = io.iters ? io.iters + (size_t)i * n_steps : nullptr;
-    out.max_residual = io.max_residual ? io.max_residual + (size_t)i * n_steps : nullptr;
-    out.tangents = io.tangents ? io.tangents + (size_t)i * n_steps * nt * n : nullptr;
-    out.velocities = io.velocities ? io.velocities + (size_t)i * n_steps * nt * 3 * nout : nullptr;
-    out.health = io.tangent_health ? io.tangent_health + (size_t)i * n_steps * 2 : nullptr;
-    out.metrics = io.metrics ? io.metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
-    out.design = io.design ? io.design + (size_t)i * 3 * nout : nullptr;
-    out.diagnostics = io.diagnostics ? io.diagnostics + (size_t)i * n_steps * hdr[OKIN_H_NDIAG] : nullptr;
-    out.status = io.status + i;
-    out.failed_step = io.failed_step + i;
-    out.worst_row = io.worst_row ? io.worst_row + i : nullptr;
-    okin_sweep<FULL, SHIM>(pr, sm, io.hardpoints + (size_t)i * 3 * nin,
-               io.params ? io.params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr,
-               io.instance_targets ? io.instance_targets + (size_t)i * nt * n_steps : io.target_values, n_steps,
-               cfg, out);
-    __syncwarp();
+    if (threadIdx.x == 0) {
+      s_base = (long long)atomicAdd(counter, (unsigned long long)quota);
+      s_next = 0;
+    }
+    __syncthreads();
+    const long long base = s_base;
+    if (base >= n_instances) break;          // uniform over the CTA
+    for (;;) {
+      int k = 0;
+      if ((threadIdx.x & 31) == 0) k = atomicAdd(&s_next, 1);
+      k = __shfl_sync(0xffffffffu, k, 0);
+      const long long i = base + k;
+      if (k >= quota || i >= n_instances) break;
+      OkinOutputs out;
+      out.positions = io.positions ? io.positions + (size_t)i * n_steps * 3 * nout : nullptr;
+      out.iters = io.iters ? io.iters + (size_t)i * n_steps : nullptr;
+      out.max_residual = io.max_residual ? io.max_residual + (size_t)i * n_steps : nullptr;
+      out.tangents = io.tangents ? io.tangents + (size_t)i * n_steps * nt * n : nullptr;
+      out.velocities = io.velocities ? io.velocities + (size_t)i * n_steps * nt * 3 * nout : nullptr;
+      out.health = io.tangent_health ? io.tangent_health + (size_t)i * n_steps * 2 : nullptr;
+      out.metrics = io.metrics ? io.metrics + (size_t)i * n_steps * hdr[OKIN_H_NM] : nullptr;
+      out.design = io.design ? io.design + (size_t)i * 3 * nout : nullptr;
+      out.diagnostics = io.diagnostics ? io.diagnostics + (size_t)i * n_steps * hdr[OKIN_H_NDIAG] : nullptr;
+      out.status = io.status + i;
+      out.failed_step = io.failed_step + i;
+      out.worst_row = io.worst_row ? io.worst_row + i : nullptr;
+      okin_sweep<FULL, SHIM>(pr, sm, io.hardpoints + (size_t)i * 3 * nin,
+                 io.params ? io.params + (size_t)i * hdr[OKIN_H_NPARAM] : nullptr,
+                 io.instance_targets ? io.instance_targets + (size_t)i * nt * n_steps : io.target_values, n_steps,
+                 cfg, out);
+      __syncwarp();
+    }
   }
 }
 
@@ -175,6 +200,20 @@ __global__ void okin_dfma_kernel(double* out, int iters, double a, double b) {
 
 namespace {
 
+const void* kernel_of(int fam, bool shim) {
+  switch (fam) {
+    case OKIN_FAM_FULL:
+      return shim ? (const void*)okin_sweep_kernel<true, true, OKIN_MAX_THREADS>
+                  : (const void*)okin_sweep_kernel<true, false, OKIN_MAX_THREADS>;
+    case OKIN_FAM_LEAN:
+      return shim ? (const void*)okin_sweep_kernel<false, true, OKIN_MAX_THREADS>
+                  : (const void*)okin_sweep_kernel<false, false, OKIN_MAX_THREADS>;
+    default:
+      return shim ? (const void*)okin_sweep_kernel<false, true, OKIN_LEAN_WIDE_THREADS>
+                  : (const void*)okin_sweep_kernel<false, false, OKIN_LEAN_WIDE_THREADS>;
+  }
+}
+
 int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
   if (device < 0 || device >= OKIN_MAX_DEVICES) return fail(OKIN_ERR_USAGE, "device id out of range");
   std::lock_guard<std::mutex> lock(t->mu);
@@ -199,10 +238,11 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
         OKIN_S_COUNT + (int)((((size_t)t->hdr[OKIN_H_NHOT] + OKIN_HDR_SIZE) * sizeof(int32_t) + 7) / 8);
     const size_t table_bytes = (size_t)d.table_doubles * 8;
     const size_t sm_budget = prop.sharedMemPerMultiprocessor;
-    for (int full = 0; full < 2; ++full) {
+    for (int fam = 0; fam < OKIN_FAM_COUNT; ++fam) {
+      const bool full = fam == OKIN_FAM_FULL;
       const size_t slice_bytes =
           (size_t)t->hdr[full ? OKIN_H_SMEM_DOUBLES : OKIN_H_SMEM_DOUBLES_LEAN] * sizeof(double);
-      const int max_threads = full ? OKIN_MAX_THREADS : OKIN_LEAN_MAX_THREADS;
+      const int max_threads = fam == OKIN_FAM_LEAN_WIDE ? OKIN_LEAN_WIDE_THREADS : OKIN_MAX_THREADS;
       const int regs_per_thread = (int)(prop.regsPerMultiprocessor / max_threads) & ~7;
       int best_w = 0, best_ctas = 0;
       const char* forced = getenv("OKIN_WARPS_PER_CTA");     // kernel experiments
@@ -213,20 +253,22 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
         int ctas = (int)(sm_budget / (cta_bytes + 1024));
         ctas = std::min(ctas, (int)(prop.regsPerMultiprocessor / (regs_per_thread * 32 * w)));
         ctas = std::min(ctas, 32);
-        if (ctas * w > best_w * best_ctas || (ctas * w == best_w * best_ctas && w < best_w && ctas * w > 0)) {
+        // most resident warps; on a tie the CTA shape closest to 6-8 warps (measured: 6 x 2 CTAs beats
+        // 3 x 4 -- fewer copies of the tables -- and 12 x 1 -- a barrier group of 12 warps)
+        const bool better_shape = best_w == 0 || (w <= 8 && w > best_w) || (best_w > 8 && w < best_w);
+        if (ctas * w > best_w * best_ctas || (ctas * w == best_w * best_ctas && ctas * w > 0 && better_shape)) {
           best_w = w;
           best_ctas = ctas;
         }
       }
       if (best_w == 0 || best_ctas == 0)
         return fail(OKIN_ERR_USAGE, "topology needs more shared memory per CTA than the device offers");
-      DeviceCopy::Shape& sh = d.shape[full];
+      DeviceCopy::Shape& sh = d.shape[fam];
       sh.warps_per_cta = best_w;
       sh.smem_bytes = (int)(table_bytes + best_w * slice_bytes);
       sh.ctas_per_sm = 1 << 30;
-      const void* kernels[2] = {full ? (const void*)okin_sweep_kernel<true, false> : (const void*)okin_sweep_kernel<false, false>,
-                                full ? (const void*)okin_sweep_kernel<true, true> : (const void*)okin_sweep_kernel<false, true>};
-      for (const void* kernel : kernels) {
+      for (int shim = 0; shim < 2; ++shim) {
+        const void* kernel = kernel_of(fam, shim != 0);
         OKIN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh.smem_bytes));
         int ctas = 0;
         OKIN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, best_w * 32, sh.smem_bytes));
@@ -234,11 +276,42 @@ int ensure_device(okin_topology* t, int device, DeviceCopy** out) {
       }
       if (sh.ctas_per_sm < 1) return fail(OKIN_ERR_CUDA, "kernel does not fit on an SM");
     }
+    if (const char* fixed = getenv("OKIN_LEAN_REGS"))        // 128 | 168: skip the calibration
+      d.lean_family = atoi(fixed) == 128 ? OKIN_FAM_LEAN : OKIN_FAM_LEAN_WIDE;
     for (int k = 0; k < OKIN_PIPE_SLOTS; ++k)
       OKIN_CUDA(cudaStreamCreateWithFlags(&d.streams[k], cudaStreamNonBlocking));
     d.ready = true;
   }
   *out = &d;
+  return OKIN_OK;
+}
+
+// One launch of a kernel family over [0, n_instances) on `stream`.
+int launch_family(okin_topology* t, DeviceCopy* d, int fam, const OkinSolverCfg& c, cudaStream_t stream,
+                  int64_t n_instances, int32_t n_steps, const okin_batch_io& io) {
+  const DeviceCopy::Shape& sh = d->shape[fam];
+  const int w = sh.warps_per_cta;
+  const int64_t needed = (n_instances + w - 1) / w;
+  const int64_t resident = (int64_t)d->num_sms * sh.ctas_per_sm;
+  const int grid = (int)std::min<int64_t>(needed, resident);
+  const void* kernel = kernel_of(fam, t->hdr[OKIN_H_NSHIM] > 0);
+  // The attribute belongs to the kernel function of this device context, not to a topology: another
+  // live topology may have lowered it since ensure_device ran, so it is set before every launch.
+  std::lock_guard<std::mutex> launch_lock(g_launch_mu[d->device]);
+  OKIN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh.smem_bytes));
+  // instance queue head of this launch (stream-ordered allocation: concurrent launches on other
+  // streams have their own)
+  unsigned long long* counter = nullptr;
+  OKIN_CUDA(cudaMallocAsync(&counter, sizeof(unsigned long long), stream));
+  OKIN_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+  long long n = (long long)n_instances;
+  int n_iblob = (int)t->ib.size();
+  OkinSolverCfg cfg = c;
+  okin_batch_io bio = io;
+  void* args[] = {&d->hdr, &d->ib, &d->fb, &n, &n_steps, &cfg, &bio, &n_iblob, &d->table_doubles, &counter};
+  const cudaError_t launch_err = cudaLaunchKernel(kernel, dim3(grid), dim3(w * 32), args, sh.smem_bytes, stream);
+  OKIN_CUDA(cudaFreeAsync(counter, stream));
+  OKIN_CUDA(launch_err);
   return OKIN_OK;
 }
 
@@ -249,23 +322,38 @@ int launch(okin_topology* t, DeviceCopy* d, const okin_solver_cfg* cfg, cudaStre
                   cfg->use_predictor};
   // lean instantiation when no per-state tangent / metric / diagnostic output is wanted
   const bool full = io.tangents || io.velocities || io.tangent_health || io.metrics || io.diagnostics;
-  const bool shim = t->hdr[OKIN_H_NSHIM] > 0;
-  const DeviceCopy::Shape& sh = d->shape[full ? 1 : 0];
-  const int w = sh.warps_per_cta;
-  const int64_t needed = (n_instances + w - 1) / w;
-  const int64_t resident = (int64_t)d->num_sms * sh.ctas_per_sm;
-  const int grid = (int)std::min<int64_t>(needed, resident);
-  auto kernel = full ? (shim ? okin_sweep_kernel<true, true> : okin_sweep_kernel<true, false>)
-                     : (shim ? okin_sweep_kernel<false, true> : okin_sweep_kernel<false, false>);
-  {
-    // The attribute belongs to the kernel function of this device context, not to a topology: another
-    // live topology may have lowered it since ensure_device ran, so it is set before every launch.
-    std::lock_guard<std::mutex> launch_lock(g_launch_mu[d->device]);
-    OKIN_CUDA(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh.smem_bytes));
-    kernel<<<grid, w * 32, sh.smem_bytes, stream>>>(
-        d->hdr, d->ib, d->fb, (long long)n_instances, n_steps, c, io, (int)t->ib.size(), d->table_doubles);
-    OKIN_CUDA(cudaGetLastError());
+  int fam = OKIN_FAM_FULL;
+  if (!full) {
+    fam = d->lean_family;
+    const int64_t sample = 4 * (int64_t)d->num_sms * std::max(d->shape[OKIN_FAM_LEAN].ctas_per_sm * d->shape[OKIN_FAM_LEAN].warps_per_cta,
+                                                              d->shape[OKIN_FAM_LEAN_WIDE].ctas_per_sm * d->shape[OKIN_FAM_LEAN_WIDE].warps_per_cta);
+    if (fam < 0 && n_instances >= 2 * sample) {
+      // Calibration, once per (topology, device): both lean families solve the same leading instances
+      // of this batch (their results are identical; the batch launch below overwrites them again).
+      cudaEvent_t e[2];
+      OKIN_CUDA(cudaEventCreate(&e[0]));
+      OKIN_CUDA(cudaEventCreate(&e[1]));
+      const int order[2] = {OKIN_FAM_LEAN_WIDE, OKIN_FAM_LEAN};
+      for (int k = 0; k < 2; ++k) {
+        int rc = launch_family(t, d, order[k], c, stream, sample, n_steps, io);   // warm-up (code, tables)
+        if (rc) return rc;
+        OKIN_CUDA(cudaEventRecord(e[0], stream));
+        rc = launch_family(t, d, order[k], c, stream, sample, n_steps, io);
+        if (rc) return rc;
+        OKIN_CUDA(cudaEventRecord(e[1], stream));
+        OKIN_CUDA(cudaEventSynchronize(e[1]));
+        float ms = 0.f;
+        OKIN_CUDA(cudaEventElapsedTime(&ms, e[0], e[1]));
+        d->lean_tune_ms[k] = ms;
+      }
+      cudaEventDestroy(e[0]);
+      cudaEventDestroy(e[1]);
+      d->lean_family = fam = d->lean_tune_ms[1] < d->lean_tune_ms[0] ? OKIN_FAM_LEAN : OKIN_FAM_LEAN_WIDE;
+    }
+    if (fam < 0) fam = OKIN_FAM_LEAN_WIDE;      // small batch: not worth timing, not recorded
   }
+  int rc = launch_family(t, d, fam, c, stream, n_instances, n_steps, io);
+  if (rc) return rc;
   if (io.diagnostics && t->hdr[OKIN_H_NDIAG] && n_steps > 0) {
     // continuity pass over the position rows the sweep kernel just wrote (same stream)
     const int stride = (n_steps - 1) | 1;   // odd: lanes walk their histories on different banks
@@ -585,12 +673,24 @@ int okin_launch_geometry(okin_topology* t, int32_t device, int64_t n_instances, 
   DeviceCopy* d = nullptr;
   int rc = ensure_device(t, device, &d);
   if (rc) return rc;
-  const DeviceCopy::Shape& sh = d->shape[0];     // the lean instantiation (positions + solver statistics)
+  // the lean family in use (positions + solver statistics), the wide one before any calibration
+  const DeviceCopy::Shape& sh = d->shape[d->lean_family >= 0 ? d->lean_family : OKIN_FAM_LEAN_WIDE];
   const int64_t needed = (n_instances + sh.warps_per_cta - 1) / sh.warps_per_cta;
   if (grid) *grid = (int32_t)std::min<int64_t>(needed, (int64_t)d->num_sms * sh.ctas_per_sm);
   if (block) *block = sh.warps_per_cta * 32;
   if (smem_bytes) *smem_bytes = sh.smem_bytes;
   if (ctas_per_sm) *ctas_per_sm = sh.ctas_per_sm;
+  return OKIN_OK;
+}
+
+int okin_lean_calibration(okin_topology* t, int32_t device, int32_t* registers, double* ms_wide, double* ms_128) {
+  if (!t) return fail(OKIN_ERR_USAGE, "null topology");
+  DeviceCopy* d = nullptr;
+  int rc = ensure_device(t, device, &d);
+  if (rc) return rc;
+  if (registers) *registers = d->lean_family < 0 ? 0 : (d->lean_family == OKIN_FAM_LEAN ? 128 : 168);
+  if (ms_wide) *ms_wide = d->lean_tune_ms[0];
+  if (ms_128) *ms_128 = d->lean_tune_ms[1];
   return OKIN_OK;
 }
 

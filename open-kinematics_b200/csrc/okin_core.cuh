@@ -28,6 +28,9 @@
 //                        (axle/mechanisms.py:432-549)
 #pragma once
 
+#ifndef OKIN_INLINE_HOT
+#define OKIN_INLINE_HOT 1
+#endif
 #include "okin_defs.h"
 #include "okin_gen_constraints.cuh"
 #include "okin_metrics.cuh"
@@ -36,8 +39,14 @@
 // (each is called from several places) costs registers (255/thread) and instruction cache.
 #if defined(__CUDACC__) && !defined(OKIN_LANE_EMU)
 #define OKIN_FN __host__ __device__ __noinline__
+#if OKIN_INLINE_HOT
+#define OKIN_FN_HOT __host__ __device__ __forceinline__
+#else
+#define OKIN_FN_HOT OKIN_FN
+#endif
 #else
 #define OKIN_FN inline
+#define OKIN_FN_HOT inline
 #endif
 
 #if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
@@ -110,26 +119,12 @@ OKIN_HD double okin_red_max(const double* red) {
 }
 #endif
 
-// Gather lists (factor update, triangular solves, assembly) are padded by the host compiler to even
-// length with null contributions (operands in the slice's zero block), so the loops below take two
-// contributions per trip without a remainder: one 64-bit index load, two independent accumulator
-// sets (the second contribution's loads do not wait for the first one's FMA chain).
-#ifndef OKIN_PAIR_LOOPS
-#define OKIN_PAIR_LOOPS 0     // 1: the topology must be compiled with list_pad = 2 (core/topology.py)
-#endif
-#ifndef OKIN_FMA_CHAIN
-#define OKIN_FMA_CHAIN 1
-#endif
-struct OkinPair { uint32_t x, y; };
-OKIN_HD OkinPair okin_pair(const int32_t* p) {
-#if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
-  const uint2 v = *reinterpret_cast<const uint2*>(p);
-  return OkinPair{v.x, v.y};
-#else
-  return OkinPair{(uint32_t)p[0], (uint32_t)p[1]};
-#endif
-}
-
+// Gather loops (factor update, triangular solves, assembly): every operand of a contribution is
+// loaded into its own variable before the first FMA.  A warp issues in order, so the shared-memory
+// latency is then paid once per contribution (twelve loads in flight) instead of once per FMA -- but
+// only if the register allocator is not squeezed: under the 128-register cap of a 16-warp CTA ptxas
+// sinks every load back to its use (LDS -> DFMA pairs through one register), which is why the lean
+// kernel runs 12 warps per SM at 168 registers (profiles/r02_*; okin_abi.cu OKIN_LEAN_MAX_THREADS).
 struct OkinProgram {
   const int32_t* hdr;  // [OKIN_HDR_SIZE]
   const int32_t* ib;   // int32 blob: at least its hot prefix hdr[OKIN_H_NHOT] (shared memory in the kernel)
@@ -435,12 +430,10 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   double* cst = sm + hdr[OKIN_H_OFF_CST];
   double* par = sm + hdr[OKIN_H_OFF_PAR];
-  double* zero = sm + hdr[OKIN_H_OFF_ZERO];
   const int nin = hdr[OKIN_H_NIN];
   const int32_t* in_point = okin_sec(pr, OKIN_S_IN_POINT);
   OKIN_PHASE_BEGIN
   for (int t = lane; t < 3 * nin; t += 32) pos[3 * OKIN_LDG(in_point + t / 3) + t % 3] = hardpoints[t];
-  if (lane < 9) zero[lane] = 0.0;
   OKIN_PHASE_END
   if (SHIM) okin_shim_presolve(pr, sm, params ? params : okin_fsec(pr, OKIN_F_PARAM_DEFAULT), invalid);
 
@@ -641,7 +634,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
 // Normal equations: A = J^T J (+ mu diag(A)) into the factor storage, g = J^T r into vec[0].
 // ---------------------------------------------------------------------------------------
 template <typename Dummy = void>
-OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_only) {
+OKIN_FN_HOT void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_only) {
   sm = OKIN_SHARED(sm);
   const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nat = hdr[OKIN_H_NAT];
@@ -662,38 +655,18 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
       // one 3x3 block of A: sum of outer products ga gb^T over the rows coupling the two points
       const int b = OKIN_LDG(aptr + t), e = OKIN_LDG(aptr + t + 1);
       double a00 = 0, a01 = 0, a02 = 0, a10 = 0, a11 = 0, a12 = 0, a20 = 0, a21 = 0, a22 = 0;
-#if OKIN_PAIR_LOOPS
-      double b00 = 0, b01 = 0, b02 = 0, b10 = 0, b11 = 0, b12 = 0, b20 = 0, b21 = 0, b22 = 0;
-      for (int q = b; q < e; q += 2) {
-        const OkinPair w = okin_pair(acon + q);
-        const double* ga = rg + ((w.x >> 16) & 0x7fffu);
-        const double* gb = rg + (w.x & 0xffffu);
-        const double* ha = rg + ((w.y >> 16) & 0x7fffu);
-        const double* hb = rg + (w.y & 0xffffu);
-        const double sg = (w.x & OKIN_CON_NEG) ? -1.0 : 1.0, sh = (w.y & OKIN_CON_NEG) ? -1.0 : 1.0;
-        const double x0 = sg * ga[0], x1 = sg * ga[1], x2 = sg * ga[2], y0 = gb[0], y1 = gb[1], y2 = gb[2];
-        const double u0 = sh * ha[0], u1 = sh * ha[1], u2 = sh * ha[2], v0 = hb[0], v1 = hb[1], v2 = hb[2];
-        a00 = fma(x0, y0, a00); a01 = fma(x0, y1, a01); a02 = fma(x0, y2, a02);
-        a10 = fma(x1, y0, a10); a11 = fma(x1, y1, a11); a12 = fma(x1, y2, a12);
-        a20 = fma(x2, y0, a20); a21 = fma(x2, y1, a21); a22 = fma(x2, y2, a22);
-        b00 = fma(u0, v0, b00); b01 = fma(u0, v1, b01); b02 = fma(u0, v2, b02);
-        b10 = fma(u1, v0, b10); b11 = fma(u1, v1, b11); b12 = fma(u1, v2, b12);
-        b20 = fma(u2, v0, b20); b21 = fma(u2, v1, b21); b22 = fma(u2, v2, b22);
-      }
-      a00 += b00; a01 += b01; a02 += b02; a10 += b10; a11 += b11; a12 += b12; a20 += b20; a21 += b21; a22 += b22;
-#else
       OKIN_UNROLL_INNER
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(acon + q);
         const double* ga = rg + ((w >> 16) & 0x7fffu);
         const double* gb = rg + (w & 0xffffu);
         const double sg = (w & OKIN_CON_NEG) ? -1.0 : 1.0;
-        const double x0 = sg * ga[0], x1 = sg * ga[1], x2 = sg * ga[2], y0 = gb[0], y1 = gb[1], y2 = gb[2];
+        const double p0 = ga[0], p1 = ga[1], p2 = ga[2], y0 = gb[0], y1 = gb[1], y2 = gb[2];
+        const double x0 = sg * p0, x1 = sg * p1, x2 = sg * p2;
         a00 = fma(x0, y0, a00); a01 = fma(x0, y1, a01); a02 = fma(x0, y2, a02);
         a10 = fma(x1, y0, a10); a11 = fma(x1, y1, a11); a12 = fma(x1, y2, a12);
         a20 = fma(x2, y0, a20); a21 = fma(x2, y1, a21); a22 = fma(x2, y2, a22);
       }
-#endif
       const int task = OKIN_LDG(atask + t);
       if (task & OKIN_ASM_DIAG) { a00 *= damp; a11 *= damp; a22 *= damp; }
       double* dst = Lb + 9 * (task & 0xffff);
@@ -702,18 +675,7 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
     } else {
       const int j = t - nat;
       const int b = OKIN_LDG(gptr + j), e = OKIN_LDG(gptr + j + 1);
-      double g0 = 0, g1 = 0, g2 = 0, h0 = 0, h1 = 0, h2 = 0;
-#if OKIN_PAIR_LOOPS
-      for (int q = b; q < e; q += 2) {
-        const OkinPair w = okin_pair(gcon + q);
-        const double* ga = rg + ((w.x >> 16) & 0x7fffu);
-        const double* ha = rg + ((w.y >> 16) & 0x7fffu);
-        const double ra = (w.x & OKIN_CON_NEG) ? -r[w.x & 0xffffu] : r[w.x & 0xffffu];
-        const double rb = (w.y & OKIN_CON_NEG) ? -r[w.y & 0xffffu] : r[w.y & 0xffffu];
-        g0 = fma(ga[0], ra, g0); g1 = fma(ga[1], ra, g1); g2 = fma(ga[2], ra, g2);
-        h0 = fma(ha[0], rb, h0); h1 = fma(ha[1], rb, h1); h2 = fma(ha[2], rb, h2);
-      }
-#else
+      double g0 = 0, g1 = 0, g2 = 0;
       OKIN_UNROLL_INNER
       for (int q = b; q < e; ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(gcon + q);
@@ -721,8 +683,7 @@ OKIN_FN void okin_assemble(const OkinProgram& pr, double* sm, double mu, bool g_
         const double res = (w & OKIN_CON_NEG) ? -r[w & 0xffffu] : r[w & 0xffffu];
         g0 = fma(ga[0], res, g0); g1 = fma(ga[1], res, g1); g2 = fma(ga[2], res, g2);
       }
-#endif
-      vec[3 * j] = -(g0 + h0); vec[3 * j + 1] = -(g1 + h1); vec[3 * j + 2] = -(g2 + h2);  // right-hand side of A h = -g
+      vec[3 * j] = -g0; vec[3 * j + 1] = -g1; vec[3 * j + 2] = -g2;  // right-hand side of A h = -g
     }
   }
   OKIN_PHASE_END
@@ -762,7 +723,7 @@ OKIN_HD void okin_write_diag_factor(double* sm, int doff, double* red, int lane)
 // carry_tangents: also run the update / scale tasks of the tangent right-hand sides vec[1..NT]
 // (ordered last in every level by the host compiler).
 template <typename Dummy = void>
-OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, bool carry_tangents) {
+OKIN_FN_HOT void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, bool carry_tangents) {
   sm = OKIN_SHARED(sm);
   const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nlev = hdr[OKIN_H_NLEV];
@@ -789,41 +750,19 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, bool 
       for (int t = ub + lane; t < ue; t += 32) {
         const int b = OKIN_LDG(uptr + t), e = OKIN_LDG(uptr + t + 1);
         double* dst = sm + OKIN_LDG(udst + t);
-        double c0 = dst[0], c1 = dst[1], c2 = dst[2], d0 = 0.0, d1 = 0.0, d2 = 0.0;
-#if OKIN_PAIR_LOOPS
-        for (int q = b; q < e; q += 2) {
-          const OkinPair w = okin_pair(ucon + q);
-          const double* a = sm + (w.x >> 16);
-          const double* B = sm + (w.x & 0xffffu);
-          const double* p = sm + (w.y >> 16);
-          const double* Q = sm + (w.y & 0xffffu);
-          const double a0 = a[0], a1 = a[1], a2 = a[2], p0 = p[0], p1 = p[1], p2 = p[2];
-          c0 = fma(-a0, B[0], c0); c1 = fma(-a0, B[3], c1); c2 = fma(-a0, B[6], c2);
-          d0 = fma(-p0, Q[0], d0); d1 = fma(-p0, Q[3], d1); d2 = fma(-p0, Q[6], d2);
-          c0 = fma(-a1, B[1], c0); c1 = fma(-a1, B[4], c1); c2 = fma(-a1, B[7], c2);
-          d0 = fma(-p1, Q[1], d0); d1 = fma(-p1, Q[4], d1); d2 = fma(-p1, Q[7], d2);
-          c0 = fma(-a2, B[2], c0); c1 = fma(-a2, B[5], c1); c2 = fma(-a2, B[8], c2);
-          d0 = fma(-p2, Q[2], d0); d1 = fma(-p2, Q[5], d1); d2 = fma(-p2, Q[8], d2);
-        }
-#else
+        double c0 = dst[0], c1 = dst[1], c2 = dst[2];
         OKIN_UNROLL_INNER
         for (int q = b; q < e; ++q) {
           const uint32_t w = (uint32_t)OKIN_LDG(ucon + q);
           const double* a = sm + (w >> 16);
           const double* B = sm + (w & 0xffffu);
           const double a0 = a[0], a1 = a[1], a2 = a[2];
-#if OKIN_FMA_CHAIN
-          c0 = fma(-a0, B[0], c0); c1 = fma(-a0, B[3], c1); c2 = fma(-a0, B[6], c2);
-          c0 = fma(-a1, B[1], c0); c1 = fma(-a1, B[4], c1); c2 = fma(-a1, B[7], c2);
-          c0 = fma(-a2, B[2], c0); c1 = fma(-a2, B[5], c1); c2 = fma(-a2, B[8], c2);
-#else
-          c0 -= a0 * B[0] + a1 * B[1] + a2 * B[2];
-          c1 -= a0 * B[3] + a1 * B[4] + a2 * B[5];
-          c2 -= a0 * B[6] + a1 * B[7] + a2 * B[8];
-#endif
+          const double b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4], b5 = B[5], b6 = B[6], b7 = B[7], b8 = B[8];
+          c0 = fma(-a0, b0, c0); c1 = fma(-a0, b3, c1); c2 = fma(-a0, b6, c2);
+          c0 = fma(-a1, b1, c0); c1 = fma(-a1, b4, c1); c2 = fma(-a1, b7, c2);
+          c0 = fma(-a2, b2, c0); c1 = fma(-a2, b5, c1); c2 = fma(-a2, b8, c2);
         }
-#endif
-        dst[0] = c0 + d0; dst[1] = c1 + d1; dst[2] = c2 + d2;
+        dst[0] = c0; dst[1] = c1; dst[2] = c2;
       }
       OKIN_PHASE_END
     }
@@ -854,7 +793,7 @@ OKIN_FN void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, bool 
 // in place.  skip_forward: vec[first] already holds L^{-1} b (the factorisation carries vec[0]
 // as an extra row).
 template <typename Dummy = void>
-OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, bool skip_forward) {
+OKIN_FN_HOT void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, bool skip_forward) {
   sm = OKIN_SHARED(sm);
   const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nlev = hdr[OKIN_H_NLEV];
@@ -874,41 +813,18 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
     for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
       const int j = OKIN_LDG(lcol + cb + t / nrhs);
       double* v = vec + (t % nrhs) * n;
-      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2], s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#if OKIN_PAIR_LOOPS
-      for (int q = OKIN_LDG(fptr + j), e = OKIN_LDG(fptr + j + 1); q < e; q += 2) {
-        const OkinPair w = okin_pair(fcon + q);
-        const double* B = Lb + (w.x >> 16);
-        const double* y = v + (w.x & 0xffffu);
-        const double* C = Lb + (w.y >> 16);
-        const double* z = v + (w.y & 0xffffu);
-        const double y0 = y[0], y1 = y[1], y2 = y[2], z0 = z[0], z1 = z[1], z2 = z[2];
-        t0 = fma(-B[0], y0, t0); t1 = fma(-B[3], y0, t1); t2 = fma(-B[6], y0, t2);
-        s0 = fma(-C[0], z0, s0); s1 = fma(-C[3], z0, s1); s2 = fma(-C[6], z0, s2);
-        t0 = fma(-B[1], y1, t0); t1 = fma(-B[4], y1, t1); t2 = fma(-B[7], y1, t2);
-        s0 = fma(-C[1], z1, s0); s1 = fma(-C[4], z1, s1); s2 = fma(-C[7], z1, s2);
-        t0 = fma(-B[2], y2, t0); t1 = fma(-B[5], y2, t1); t2 = fma(-B[8], y2, t2);
-        s0 = fma(-C[2], z2, s0); s1 = fma(-C[5], z2, s1); s2 = fma(-C[8], z2, s2);
-      }
-#else
+      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2];
       OKIN_UNROLL_INNER
       for (int q = OKIN_LDG(fptr + j); q < OKIN_LDG(fptr + j + 1); ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(fcon + q);
         const double* B = Lb + (w >> 16);
         const double* y = v + (w & 0xffffu);
-#if OKIN_FMA_CHAIN
         const double y0 = y[0], y1 = y[1], y2 = y[2];
-        t0 = fma(-B[0], y0, t0); t1 = fma(-B[3], y0, t1); t2 = fma(-B[6], y0, t2);
-        t0 = fma(-B[1], y1, t0); t1 = fma(-B[4], y1, t1); t2 = fma(-B[7], y1, t2);
-        t0 = fma(-B[2], y2, t0); t1 = fma(-B[5], y2, t1); t2 = fma(-B[8], y2, t2);
-#else
-        t0 -= B[0] * y[0] + B[1] * y[1] + B[2] * y[2];
-        t1 -= B[3] * y[0] + B[4] * y[1] + B[5] * y[2];
-        t2 -= B[6] * y[0] + B[7] * y[1] + B[8] * y[2];
-#endif
+        const double b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4], b5 = B[5], b6 = B[6], b7 = B[7], b8 = B[8];
+        t0 = fma(-b0, y0, t0); t1 = fma(-b3, y0, t1); t2 = fma(-b6, y0, t2);
+        t0 = fma(-b1, y1, t0); t1 = fma(-b4, y1, t1); t2 = fma(-b7, y1, t2);
+        t0 = fma(-b2, y2, t0); t1 = fma(-b5, y2, t1); t2 = fma(-b8, y2, t2);
       }
-#endif
-      t0 += s0; t1 += s1; t2 += s2;
       const double* f = sm + OKIN_LDG(doffs + j);
       const double y0 = t0 * f[6];
       const double y1 = (t1 - f[1] * y0) * f[7];
@@ -923,41 +839,18 @@ OKIN_FN void okin_solve(const OkinProgram& pr, double* sm, int first, int nrhs, 
     for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
       const int j = OKIN_LDG(lcol + cb + t / nrhs);
       double* v = vec + (t % nrhs) * n;
-      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2], s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#if OKIN_PAIR_LOOPS
-      for (int q = OKIN_LDG(bptr + j), e = OKIN_LDG(bptr + j + 1); q < e; q += 2) {
-        const OkinPair w = okin_pair(bcon + q);
-        const double* B = Lb + (w.x >> 16);
-        const double* x = v + (w.x & 0xffffu);
-        const double* C = Lb + (w.y >> 16);
-        const double* z = v + (w.y & 0xffffu);
-        const double x0 = x[0], x1 = x[1], x2 = x[2], z0 = z[0], z1 = z[1], z2 = z[2];
-        t0 = fma(-B[0], x0, t0); t1 = fma(-B[1], x0, t1); t2 = fma(-B[2], x0, t2);
-        s0 = fma(-C[0], z0, s0); s1 = fma(-C[1], z0, s1); s2 = fma(-C[2], z0, s2);
-        t0 = fma(-B[3], x1, t0); t1 = fma(-B[4], x1, t1); t2 = fma(-B[5], x1, t2);
-        s0 = fma(-C[3], z1, s0); s1 = fma(-C[4], z1, s1); s2 = fma(-C[5], z1, s2);
-        t0 = fma(-B[6], x2, t0); t1 = fma(-B[7], x2, t1); t2 = fma(-B[8], x2, t2);
-        s0 = fma(-C[6], z2, s0); s1 = fma(-C[7], z2, s1); s2 = fma(-C[8], z2, s2);
-      }
-#else
+      double t0 = v[3 * j], t1 = v[3 * j + 1], t2 = v[3 * j + 2];
       OKIN_UNROLL_INNER
       for (int q = OKIN_LDG(bptr + j); q < OKIN_LDG(bptr + j + 1); ++q) {
         const uint32_t w = (uint32_t)OKIN_LDG(bcon + q);
         const double* B = Lb + (w >> 16);
         const double* x = v + (w & 0xffffu);
-#if OKIN_FMA_CHAIN
         const double x0 = x[0], x1 = x[1], x2 = x[2];
-        t0 = fma(-B[0], x0, t0); t1 = fma(-B[1], x0, t1); t2 = fma(-B[2], x0, t2);
-        t0 = fma(-B[3], x1, t0); t1 = fma(-B[4], x1, t1); t2 = fma(-B[5], x1, t2);
-        t0 = fma(-B[6], x2, t0); t1 = fma(-B[7], x2, t1); t2 = fma(-B[8], x2, t2);
-#else
-        t0 -= B[0] * x[0] + B[3] * x[1] + B[6] * x[2];
-        t1 -= B[1] * x[0] + B[4] * x[1] + B[7] * x[2];
-        t2 -= B[2] * x[0] + B[5] * x[1] + B[8] * x[2];
-#endif
+        const double b0 = B[0], b1 = B[1], b2 = B[2], b3 = B[3], b4 = B[4], b5 = B[5], b6 = B[6], b7 = B[7], b8 = B[8];
+        t0 = fma(-b0, x0, t0); t1 = fma(-b1, x0, t1); t2 = fma(-b2, x0, t2);
+        t0 = fma(-b3, x1, t0); t1 = fma(-b4, x1, t1); t2 = fma(-b5, x1, t2);
+        t0 = fma(-b6, x2, t0); t1 = fma(-b7, x2, t1); t2 = fma(-b8, x2, t2);
       }
-#endif
-      t0 += s0; t1 += s1; t2 += s2;
       const double* f = sm + OKIN_LDG(doffs + j);
       const double x2 = t2 * f[8];
       const double x1 = (t1 - f[4] * x2) * f[7];
@@ -1191,7 +1084,7 @@ OKIN_HD void okin_point_vel_base(const OkinProgram& pr, const double* sm, int p,
   sm = OKIN_SHARED(sm);
   v[0] = v[1] = v[2] = 0.0;
   if (p < 0) return;
-  const int e = OKIN_LDG(okin_sec(pr, OKIN_S_POINT_ELIM) + p);
+  const int e = OKIN_LDG(OKIN_SHARED(okin_sec(pr, OKIN_S_POINT_ELIM)) + p);
   if (e < 0) return;
   const double* V = sm + pr.hdr[OKIN_H_OFF_VEC] + (1 + j) * 3 * pr.hdr[OKIN_H_NF] + 3 * e;
   v[0] = V[0]; v[1] = V[1]; v[2] = V[2];
@@ -1209,7 +1102,7 @@ OKIN_HD void okin_point_vel_op(const OkinProgram& pr, const double* sm, int d, c
 }
 OKIN_HD void okin_point_vel1(const OkinProgram& pr, const double* sm, int p, int j, double v[3]) {
   sm = OKIN_SHARED(sm);
-  const int d = p < 0 ? -1 : OKIN_LDG(okin_sec(pr, OKIN_S_POINT_DOP) + p);
+  const int d = p < 0 ? -1 : OKIN_LDG(OKIN_SHARED(okin_sec(pr, OKIN_S_POINT_DOP)) + p);
   if (d < 0) { okin_point_vel_base(pr, sm, p, j, v); return; }
   const int32_t* rec = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP)) + d * OKIN_DOP_STRIDE;
   double da[3], db[3], dc[3];
@@ -1220,7 +1113,7 @@ OKIN_HD void okin_point_vel1(const OkinProgram& pr, const double* sm, int p, int
 }
 OKIN_HD void okin_point_vel(const OkinProgram& pr, const double* sm, int p, int j, double v[3]) {
   sm = OKIN_SHARED(sm);
-  const int d = p < 0 ? -1 : OKIN_LDG(okin_sec(pr, OKIN_S_POINT_DOP) + p);
+  const int d = p < 0 ? -1 : OKIN_LDG(OKIN_SHARED(okin_sec(pr, OKIN_S_POINT_DOP)) + p);
   if (d < 0) { okin_point_vel_base(pr, sm, p, j, v); return; }
   const int32_t* rec = OKIN_SHARED(okin_sec(pr, OKIN_S_DOP)) + d * OKIN_DOP_STRIDE;
   double da[3], db[3], dc[3];
@@ -1418,8 +1311,8 @@ OKIN_FN void okin_metrics(const OkinProgram& pr, double* sm, double* out) {
   sm = OKIN_SHARED(sm);
   const int32_t* hdr = OKIN_SHARED(pr.hdr);
   const int nmc = hdr[OKIN_H_NMC], nmop = hdr[OKIN_H_NMOP];
-  const int32_t* corners = okin_sec(pr, OKIN_S_MCORNER);
-  const int32_t* mops = okin_sec(pr, OKIN_S_MOP);
+  const int32_t* corners = OKIN_SHARED(okin_sec(pr, OKIN_S_MCORNER));
+  const int32_t* mops = OKIN_SHARED(okin_sec(pr, OKIN_S_MOP));
   double* ctx = sm + hdr[OKIN_H_OFF_MCTX];
   const int nt = hdr[OKIN_H_NT];
   OKIN_PHASE_BEGIN
@@ -1458,7 +1351,7 @@ OKIN_FN void okin_metrics(const OkinProgram& pr, double* sm, double* out) {
   OKIN_PHASE_END
   if (hdr[OKIN_H_NMAXLE]) {
     // axle-level state metrics (axle_metrics.py:18-95)
-    const int32_t* rec = okin_sec(pr, OKIN_S_MAXLE);
+    const int32_t* rec = OKIN_SHARED(okin_sec(pr, OKIN_S_MAXLE));
     const double* pos = sm + hdr[OKIN_H_OFF_POS];
     const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
     OKIN_PHASE_BEGIN

@@ -128,7 +128,6 @@ enum okin_hdr_slot {
   OKIN_H_NDIAG,    // diagnostic columns per state (OKIN_DIAG_BASE + topology columns), 0 = no program
   OKIN_H_NDGOP,    // topology diagnostic ops
   OKIN_H_FREE_ALL_OUT,  // 1 when every free point is an output point (ELIM_OUT has no -1)
-  OKIN_H_OFF_ZERO,   // 9 doubles kept at zero: operands of the null contributions that pad gather lists
   OKIN_H_OFF_XPREV,  // previous accepted solution (3*NF doubles, elimination order)
   OKIN_H_OFF_DHIST,  // three older solution increments as float32 vectors (extrapolation predictor)
   OKIN_H_SMEM_DOUBLES_LEAN,  // slice size of an instance solved without tangents / metrics / diagnostics
@@ -174,6 +173,13 @@ enum okin_isec {
   OKIN_S_DIAG_OFF,       // [NF] shared-memory offset of the diagonal block of elimination column j
   OKIN_S_ROW_HOT,        // [NGROW][OKIN_ROW_STRIDE] records of the generic-path rows in evaluation order
                          // (grouped by family), each carrying its row index in OKIN_R_ROWID
+  // metric program and the point maps its velocity look-ups walk: read once per state by the
+  // full-output kernels (pointer chasing through global memory cost more than the solve itself)
+  OKIN_S_POINT_ELIM,     // [P] elimination position of a free point, else -1
+  OKIN_S_POINT_DOP,      // [P] derived-op index of a derived point, else -1
+  OKIN_S_MCORNER,        // [NMC][OKIN_MCORNER_STRIDE]
+  OKIN_S_MOP,            // [NMOP][OKIN_MOP_STRIDE]
+  OKIN_S_MAXLE,          // [NMAXLE][OKIN_MAXLE_STRIDE]
   // cold sections (index >= OKIN_S_COLD0): set-up rules, outputs requested per state, metrics,
   // diagnostics, shims; they stay in global memory
   OKIN_S_COLD0,
@@ -183,11 +189,6 @@ enum okin_isec {
   OKIN_S_PAR_MODE,       // [NPAR]
   OKIN_S_POINT_KIND, // [P]
   OKIN_S_DESIGN_PT,      // [NDSN] points whose design position is kept for the metrics
-  OKIN_S_POINT_ELIM,     // [P] elimination position of a free point, else -1
-  OKIN_S_POINT_DOP,      // [P] derived-op index of a derived point, else -1
-  OKIN_S_MCORNER,        // [NMC][OKIN_MCORNER_STRIDE]
-  OKIN_S_MOP,            // [NMOP][OKIN_MOP_STRIDE]
-  OKIN_S_MAXLE,          // [NMAXLE][OKIN_MAXLE_STRIDE]
   OKIN_S_SHIM,           // [NSHIM][OKIN_SHIM_STRIDE]
   OKIN_S_SHIM_PTS,       // point lists referenced by SHIM (upright attachments, rocker group)
   OKIN_S_FREE_OUT,       // [NF] output slot of free point k (reference column order), -1 = not exported

@@ -25,7 +25,7 @@ def metric_tolerances(names):
         if base.startswith("deriv_"):
             tol.append(("rel", 2e-7))
         elif base in angle:
-            tol.append(("abs", max(ANGLE_TOL_DEG, 1e-9) if base != "svsa_angle" else 1e-7))
+            tol.append(("abs", ANGLE_TOL_DEG))          # every angle column, svsa_angle included (measured ~1e-13 rad)
         elif base.startswith(ic):
             tol.append(("rel", 1e-6))     # never tighter than the 1e-6 mm position bar it is built from
         else:

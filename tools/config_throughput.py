@@ -89,7 +89,8 @@ def run(label, sus, sweep, n, sigma, metrics=False, shim_mc=False):
     ok = st == 0
     rec = {"config": label, "instances": n, "steps": S, "n_unknowns": prog.n_unknowns, "metrics": bool(metrics),
            "states_per_s": n * S / (ms * 1e-3), "ms_per_launch": ms, "ok_fraction": float(ok.double().mean()),
-           "mean_nfev": float(it[ok].double().mean()), "launch": solver.topology.launch_geometry(n)}
+           "mean_nfev": float(it[ok].double().mean()), "launch": solver.topology.launch_geometry(n),
+           "lean_family": solver.topology.lean_calibration(0)}
     print(json.dumps(rec), flush=True)
     solver.close()
     return rec
