@@ -447,7 +447,10 @@ def run_cuda(args) -> None:
     import psutil
     avail = psutil.virtual_memory().available
     bytes_per_inst_out = S * nout3 * 8 + S * 12 + 8
-    e2e_inst = int(min(n_inst * n_dev, max(4096, min(30e9 * n_dev, 0.25 * avail / max(world, 1)) // bytes_per_inst_out)))
+    budget = min(30e9 * n_dev, 0.25 * avail / max(world, 1))
+    if single:
+        budget = min(budget, 64e9)          # one process page-locks every buffer itself: keep that bounded
+    e2e_inst = int(min(n_inst * n_dev, max(4096, budget // bytes_per_inst_out)))
     host_hp = solver.pinned_hardpoints(e2e_inst, devices[0])
     per = (e2e_inst + n_dev - 1) // n_dev
     for k, index in enumerate(devices):
