@@ -500,7 +500,7 @@ def run_cuda(args) -> None:
         head = variants["all_points"]
         peak = ctypes.c_double(0.0)
         _lib.check(lib.okin_fp64_peak(local, ctypes.byref(peak)), "okin_fp64_peak")
-        model_flops_state = algorithmic_flops_per_state(prog.stats, mean_iters, nt)
+        model_flops_state = algorithmic_flops_per_state(prog.stats, mean_iters, 0)   # lean kernel: no tangent solves
         k_ms = float(np.mean(kernel_ms))
         executed, flops_src = None, None
         try:

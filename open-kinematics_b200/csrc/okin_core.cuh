@@ -648,7 +648,7 @@ OKIN_FN_HOT void okin_assemble(const OkinProgram& pr, double* sm, double mu, boo
   const double* r = sm + hdr[OKIN_H_OFF_R];
   double* Lb = sm + hdr[OKIN_H_OFF_LB];
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
-  const double damp = 1.0 + mu;
+  const double damp = 1.0 + mu, lev = mu * 1e-9;
   OKIN_PHASE_BEGIN
   for (int t = (g_only ? nat : 0) + lane; t < nat + nf; t += 32) {
     if (t < nat) {
@@ -668,7 +668,10 @@ OKIN_FN_HOT void okin_assemble(const OkinProgram& pr, double* sm, double mu, boo
         a20 = fma(x2, y0, a20); a21 = fma(x2, y1, a21); a22 = fma(x2, y2, a22);
       }
       const int task = OKIN_LDG(atask + t);
-      if (task & OKIN_ASM_DIAG) { a00 *= damp; a11 *= damp; a22 *= damp; }
+      // Marquardt scaling plus a small Levenberg shift: a row whose gradient vanishes at the current
+      // point (a spherical joint that is exactly closed) leaves a zero diagonal that scaling alone never
+      // makes positive; MINPACK substitutes 1 for a zero column norm there (lmder, diag(j) = 1).
+      if (task & OKIN_ASM_DIAG) { a00 = a00 * damp + lev; a11 = a11 * damp + lev; a22 = a22 * damp + lev; }
       double* dst = Lb + 9 * (task & 0xffff);
       dst[0] = a00; dst[1] = a01; dst[2] = a02; dst[3] = a10; dst[4] = a11; dst[5] = a12;
       dst[6] = a20; dst[7] = a21; dst[8] = a22;

@@ -508,6 +508,35 @@ def run_generic() -> None:
     print("generic mechanism:", len(states), "states, max residual", max(s.max_residual for s in stats))
 
 
+def run_generic_parallel_spherical() -> None:
+    """The two generic families no other golden exercises in a solve: a parallelogram A-B-C-D in the XZ
+    plane whose sides AB and DC are kept parallel by VectorsParallelConstraint, and a point E tied to C
+    by a SphericalJointConstraint (one scalar row whose gradient vanishes when the joint is closed)."""
+    from kinematics.core.state import SuspensionState
+    from kinematics.core.points.derived.manager import DerivedPointsSpec
+    from kinematics.core.targeting import PointTarget, PointTargetAxis, SweepConfig
+    from kinematics.core.enums import TargetPositionMode
+    a, d, b, c, e = (PointID.LOWER_WISHBONE_INBOARD_FRONT, PointID.UPPER_WISHBONE_INBOARD_FRONT,
+                     PointID.LOWER_WISHBONE_OUTBOARD, PointID.UPPER_WISHBONE_OUTBOARD, PointID.WHEEL_CENTER)
+    pts = {a: [0, 0, 0], d: [100, 0, 0], b: [0, 0, 100], c: [100, 0, 100], e: [100, 0, 100]}
+    state = SuspensionState(positions={k: Point3(np.array(v, float)) for k, v in pts.items()}, free_points={b, c, e})
+    y0 = (Point3(np.zeros(3)), Direction3(np.array([0.0, 1.0, 0.0])))
+    cons = [C.DistanceConstraint(a, b, 100.0), C.DistanceConstraint(b, c, 100.0), C.DistanceConstraint(d, c, 100.0),
+            C.VectorsParallelConstraint(a, b, d, c), C.PointOnPlaneConstraint(b, *y0), C.PointOnPlaneConstraint(c, *y0),
+            C.SphericalJointConstraint(c, e), C.FixedAxisConstraint(e, Axis.Y, 0.0), C.DistanceConstraint(d, e, 100.0)]
+    values = np.linspace(0.0, 30.0, 7).tolist()
+    sweep = SweepConfig([[PointTarget(b, PointTargetAxis(Axis.X), v, TargetPositionMode.RELATIVE) for v in values]])
+    dm = DerivedPointsManager(DerivedPointsSpec(functions={}, dependencies={}))
+    states, stats = solve_suspension_sweep(state, cons, sweep, dm, TIGHT)
+    keys = sorted(state.positions)
+    np.savez_compressed(os.path.join(OUT, "generic_parallel_spherical.npz"), positions_tight=positions_array(states, keys),
+                        max_residual=np.array([s.max_residual for s in stats]), values=np.array(values))
+    json.dump({"point_keys": [key_name(k) for k in keys], "free": [key_name(k) for k in (b, c, e)]},
+              open(os.path.join(OUT, "generic_parallel_spherical.json"), "w"), indent=1)
+    print("generic parallel + spherical:", len(states), "states, max residual", max(s.max_residual for s in stats),
+          "joint gap", float(np.linalg.norm(states[-1].positions[c].data - states[-1].positions[e].data)))
+
+
 # --------------------------------------------------------------------------- result files
 def run_result_files() -> None:
     """The reference's own sweep file for the C1 case (cli/commands/sweep.py:39-79 -> CSV, format
@@ -571,5 +600,7 @@ if __name__ == "__main__":
         run_diagnostics()
     if not only or "generic" in only:
         run_generic()
+    if not only or "generic2" in only:
+        run_generic_parallel_spherical()
     if not only or "results" in only:
         run_result_files()

@@ -68,3 +68,7 @@ def test_per_instance_target_tables(emu_device):
 
 def test_worst_residual_row_is_reported(emu_device):
     G.test_worst_residual_row_is_reported()
+
+
+def test_vectors_parallel_and_spherical_families(emu_device):
+    G.test_vectors_parallel_and_spherical_families_solve_like_the_reference()

@@ -736,3 +736,40 @@ def test_worst_residual_row_is_reported():
         assert ok.status[0] == 0 and ok.worst_row[0] == -1
     finally:
         solver.close()
+
+
+def test_vectors_parallel_and_spherical_families_solve_like_the_reference():
+    """The two generic families no shipped topology and no other golden uses in a solve
+    (VectorsParallelConstraint, SphericalJointConstraint; reference core/constraints.py:137-200,
+    :311-400) through boundary B1, against the reference's tight run of the same linkage
+    (tests/golden/generic_parallel_spherical.*).  The closed spherical joint is a row whose gradient
+    vanishes at the solution: positions of the joint's free end are determined to second order only,
+    so it is checked through the joint gap; everything else at the position bar."""
+    from open_kinematics_b200.core import constraints as PC
+    from open_kinematics_b200.core.enums import Axis, PointID as P, TargetPositionMode
+    from open_kinematics_b200.core.points.derived.manager import DerivedPointsManager, DerivedPointsSpec
+    from open_kinematics_b200.core.primitives.geometry import Direction3, Point3
+    from open_kinematics_b200.core.solver import solve_suspension_sweep
+    from open_kinematics_b200.core.state import SuspensionState
+    from open_kinematics_b200.core.targeting import PointTarget, PointTargetAxis, SweepConfig
+    meta = json.load(open(os.path.join(GOLDEN, "generic_parallel_spherical.json")))
+    arr = np.load(os.path.join(GOLDEN, "generic_parallel_spherical.npz"))
+    a, d, b, c, e = (P.LOWER_WISHBONE_INBOARD_FRONT, P.UPPER_WISHBONE_INBOARD_FRONT, P.LOWER_WISHBONE_OUTBOARD,
+                     P.UPPER_WISHBONE_OUTBOARD, P.WHEEL_CENTER)
+    pts = {a: [0, 0, 0], d: [100, 0, 0], b: [0, 0, 100], c: [100, 0, 100], e: [100, 0, 100]}
+    state = SuspensionState(positions={k: Point3(np.array(v, float)) for k, v in pts.items()}, free_points={b, c, e})
+    y0 = (Point3(np.zeros(3)), Direction3(np.array([0.0, 1.0, 0.0])))
+    cons = [PC.DistanceConstraint(a, b, 100.0), PC.DistanceConstraint(b, c, 100.0), PC.DistanceConstraint(d, c, 100.0),
+            PC.VectorsParallelConstraint(a, b, d, c), PC.PointOnPlaneConstraint(b, *y0), PC.PointOnPlaneConstraint(c, *y0),
+            PC.SphericalJointConstraint(c, e), PC.FixedAxisConstraint(e, Axis.Y, 0.0), PC.DistanceConstraint(d, e, 100.0)]
+    sweep = SweepConfig([[PointTarget(b, PointTargetAxis(Axis.X), float(v), TargetPositionMode.RELATIVE)
+                          for v in arr["values"]]])
+    manager = DerivedPointsManager(DerivedPointsSpec(functions={}, dependencies={}))
+    states, stats = solve_suspension_sweep(state, cons, sweep, manager)
+    assert len(states) == len(arr["values"]) and all(s.converged and s.max_residual <= 1e-3 for s in stats)
+    keys = [key_from_name(n) for n in meta["point_keys"]]
+    got = np.array([[st.positions[k].data for k in keys] for st in states])
+    firm = [i for i, k in enumerate(keys) if k != e]
+    assert np.abs(got[:, firm] - arr["positions_tight"][:, firm]).max() <= POS_TOL_MM
+    gap = np.linalg.norm(got[:, keys.index(e)] - got[:, keys.index(c)], axis=1)
+    assert gap.max() <= 1e-4, gap       # the reference accepts any gap below ~4.5e-5 mm (softnorm, tolerance 1e-3)

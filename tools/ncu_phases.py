@@ -19,7 +19,7 @@ def main():
     core = open(__file__.replace("tools/ncu_phases.py", "open-kinematics_b200/csrc/okin_core.cuh")).read().split("\n")
     starts = []
     for i, line in enumerate(core, 1):
-        m = re.match(r"OKIN_(?:FN|HD) \w[\w\s\*]*?\b(okin_\w+)\(", line)
+        m = re.match(r"OKIN_(?:FN_HOT|FN|HD) \w[\w\s\*]*?\b(okin_\w+)\(", line)
         if m:
             starts.append((i, m.group(1)))
 
