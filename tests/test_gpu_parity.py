@@ -773,3 +773,36 @@ def test_vectors_parallel_and_spherical_families_solve_like_the_reference():
     assert np.abs(got[:, firm] - arr["positions_tight"][:, firm]).max() <= POS_TOL_MM
     gap = np.linalg.norm(got[:, keys.index(e)] - got[:, keys.index(c)], axis=1)
     assert gap.max() <= 1e-4, gap       # the reference accepts any gap below ~4.5e-5 mm (softnorm, tolerance 1e-3)
+
+
+def test_lean_kernel_families_are_bit_identical_and_calibrated(monkeypatch):
+    """The lean kernel exists in a 128- and a 168-register family (same source; csrc/okin_abi.cu); the
+    first large batch of a topology times both and keeps the faster.  Pinned to either family
+    (OKIN_LEAN_REGS, read when the topology is made resident) the results are bit-identical, and a
+    calibrated solver reports which family it chose."""
+    from open_kinematics_b200.core.sweep import BatchSolver
+    meta, _ = load_golden("c3_rocker_ubar_coilover_roll")
+    sus, sweep = build_case(meta)
+    results = {}
+    hp = None
+    for regs in ("128", "168", None):
+        if regs is None:
+            monkeypatch.delenv("OKIN_LEAN_REGS", raising=False)
+        else:
+            monkeypatch.setenv("OKIN_LEAN_REGS", regs)
+        solver = BatchSolver(sus, sweep)
+        try:
+            if hp is None:
+                hp = _perturbed(solver, 40000, seed=9)
+            results[regs] = solver.solve(hp)
+            cal = solver.topology.lean_calibration(0)
+            if regs is None:
+                assert cal["registers"] in (128, 168) and cal["ms_128"] > 0.0 and cal["ms_168"] > 0.0
+            else:
+                assert cal["registers"] == int(regs)
+        finally:
+            solver.close()
+    for other in ("168", None):
+        assert np.array_equal(results["128"].positions, results[other].positions, equal_nan=True)
+        assert np.array_equal(results["128"].nfev, results[other].nfev)
+        assert np.array_equal(results["128"].status, results[other].status)

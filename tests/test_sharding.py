@@ -64,7 +64,8 @@ def test_committed_bench_lines_follow_the_contract():
     to bench.py that drops one shows up here, without a GPU)."""
     import json
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for name in ("r01_bench_1gpu.json", "r01_bench_8gpu.json"):
+    for name in ("r01_bench_1gpu.json", "r01_bench_8gpu.json", "r02_bench_1gpu.json", "r02_bench_8gpu.json",
+                 "r02_bench_8gpu_single_process.json"):
         line = json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
         for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                     "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks",
@@ -77,7 +78,14 @@ def test_committed_bench_lines_follow_the_contract():
         assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
         assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
         assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
-        assert abs(line["value"] - line["n_gpus"] * line["config"]["instances_per_gpu"] * line["config"]["sweep_steps"]
-                   / (line["ms_per_step"] * 1e-3)) <= 1e-6 * line["value"]
+        accepted = line["config"].get("accepted_state_fraction", 1.0)      # round 2: only accepted states count
+        assert abs(line["value"] - accepted * line["n_gpus"] * line["config"]["instances_per_gpu"]
+                   * line["config"]["sweep_steps"] / (line["ms_per_step"] * 1e-3)) <= 1e-6 * line["value"]
+        if name.startswith("r02"):
+            assert line["config"]["parity_max_mm"] <= 1e-6 and line["config"]["parity_flags_identical"]
+            assert set(line["e2e"]["variants"]) >= {"all_points", "metrics_only"}
+            assert line["e2e"]["value"] == line["e2e"]["variants"]["all_points"]["value"]
     ref = json.loads(open(os.path.join(root, "profiles", "r01_bench_reference_arm.json")).read().strip().splitlines()[-1])
     assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "port"
+    ref2 = json.loads(open(os.path.join(root, "profiles", "r02_bench_reference_arm.json")).read().strip().splitlines()[-1])
+    assert ref2["impl"] == "reference" and ref2["cpu_baseline"]["kind"] == "reference" and ref2["gpu_launches"] == 0
