@@ -575,6 +575,24 @@ def compile_topology(
         g_con.extend(per_block.get(j, []))
         g_ptr.append(len(g_con))
 
+    # ---- row-wise Jacobian lists (r + J h of the linear model, okin_linear_residuals) ------------
+    # per least-squares row: (rg offset of its gradient w.r.t. one effective block) << 16 | 3 * that
+    # block's elimination position, same sign convention as the assembly words
+    jh_ptr, jh_con = [0], []
+    for row in ls_rows:
+        for e, cblk in enumerate(row.eff):
+            off_e, neg = row.grad_ref(e)
+            jh_con.append((off_e << 16) | (3 * pos_of[cblk]) | (D["OKIN_CON_NEG"] if neg else 0))
+        jh_ptr.append(len(jh_con))
+    # report rows (original point-on-line residuals) as softnorm of their two pin rows
+    pin_row = {}
+    for i, row in enumerate(ls_rows):
+        if row.source[0] == "pin":
+            pin_row[(row.source[1], row.source[2])] = i
+    rep_pins = []
+    for row in report_rows:
+        rep_pins += [pin_row[(row.source[1], 0)], pin_row[(row.source[1], 1)]]
+
     # ---- left-looking update lists, scale tasks -------------------------------
     # One task per block *row* (3 entries): acc[c] -= a . B[c][:] for every earlier column K,
     # a = row r of L_iK, B = L_jK.  The right-hand side of the step equation is carried as one
@@ -808,6 +826,7 @@ def compile_topology(
         "OKIN_S_ASM_PTR": asm_ptr, "OKIN_S_ASM_TASK": asm_task, "OKIN_S_ASM_CON": asm_con,
         "OKIN_S_G_PTR": g_ptr, "OKIN_S_G_CON": g_con,
         "OKIN_S_LEV_UPD_MID": lev_upd_mid, "OKIN_S_LEV_SCL_MID": lev_scl_mid,
+        "OKIN_S_JH_PTR": jh_ptr, "OKIN_S_JH_CON": jh_con, "OKIN_S_REP_PINS": rep_pins,
         "OKIN_S_LEV_UPD": lev_upd, "OKIN_S_UPD_DST": upd_dst, "OKIN_S_UPD_PTR": upd_ptr, "OKIN_S_UPD_CON": upd_con,
         "OKIN_S_LEV_SCL": lev_scl, "OKIN_S_SCL": scl,
         "OKIN_S_LEV_COL_PTR": lev_col_ptr, "OKIN_S_LEV_COL": lev_col,

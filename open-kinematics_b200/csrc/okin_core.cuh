@@ -983,6 +983,76 @@ OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
   OKIN_PHASE_END
 }
 
+// Residuals of the linear model at the step just taken: r <- r + J h (J = the row gradients of the
+// linearisation the step came from, h = vec[0]); report rows from their two pins.  For a final step
+// |h| <= fine_tol this differs from the residuals at the new point by the second-order term
+// (curvature x |h|^2, ~1e-10 mm), so the lean kernel reports it as max|r| instead of paying a second
+// row evaluation per state.  Sets st.f2 / st.rmax like okin_eval_rows.
+template <typename Dummy = void>
+OKIN_FN void okin_linear_residuals(const OkinProgram& pr, double* sm, OkinState& st) {
+  sm = OKIN_SHARED(sm);
+  const int32_t* hdr = OKIN_SHARED(pr.hdr);
+  const int nls = hdr[OKIN_H_NROW], nrep = hdr[OKIN_H_NREP];
+  const int32_t* jptr = OKIN_SHARED(okin_sec(pr, OKIN_S_JH_PTR));
+  const int32_t* jcon = OKIN_SHARED(okin_sec(pr, OKIN_S_JH_CON));
+  const int32_t* rpin = OKIN_SHARED(okin_sec(pr, OKIN_S_REP_PINS));
+  const double* rg = sm + hdr[OKIN_H_OFF_RG];
+  const double* h = sm + hdr[OKIN_H_OFF_VEC];
+  double* r = sm + hdr[OKIN_H_OFF_R];
+  double* red = sm + hdr[OKIN_H_OFF_RED];
+  double sq = 0.0, mx = 0.0;
+  OKIN_PHASE_BEGIN
+  for (int t = lane; t < nls; t += 32) {
+    double acc = r[t];
+    for (int q = OKIN_LDG(jptr + t), e = OKIN_LDG(jptr + t + 1); q < e; ++q) {
+      const uint32_t w = (uint32_t)OKIN_LDG(jcon + q);
+      const double* g = rg + ((w >> 16) & 0x7fffu);
+      const double* x = h + (w & 0xffffu);
+      const double g0 = g[0], g1 = g[1], g2 = g[2], x0 = x[0], x1 = x[1], x2 = x[2];
+      const double dot = fma(g0, x0, fma(g1, x1, g2 * x2));
+      acc += (w & OKIN_CON_NEG) ? -dot : dot;
+    }
+    r[t] = acc;
+  }
+  OKIN_PHASE_END
+  OKIN_PHASE_BEGIN
+  double lsq = 0.0, lmx = 0.0;
+  for (int t = lane; t < nls; t += 32) {
+    const double v = r[t], a = fabs(v);
+    lsq += v * v;
+    lmx = (a > lmx || a != a) ? a : lmx;
+  }
+  for (int t = lane; t < nrep; t += 32) {
+    const double p1 = r[OKIN_LDG(rpin + 2 * t)], p2 = r[OKIN_LDG(rpin + 2 * t + 1)];
+    const double v = sqrt(p1 * p1 + p2 * p2 + OKIN_EPS_SQ) - OKIN_EPS;
+    r[nls + t] = v;
+    lmx = (v > lmx || v != v) ? v : lmx;
+  }
+  red[lane] = lsq;
+  sq = lsq; mx = lmx;
+  OKIN_PHASE_END
+#if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
+  st.f2 = okin_red_sum(red);
+  for (int o = 16; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = (w > mx || w != w) ? w : mx;
+  }
+  st.rmax = mx;
+  (void)sq;
+#else
+  // lane emulation: the phase body ran once per lane; redo the reductions serially
+  double f2 = 0.0, rm = 0.0;
+  for (int t = 0; t < nls + nrep; ++t) {
+    const double a = fabs(r[t]);
+    if (t < nls) f2 += r[t] * r[t];
+    rm = (a > rm || a != a) ? a : rm;
+  }
+  st.f2 = f2;
+  st.rmax = rm;
+  (void)sq; (void)mx;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // One sweep step: Gauss-Newton on the pinned least-squares system, Marquardt damping only
 // after a step that fails to reduce ||r||^2.  A step below fine_tol ends the iteration (error
@@ -1025,6 +1095,13 @@ OKIN_HD int okin_solve_step(const OkinProgram& pr, double* sm, const double* tva
       // the solution anyway (exported tangents / metrics) and this step already ends the iteration,
       // the row gradients are evaluated in the same pass.
       const bool last = hmax <= cfg.fine_tol;
+      if (last && !relinearise) {
+        // final step of a solve that needs nothing at the solution but max|r|: residuals of the linear
+        // model instead of a second row evaluation (error of second order in hmax)
+        okin_linear_residuals(pr, sm, st);
+        *converged = true;
+        break;
+      }
       okin_eval_rows(pr, sm, tval, relinearise && last, st);
       ++nfev;
       if (last) {                                // error left ~ k hmax^2: done without verification

@@ -152,6 +152,9 @@ enum okin_isec {
   OKIN_S_G_CON,          // (irg << 16) | row: g_j += rg[irg..irg+3) * r[row]
   OKIN_S_LEV_UPD_MID,    // [NLEV] end of the level's update tasks that do not belong to tangent right-hand sides
   OKIN_S_LEV_SCL_MID,    // [NLEV] same for the scale tasks
+  OKIN_S_JH_PTR,         // [NROW+1] ranges into JH_CON: the Jacobian row of each least-squares row
+  OKIN_S_JH_CON,         // (rg offset << 16) | 3 * elimination position (| OKIN_CON_NEG): r_t += rg . h_j
+  OKIN_S_REP_PINS,       // [NREP][2] the two pin rows of each report (point-on-line) row
   OKIN_S_LEV_UPD,        // [NLEV+1] ranges into UPD_DST/UPD_PTR
   OKIN_S_UPD_DST,        // shared-memory offset of the 3-entry row being updated
   OKIN_S_UPD_PTR,        // [n_upd+1]
