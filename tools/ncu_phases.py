@@ -47,12 +47,13 @@ def main():
         if active and re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+\S", raw):
             locs.append(cur)
     rows = list(csv.reader(open(sass)))
-    agg = defaultdict(lambda: [0, 0, 0])
+    agg = defaultdict(lambda: [0, 0, 0, 0.0])
     total = [0, 0]
     kernels = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
     h = next(i for i, r in enumerate(rows) if "Address" in r and "Source" in r)
     hdr = rows[h]
     ci, si, ti = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
+    wi = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
     data = [r for r in rows[h + 1:] if len(r) == len(hdr)]
     if len(locs) != len(data):
         print(f"warning: {len(locs)} disassembled instructions vs {len(data)} profiled rows", file=sys.stderr)
@@ -60,11 +61,13 @@ def main():
         n, s, t = int(r[ci]), int(r[si]), int(r[ti])
         a = agg[region(loc)]
         a[0] += n; a[1] += s; a[2] += t
+        if wi is not None and r[wi]:
+            a[3] += float(r[wi])
         total[0] += n; total[1] += s
     print(f"warp instructions {total[0]:,} = {total[0] / states:,.0f} per state; samples {total[1]:,}")
-    for k, (n, s, t) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    for k, (n, s, t, w) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         print(f"{k:26s} {100 * n / total[0]:6.2f}% inst {100 * s / max(total[1], 1):6.2f}% smp "
-              f"{n / states:8.0f} inst/state  lanes {t / max(n, 1):5.1f}")
+              f"{n / states:8.0f} inst/state  lanes {t / max(n, 1):5.1f}  smem wavefronts/state {w / states:7.0f}")
 
 
 if __name__ == "__main__":
