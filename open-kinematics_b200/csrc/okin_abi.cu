@@ -1,14 +1,15 @@
 // C ABI (include/okin.h) and the sm_100a kernels behind it.
 //
-// Kernel mapping: one warp per suspension instance, W instances per CTA (W chosen per topology by
-// ensure_device), each warp working in its own slice of dynamic shared memory next to one shared
-// copy of the hot topology tables; the grid is persistent (SM count x resident CTAs per SM) and
-// strides over the instance range.  The work is irregular fp64 on systems of tens of unknowns
-// (measured: shared-memory data pipe and instruction issue are the busy
-// units, profiles/), so tensor cores and TMA have nothing to act on; the only global traffic is the
-// coalesced instance-major hardpoint read and state write.  okin_sweep_kernel<FULL, SHIM> has four
-// instantiations (lean / full outputs, with / without the camber-shim pre-solve); the continuity pass
-// of the diagnostics is a second kernel on the same stream.
+// Kernel mapping: one warp per suspension instance, W instances per CTA (W chosen per topology and
+// kernel family by ensure_device), each warp working in its own slice of dynamic shared memory next
+// to one shared copy of the hot topology tables; the grid is persistent (SM count x resident CTAs
+// per SM) and its warps claim instances from a global counter.  The work is irregular fp64 on
+// systems of tens of unknowns (measured: the shared-memory data pipe is the
+// binding unit, profiles/r02_d_*), so tensor cores and TMA have nothing to act on; the only global
+// traffic is the coalesced instance-major hardpoint read and state write.
+// okin_sweep_kernel<FULL, SHIM, MAX_THREADS> has six instantiations: full outputs (128 registers) and
+// two lean families (128 / 168 registers), each with / without the camber-shim pre-solve; the
+// continuity pass of the diagnostics is a second kernel on the same stream.
 #include <cuda_runtime.h>
 
 #include <pthread.h>

@@ -17,10 +17,12 @@
 //   okin_derived_*    <- DerivedPointsManager.update_in_place / compute_point_jacobian
 //                        (points/derived/manager.py:186-197, :271-324), hand-written JVPs
 //   okin_solve_step   <- least_squares(method="lm") call (solver.py:124-169, :717-724)
-//   okin_sweep        <- solve_suspension_sweep loop (solver.py:716-774)
+//   okin_sweep        <- solve_suspension_sweep loop (solver.py:716-774); okin_extrapolate is the
+//                        predicted start, okin_worst_row <- describe_worst_residual (solver.py:640-651)
 //   tangent columns   <- compute_state_tangents (sensitivity.py:57-143): right-hand sides carried through
-//                        the Cholesky factorisation (okin_tangent_rhs, okin_factor, okin_solve),
-//                        okin_point_vel for derived points, okin_tangent_health for rank / sigma_min / cond
+//                        the Cholesky factorisation of the system linearised at the solution
+//                        (okin_tangent_rhs, okin_factor, okin_solve), okin_point_vel for derived points,
+//                        okin_tangent_health for rank / sigma_min / cond
 //   okin_shim_presolve <- solve_camber_shim_assembly + application (suspensions/config/shims.py:284-501,
 //                        corner/double_wishbone.py:501-571)
 //   okin_metrics      <- Suspension.compute_state_metrics (metrics/*.py; kernels in okin_metrics.cuh)
@@ -36,7 +38,10 @@
 #include "okin_metrics.cuh"
 
 // Phase functions are kept out of line on the device: inlining all of them into the sweep loop
-// (each is called from several places) costs registers (255/thread) and instruction cache.
+// (each is called from several places) costs registers (255/thread) and instruction cache.  The
+// three gather-loop phases (assembly, factorisation, triangular solves) are the exception
+// (OKIN_FN_HOT): inlined they are scheduled with the caller's registers, +7 % on the flagship and
+// +15 % on the corner topologies (profiles/README.md, round 2).
 #if defined(__CUDACC__) && !defined(OKIN_LANE_EMU)
 #define OKIN_FN __host__ __device__ __noinline__
 #if OKIN_INLINE_HOT
