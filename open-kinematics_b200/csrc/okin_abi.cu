@@ -133,7 +133,8 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
   for (;;) {
     // wait while too far ahead of the slowest live warp (finished warps park at INT_MAX)
     for (;;) {
-      int v = (int)(threadIdx.x & 31) < warps_per_cta ? ((volatile int*)s_done)[threadIdx.x & 31] : 0x7fffffff;
+      // (progress counters are read and written with shared-memory atomics: a defined cross-warp handshake)
+      int v = (int)(threadIdx.x & 31) < warps_per_cta ? atomicOr(&s_done[threadIdx.x & 31], 0) : 0x7fffffff;
       for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
       if (mine - v < OKIN_DRIFT) break;
       __nanosleep(256);
@@ -163,9 +164,9 @@ okin_sweep_kernel(const int32_t* __restrict__ hdr, const int32_t* __restrict__ i
       __syncwarp();
     }
     ++mine;
-    if ((threadIdx.x & 31) == 0) ((volatile int*)s_done)[warp] = mine;
+    if ((threadIdx.x & 31) == 0) atomicExch(&s_done[warp], mine);
   }
-  if ((threadIdx.x & 31) == 0) ((volatile int*)s_done)[warp] = 0x7fffffff;
+  if ((threadIdx.x & 31) == 0) atomicExch(&s_done[warp], 0x7fffffff);
 }
 
 // Second pass of the sweep diagnostics: one warp per instance walks the instance's position rows
