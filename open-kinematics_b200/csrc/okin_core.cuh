@@ -33,6 +33,15 @@
 #ifndef OKIN_INLINE_HOT
 #define OKIN_INLINE_HOT 1
 #endif
+// Code footprint matters (profiles/README.md, round 2 step f): the interpreter does not fit the
+// instruction caches once the warps of a CTA are in different phases.  OKIN_COMPACT_LOOPS 1: lane-strided
+// loops (one to three rounds) are not unrolled; 2: nor are the short runtime-count loops of the row
+// evaluation.  Measured and rejected: warp reductions and sqrt / rsqrt / atan2 as calls of one shared
+// copy each (the calls spill around themselves, and local-memory traffic uses the pipe the kernel is
+// bound by).
+#ifndef OKIN_COMPACT_LOOPS
+#define OKIN_COMPACT_LOOPS 2
+#endif
 #include "okin_defs.h"
 #include "okin_gen_constraints.cuh"
 #include "okin_metrics.cuh"
@@ -86,6 +95,17 @@ extern __shared__ double okin_smem[];
 // code measured 5 % faster than the compiler's own 4x unrolling (profiles/r01_g_*).
 #ifndef OKIN_INNER_UNROLL
 #define OKIN_INNER_UNROLL 1
+#endif
+// Lane-strided loops run one to three rounds; left to itself the compiler unrolls them four times.
+#if defined(__CUDA_ARCH__) && OKIN_COMPACT_LOOPS
+#define OKIN_LANE_LOOP _Pragma("unroll 1")
+#else
+#define OKIN_LANE_LOOP
+#endif
+#if defined(__CUDA_ARCH__) && OKIN_COMPACT_LOOPS >= 2
+#define OKIN_SHORT_LOOP _Pragma("unroll 1")
+#else
+#define OKIN_SHORT_LOOP
 #endif
 #define OKIN_STR2(x) #x
 #define OKIN_STR(x) OKIN_STR2(x)
@@ -216,6 +236,7 @@ OKIN_FN void okin_derived_update(const OkinProgram& pr, double* sm, bool active_
   for (int lv = 0; lv < nlev; ++lv) {
     const int b = OKIN_LDG(lev + lv), e = OKIN_LDG(lev + lv + 1);
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int d = b + lane; d < e; d += 32) {
       const int32_t* rec = dop + d * OKIN_DOP_STRIDE;
       if (active_only && !OKIN_LDG(rec + 7)) continue;
@@ -245,6 +266,7 @@ OKIN_FN void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
   const double* par = sm + pr.hdr[OKIN_H_OFF_PAR];
   double* dblk = sm + pr.hdr[OKIN_H_OFF_DBLK];
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int t = lane; t < nad; t += 32) {
     const int32_t* rec = adj + t * OKIN_ADJ_STRIDE;
     const int base = OKIN_LDG(rec + 1), comp = OKIN_LDG(rec + 2), off = OKIN_LDG(rec + 3);
@@ -256,6 +278,7 @@ OKIN_FN void okin_derived_jacobians(const OkinProgram& pr, double* sm) {
     seed[comp] = 1.0;
     const double z[3] = {0.0, 0.0, 0.0};
     double dout[3] = {0.0, 0.0, 0.0};
+    OKIN_SHORT_LOOP
     for (int q = cb; q < ce; ++q) {
       const int32_t* op = dop + OKIN_LDG(chain + q) * OKIN_DOP_STRIDE;
       const int in[3] = {OKIN_LDG(op + 2), OKIN_LDG(op + 3), OKIN_LDG(op + 4)};
@@ -438,6 +461,7 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
   const int nin = hdr[OKIN_H_NIN];
   const int32_t* in_point = okin_sec(pr, OKIN_S_IN_POINT);
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int t = lane; t < 3 * nin; t += 32) pos[3 * OKIN_LDG(in_point + t / 3) + t % 3] = hardpoints[t];
   OKIN_PHASE_END
   if (SHIM) okin_shim_presolve(pr, sm, params ? params : okin_fsec(pr, OKIN_F_PARAM_DEFAULT), invalid);
@@ -449,6 +473,7 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
   const int32_t* par_mode = okin_sec(pr, OKIN_S_PAR_MODE);
   const double* par_val = okin_fsec(pr, OKIN_F_PAR_VAL);
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int d = lane; d < ndop; d += 32) {
     const int32_t* rec = dop + d * OKIN_DOP_STRIDE;
     const int p = OKIN_LDG(rec + 5);
@@ -472,6 +497,7 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
     const int32_t* dpt = okin_sec(pr, OKIN_S_DESIGN_PT);
     double* dsn = sm + hdr[OKIN_H_OFF_DSN];
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int t = lane; t < 3 * ndsn; t += 32) dsn[t] = pos[3 * OKIN_LDG(dpt + t / 3) + t % 3];
     OKIN_PHASE_END
   }
@@ -483,9 +509,11 @@ OKIN_FN void okin_setup(const OkinProgram& pr, double* sm, const double* __restr
   const double* cst_init = okin_fsec(pr, OKIN_F_CST_INIT);
   const int ncst = hdr[OKIN_H_NCST];
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int t = lane; t < ncst; t += 32) cst[t] = OKIN_LDG(cst_init + t);
   OKIN_PHASE_END
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int t = lane; t < nrows; t += 32) {
     const int32_t* rec = rows + t * OKIN_ROW_STRIDE;
     const int rule = OKIN_LDG(rec + OKIN_R_RULE);
@@ -554,6 +582,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   double sq = 0.0;
   // Fast path: plain distance rows (most of every shipped topology).  r = sqrt(s + eps^2) - eps - L,
   // u = (p2 - p1)/sqrt(s + eps^2) is the whole gradient (dR/dp2 = u, dR/dp1 = -u).
+  OKIN_LANE_LOOP
   for (int slot = lane; slot < ndrow; slot += 32) {
     const uint32_t pp = (uint32_t)OKIN_LDG(drow + slot), oo = (uint32_t)OKIN_LDG(drow + ndrow + slot);
     const double* a = pos + 3 * (pp & 0xffffu);
@@ -569,6 +598,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
       u[0] = dx * inv; u[1] = dy * inv; u[2] = dz * inv;
     }
   }
+  OKIN_LANE_LOOP
   for (int slot = lane; slot < ngrow; slot += 32) {
     const int32_t* rec = rows + slot * OKIN_ROW_STRIDE;
     const int t = OKIN_LDG(rec + OKIN_R_ROWID);
@@ -598,6 +628,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
       double* out = rg + OKIN_LDG(rec + OKIN_R_RG);
       const int neff = OKIN_LDG(rec + OKIN_R_NEFF);
       for (int e = 0; e < 3 * neff; ++e) out[e] = 0.0;
+      OKIN_SHORT_LOOP
       for (int s = 0; s < np; ++s) {
         const int m = OKIN_LDG(rec + OKIN_R_S0 + s);
         if (m < 0) continue;
@@ -607,6 +638,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
         } else {
           const int32_t* dd = der + (m - OKIN_SLOT_DER) * OKIN_DER_STRIDE;
           const int nd = OKIN_LDG(dd);
+          OKIN_SHORT_LOOP
           for (int q = 0; q < nd; ++q) {
             const double* B = dblk + OKIN_LDG(dd + 1 + 2 * q);
             const int e = OKIN_LDG(dd + 2 + 2 * q);
@@ -624,6 +656,7 @@ OKIN_FN void okin_eval_rows(const OkinProgram& pr, double* sm, const double* tva
   // max|r| in a second sweep over r[] so that the reduction scratch stays one value per lane
   OKIN_PHASE_BEGIN
   double mx = 0.0;
+  OKIN_LANE_LOOP
   for (int t = lane; t < nrows; t += 32) {
     const double ar = fabs(r[t]);
     mx = (ar > mx || ar != ar) ? ar : mx;
@@ -655,6 +688,7 @@ OKIN_FN_HOT void okin_assemble(const OkinProgram& pr, double* sm, double mu, boo
   double* vec = sm + hdr[OKIN_H_OFF_VEC];
   const double damp = 1.0 + mu, lev = mu * 1e-9;
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int t = (g_only ? nat : 0) + lane; t < nat + nf; t += 32) {
     if (t < nat) {
       // one 3x3 block of A: sum of outer products ga gb^T over the rows coupling the two points
@@ -755,6 +789,7 @@ OKIN_FN_HOT void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, b
     if (ue > ub) {
       OKIN_PHASE_BEGIN
       // left-looking update of one block row (or of a carried right-hand side), two contributions per trip
+      OKIN_LANE_LOOP
       for (int t = ub + lane; t < ue; t += 32) {
         const int b = OKIN_LDG(uptr + t), e = OKIN_LDG(uptr + t + 1);
         double* dst = sm + OKIN_LDG(udst + t);
@@ -778,11 +813,13 @@ OKIN_FN_HOT void okin_factor(const OkinProgram& pr, double* sm, OkinState& st, b
     // the scale tasks below and the triangular solves later read the factor instead of recomputing it.
     const int wb = OKIN_LDG(lcp + lv), we = OKIN_LDG(lcp + lv + 1);
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int c = wb + lane; c < we; c += 32)
       okin_write_diag_factor(sm, OKIN_LDG(doffs + OKIN_LDG(lcol + c)), red, lane);
     OKIN_PHASE_END
     const int sb = OKIN_LDG(lev_scl + lv), se = carry_tangents ? OKIN_LDG(lev_scl + lv + 1) : OKIN_LDG(lev_scl_mid + lv);
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int t = sb + lane; t < se; t += 32) {
       const uint32_t w = (uint32_t)OKIN_LDG(scl + t);
       const double* f = sm + (w & 0xffffu);
@@ -818,6 +855,7 @@ OKIN_FN_HOT void okin_solve(const OkinProgram& pr, double* sm, int first, int nr
   for (int lv = 0; lv < (skip_forward ? 0 : nlev); ++lv) {  // L y = b
     const int cb = OKIN_LDG(lcp + lv), ce = OKIN_LDG(lcp + lv + 1);
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
       const int j = OKIN_LDG(lcol + cb + t / nrhs);
       double* v = vec + (t % nrhs) * n;
@@ -844,6 +882,7 @@ OKIN_FN_HOT void okin_solve(const OkinProgram& pr, double* sm, int first, int nr
   for (int lv = nlev - 1; lv >= 0; --lv) {  // L^T x = y
     const int cb = OKIN_LDG(lcp + lv), ce = OKIN_LDG(lcp + lv + 1);
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int t = lane; t < (ce - cb) * nrhs; t += 32) {
       const int j = OKIN_LDG(lcol + cb + t / nrhs);
       double* v = vec + (t % nrhs) * n;
@@ -881,6 +920,7 @@ OKIN_FN double okin_apply_step(const OkinProgram& pr, double* sm, int which, dou
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   double mx = 0.0;
+  OKIN_LANE_LOOP
   for (int u = lane; u < n; u += 32) {
     const int idx = 3 * OKIN_LDG(ep + u / 3) + u % 3;
     const double x = pos[idx];
@@ -903,6 +943,7 @@ OKIN_FN void okin_restore(const OkinProgram& pr, double* sm) {
   double* pos = sm + hdr[OKIN_H_OFF_POS];
   const double* h = sm + hdr[OKIN_H_OFF_VEC];   // the step just applied (vec[0], scale 1)
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(ep + u / 3) + u % 3] -= h[u];
   OKIN_PHASE_END
 }
@@ -916,6 +957,7 @@ OKIN_FN double okin_vec_max(const OkinProgram& pr, double* sm, int which) {
   double* red = sm + pr.hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   double mx = 0.0;
+  OKIN_LANE_LOOP
   for (int u = lane; u < n; u += 32) {
     const double a = fabs(v[u]);
     mx = (a > mx || a != a) ? a : mx;
@@ -944,6 +986,7 @@ OKIN_FN void okin_extrapolate(const OkinProgram& pr, double* sm, int order) {
   float* h2 = h1 + 2 * ((n + 1) / 2);
   float* h3 = h2 + 2 * ((n + 1) / 2);
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int u = lane; u < n; u += 32) {
     const int idx = 3 * OKIN_LDG(ep + u / 3) + u % 3;
     const double x = pos[idx];
@@ -977,6 +1020,7 @@ OKIN_FN void okin_tangent_rhs(const OkinProgram& pr, double* sm) {
   const double* rg = sm + hdr[OKIN_H_OFF_RG];
   double* vec = sm + hdr[OKIN_H_OFF_VEC] + n;
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int t = lane; t < nt * n; t += 32) vec[t] = 0.0;
   OKIN_PHASE_END
   OKIN_PHASE_BEGIN
@@ -1007,6 +1051,7 @@ OKIN_FN void okin_linear_residuals(const OkinProgram& pr, double* sm, OkinState&
   double* red = sm + hdr[OKIN_H_OFF_RED];
   double sq = 0.0, mx = 0.0;
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int t = lane; t < nls; t += 32) {
     double acc = r[t];
     for (int q = OKIN_LDG(jptr + t), e = OKIN_LDG(jptr + t + 1); q < e; ++q) {
@@ -1022,11 +1067,13 @@ OKIN_FN void okin_linear_residuals(const OkinProgram& pr, double* sm, OkinState&
   OKIN_PHASE_END
   OKIN_PHASE_BEGIN
   double lsq = 0.0, lmx = 0.0;
+  OKIN_LANE_LOOP
   for (int t = lane; t < nls; t += 32) {
     const double v = r[t], a = fabs(v);
     lsq += v * v;
     lmx = (a > lmx || a != a) ? a : lmx;
   }
+  OKIN_LANE_LOOP
   for (int t = lane; t < nrep; t += 32) {
     const double p1 = r[OKIN_LDG(rpin + 2 * t)], p2 = r[OKIN_LDG(rpin + 2 * t + 1)];
     const double v = sqrt(p1 * p1 + p2 * p2 + OKIN_EPS_SQ) - OKIN_EPS;
@@ -1038,11 +1085,10 @@ OKIN_FN void okin_linear_residuals(const OkinProgram& pr, double* sm, OkinState&
   OKIN_PHASE_END
 #if defined(__CUDA_ARCH__) && !defined(OKIN_LANE_EMU)
   st.f2 = okin_red_sum(red);
-  for (int o = 16; o > 0; o >>= 1) {
-    const double w = __shfl_xor_sync(0xffffffffu, mx, o);
-    mx = (w > mx || w != w) ? w : mx;
-  }
-  st.rmax = mx;
+  OKIN_PHASE_BEGIN
+  red[lane] = mx;
+  OKIN_PHASE_END
+  st.rmax = okin_red_max(red);
   (void)sq;
 #else
   // lane emulation: the phase body ran once per lane; redo the reductions serially
@@ -1499,11 +1545,13 @@ OKIN_FN void okin_diagnostics(const OkinProgram& pr, double* sm, double* row, bo
   const double* dsn = sm + hdr[OKIN_H_OFF_DSN];
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int t = lane; t < nd; t += 32) row[t] = t == 3 ? -1.0 : (t < OKIN_DIAG_BASE || ok ? 0.0 : NAN);
   red[lane] = 0.0;
   OKIN_PHASE_END
   if (ok) {
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int t = lane; t < nop; t += 32) {
       const int32_t* rec = okin_sec(pr, OKIN_S_DGOP) + t * OKIN_DGOP_STRIDE;
       const int col = OKIN_LDG(rec + 6);
@@ -1586,6 +1634,7 @@ OKIN_HD void okin_continuity(const OkinProgram& pr, double* scratch, int stride,
   double* slots = thr + 32;
   if (jumps) {
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int t = lane; t < n_steps * nf; t += 32) jumps[t] = 0.0;
     OKIN_PHASE_END
   }
@@ -1634,6 +1683,7 @@ OKIN_HD void okin_continuity(const OkinProgram& pr, double* scratch, int stride,
     slots[lane] = (double)slot;
     OKIN_PHASE_END
     OKIN_PHASE_BEGIN     // lane = transition: fold this group of points into the step's row
+    OKIN_LANE_LOOP
     for (int t = lane; t < ntr; t += 32) {
       double* row = diag + (size_t)(t + 1) * nd;
       double count = row[1], worst = row[2], wslot = row[3], wthr = row[4];
@@ -1667,6 +1717,7 @@ OKIN_FN double okin_factor_multiply(const OkinProgram& pr, double* sm, const dou
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   double acc = 0.0;
+  OKIN_LANE_LOOP
   for (int j = lane; j < nf; j += 32) {
     const double* f = sm + OKIN_LDG(doffs + j);   // {l00,l10,l11,l20,l21,l22,...}
     const double x0 = src[3 * j], x1 = src[3 * j + 1], x2 = src[3 * j + 2];
@@ -1703,6 +1754,7 @@ OKIN_FN double okin_scale_norm2(const OkinProgram& pr, double* sm, double* v, do
   double* red = sm + pr.hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   double acc = 0.0;
+  OKIN_LANE_LOOP
   for (int u = lane; u < n; u += 32) {
     const double x = v[u] * s;
     v[u] = x;
@@ -1731,6 +1783,7 @@ OKIN_FN void okin_tangent_health(const OkinProgram& pr, double* sm, bool notpd, 
   double* z = x + n;
   double* v0 = sm + hdr[OKIN_H_OFF_VEC];
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int u = lane; u < n; u += 32) {
     // deterministic start vectors: positive for the dominant direction, signed for the weakest
     const uint32_t hsh = ((uint32_t)u + 1u) * 2654435761u;
@@ -1788,6 +1841,7 @@ OKIN_FN int okin_worst_row(const OkinProgram& pr, double* sm) {
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
   double mx = -1.0;
+  OKIN_LANE_LOOP
   for (int t = lane; t < nrows; t += 32) {
     const double ar = fabs(r[t]);
     if (ar > mx || ar != ar) mx = ar;
@@ -1797,6 +1851,7 @@ OKIN_FN int okin_worst_row(const OkinProgram& pr, double* sm) {
   const double rmax = okin_red_max(red);
   OKIN_PHASE_BEGIN
   int first = 1 << 30;
+  OKIN_LANE_LOOP
   for (int t = lane; t < nrows; t += 32) {
     const double ar = fabs(r[t]);
     if ((ar == rmax || (ar != ar && rmax != rmax)) && t < first) first = t;
@@ -1845,6 +1900,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   okin_setup<SHIM>(pr, sm, hardpoints, params, &invalid, FULL);
   if (out.design) {  // design (setup) pose of every output point
     OKIN_PHASE_BEGIN
+    OKIN_LANE_LOOP
     for (int t = lane; t < 3 * nout; t += 32) out.design[t] = pos[3 * OKIN_LDG(out_point + t / 3) + t % 3];
     OKIN_PHASE_END
   }
@@ -1858,9 +1914,11 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
   double* dt = tcur + OKIN_MAX_TARGETS;
   double* red = sm + hdr[OKIN_H_OFF_RED];
   OKIN_PHASE_BEGIN
+  OKIN_LANE_LOOP
   for (int j = lane; j < 2 * OKIN_MAX_TARGETS; j += 32) tcur[j] = 0.0;
   {   // increment history of the extrapolation predictor
     float* h = reinterpret_cast<float*>(sm + hdr[OKIN_H_OFF_DHIST]);
+    OKIN_LANE_LOOP
     for (int u = lane; u < 6 * ((n + 1) / 2); u += 32) h[u] = 0.0f;
   }
   OKIN_PHASE_END
@@ -1899,6 +1957,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
       for (int attempt = 0; attempt < 2; ++attempt) {
         if (attempt == 1) {
           OKIN_PHASE_BEGIN
+          OKIN_LANE_LOOP
           for (int u = lane; u < n; u += 32) pos[3 * OKIN_LDG(elim_point + u / 3) + u % 3] = xprev[u];
           OKIN_PHASE_END
           run = 1;
@@ -1949,6 +2008,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
     if (out.positions) {
       double* dst = out.positions + (size_t)s * 3 * nout;
       OKIN_PHASE_BEGIN
+      OKIN_LANE_LOOP
       for (int t = lane; t < 3 * nout; t += 32)
         dst[t] = ok ? pos[3 * OKIN_LDG(out_point + t / 3) + t % 3] : NAN;
       OKIN_PHASE_END
@@ -1960,6 +2020,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
         okin_metrics(pr, sm, dst);
       } else {
         OKIN_PHASE_BEGIN
+        OKIN_LANE_LOOP
         for (int t = lane; t < nm; t += 32) dst[t] = NAN;
         OKIN_PHASE_END
       }
@@ -1967,6 +2028,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
     if (FULL && o_velocities) {  // TangentField.velocities (sensitivity.py:115-141)
       double* dst = o_velocities + (size_t)s * nt * 3 * nout;
       OKIN_PHASE_BEGIN
+      OKIN_LANE_LOOP
       for (int t = lane; t < nt * nout; t += 32) {
         double v[3] = {NAN, NAN, NAN};
         if (ok) okin_point_vel(pr, sm, OKIN_LDG(out_point + t % nout), t / nout, v);
@@ -1977,6 +2039,7 @@ OKIN_HD void okin_sweep(const OkinProgram& pr, double* sm, const double* __restr
     if (FULL && o_tangents) {
       double* dst = o_tangents + (size_t)s * nt * n;
       OKIN_PHASE_BEGIN
+      OKIN_LANE_LOOP
       for (int t = lane; t < nt * n; t += 32) {
         const int j = t / n, u = t % n;  // u: elimination-ordered unknown
         dst[j * n + 3 * OKIN_LDG(ecol + u / 3) + u % 3] = ok ? vec[n + j * n + u] : NAN;
